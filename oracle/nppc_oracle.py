@@ -1,0 +1,431 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement ("oracle") of the reference's NPPC-over-FullSubNet+ hot path.
+
+This file is the *checker*, never the product: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / `--impl reference` leg may import it.  The product path (generative-audio_b200/) runs
+hand-written sm_100a CUDA and fails loudly when its shared library is missing.
+
+Parity pinning: the reference has NO tests, golden vectors or known-answer fixtures for this path
+ — "parity unpinned" by the reference's own tests.  This restatement is therefore
+pinned against OUTPUTS OF THE REFERENCE ITSELF, run in the dev container by oracle/make_golden.py
+(which imports the unmodified reference from /root/reference through oracle/ref_loader.py) and committed
+under tests/golden/.  tests/test_oracle_vs_golden.py re-checks that pin on every run.
+
+Every function is written from the reference's *behaviour* (no code copied) and cites the reference
+file:line it follows (paths relative to /root/reference).  It is dtype-generic: pass float64 params and
+inputs to get the fp64 yardstick used to adjudicate tolerances.
+
+Parameters are passed as a flat `dict[str, Tensor]` with the reference's state_dict keys.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+EPSILON = float(torch.finfo(torch.float32).eps)  # FullSubNet_plus/speech_enhance/audio_zen/constant.py:8
+
+
+# --------------------------------------------------------------------------------------------
+# a1 / a15  STFT front end, iSTFT back end
+# --------------------------------------------------------------------------------------------
+def hann_periodic(n: int, dtype=torch.float32) -> torch.Tensor:
+    """torch.hann_window(n) default periodic=True (utils.py:124)."""
+    k = torch.arange(n, dtype=torch.float64)
+    return (0.5 - 0.5 * torch.cos(2.0 * math.pi * k / n)).to(dtype)
+
+
+def stft_mri(wave: torch.Tensor, n_fft: int = 512, hop: int = 256, win: int = 512):
+    """utils.py:107-147 prepare_input_from_waveform -> (mag, real, imag), each [B,1,F,T].
+
+    center=True reflect padding of n_fft//2, periodic hann, un-normalised rFFT, T = 1 + L//hop.
+    """
+    if wave.dim() == 1:
+        wave = wave[None]
+    assert win == n_fft, "reference configs always use win_length == n_fft"
+    w = hann_periodic(win, wave.dtype)
+    xp = F.pad(wave[:, None, :], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    frames = xp.unfold(-1, n_fft, hop)  # [B, T, n_fft]
+    spec = torch.fft.rfft(frames * w, dim=-1)  # [B, T, F]
+    real = spec.real.transpose(1, 2).contiguous()
+    imag = spec.imag.transpose(1, 2).contiguous()
+    mag = torch.sqrt(real ** 2 + imag ** 2)  # utils.py:140
+    return mag[:, None], real[:, None], imag[:, None]
+
+
+def istft(real: torch.Tensor, imag: torch.Tensor, length: int, n_fft: int = 512, hop: int = 256):
+    """torch.istft(center=True, window=hann, length=L) as called at utils.py:60-70, validator.py:136.
+
+    frame_t = irfft(X[:,t]) * w ; overlap-add ; divide by sum_t w^2 ; drop n_fft//2 ; trim / pad to length.
+    real/imag: [B, F, T] -> [B, length]
+    """
+    B, Fq, T = real.shape
+    w = hann_periodic(n_fft, real.dtype)
+    frames = torch.fft.irfft(torch.complex(real, imag).transpose(1, 2), n=n_fft, dim=-1) * w  # [B,T,n_fft]
+    total = n_fft + hop * (T - 1)
+    out = torch.zeros(B, total, dtype=real.dtype)
+    env = torch.zeros(total, dtype=real.dtype)
+    for t in range(T):
+        out[:, t * hop:t * hop + n_fft] += frames[:, t]
+        env[t * hop:t * hop + n_fft] += w * w
+    start = n_fft // 2
+    end = min(start + length, total - n_fft // 2) if length is not None else total - n_fft // 2
+    y = out[:, start:end] / env[start:end]
+    if length is not None and y.shape[1] < length:
+        y = F.pad(y, (0, length - y.shape[1]))
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# a2  normalisation
+# --------------------------------------------------------------------------------------------
+def offline_laplace_norm(x: torch.Tensor) -> torch.Tensor:
+    """base_model.py:210-224: x / (mean over (C,F,T) per sample + 1e-5)."""
+    mu = x.reshape(x.shape[0], -1).mean(dim=1).reshape(-1, 1, 1, 1)
+    return x / (mu + 1e-5)
+
+
+def cumulative_laplace_norm(x: torch.Tensor) -> torch.Tensor:
+    """base_model.py:227-257: y[f,t] = x[f,t] / (cumsum_t(sum_f x)/(F*(t+1)) + EPSILON)."""
+    B, C, Fq, T = x.shape
+    z = x.reshape(B * C, Fq, T)
+    cs = torch.cumsum(z.sum(dim=1), dim=-1)
+    cnt = (torch.arange(1, T + 1, dtype=x.dtype) * Fq)[None]
+    return (z / ((cs / cnt)[:, None, :] + EPSILON)).reshape(B, C, Fq, T)
+
+
+NORMS = {"offline_laplace_norm": offline_laplace_norm, "cumulative_laplace_norm": cumulative_laplace_norm}
+
+
+# --------------------------------------------------------------------------------------------
+# a3  TSSE channel attention
+# --------------------------------------------------------------------------------------------
+def tsse(x: torch.Tensor, p: Params, pre: str) -> torch.Tensor:
+    """attention_model.py:78-98 ChannelTimeSenseSELayer.forward; x [B,C,T]."""
+    C = x.shape[1]
+    feats = []
+    for name in ("smallConv1d", "middleConv1d", "largeConv1d"):
+        w, b = p[f"{pre}.{name}.0.weight"], p[f"{pre}.{name}.0.bias"]
+        y = F.conv1d(x, w, b, groups=C)  # depthwise, valid
+        feats.append(torch.relu(y.mean(dim=-1)))  # AdaptiveAvgPool1d(1) then ReLU
+    f = torch.stack(feats, dim=-1)  # [B,C,3]
+    s = (f * p[f"{pre}.feature_concate_fc.weight"][0]).sum(-1) + p[f"{pre}.feature_concate_fc.bias"][0]
+    h = torch.relu(s @ p[f"{pre}.fc1.weight"].T + p[f"{pre}.fc1.bias"])
+    g = torch.sigmoid(h @ p[f"{pre}.fc2.weight"].T + p[f"{pre}.fc2.bias"])
+    return x * g[:, :, None]
+
+
+# --------------------------------------------------------------------------------------------
+# a4  full-band TCN stack
+# --------------------------------------------------------------------------------------------
+TCN_DILATIONS = (1, 2, 5, 9, 1, 2, 5, 9)  # sequence_model.py:48-57
+
+
+def _prelu(x, a):
+    return torch.where(x >= 0, x, a * x)
+
+
+def _groupnorm1(x, gamma, beta, eps=1e-8):
+    """GroupNorm(1, C): per-sample mean / biased variance over all (C, T) (causal_conv.py:73,79)."""
+    mu = x.mean(dim=(1, 2), keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=(1, 2), keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * gamma[None, :, None] + beta[None, :, None]
+
+
+def tcn_block(x: torch.Tensor, p: Params, pre: str, dilation: int) -> torch.Tensor:
+    """causal_conv.py:96-108 TCNBlock.forward (use_skip_connection=True, causal=False)."""
+    y = F.conv1d(x, p[f"{pre}.conv1x1.weight"], p[f"{pre}.conv1x1.bias"])
+    y = _groupnorm1(_prelu(y, p[f"{pre}.prelu1.weight"]), p[f"{pre}.norm1.weight"], p[f"{pre}.norm1.bias"])
+    Ch = y.shape[1]
+    y = F.conv1d(y, p[f"{pre}.depthwise_conv.weight"], p[f"{pre}.depthwise_conv.bias"],
+                 padding=dilation, dilation=dilation, groups=Ch)
+    y = _groupnorm1(_prelu(y, p[f"{pre}.prelu2.weight"]), p[f"{pre}.norm2.weight"], p[f"{pre}.norm2.bias"])
+    return x + F.conv1d(y, p[f"{pre}.sconv.weight"], p[f"{pre}.sconv.bias"])
+
+
+def tcn_sequence_model(x: torch.Tensor, p: Params, pre: str) -> torch.Tensor:
+    """sequence_model.py:47-58,106-112 (TCN branch) incl. fc_output_layer + ReLU output activation."""
+    for i, d in enumerate(TCN_DILATIONS):
+        x = tcn_block(x, p, f"{pre}.sequence_model.{i}", d)
+    x = torch.relu(x)
+    o = x.transpose(1, 2) @ p[f"{pre}.fc_output_layer.weight"].T + p[f"{pre}.fc_output_layer.bias"]
+    return torch.relu(o).transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------------
+# a5 / a6  sub-band unfold, drop_band
+# --------------------------------------------------------------------------------------------
+def unfold(x: torch.Tensor, n: int) -> torch.Tensor:
+    """base_model.py:15-46: [B,C,F,T] -> [B,F,C,2n+1,T]; out[b,f,c,k,t] = x[b,c,reflect(f+k-n),t]."""
+    B, C, Fq, T = x.shape
+    if n < 1:
+        return x.permute(0, 2, 1, 3).reshape(B, Fq, C, 1, T)
+    idx = torch.arange(Fq)[:, None] + torch.arange(2 * n + 1)[None, :] - n
+    idx = torch.where(idx < 0, -idx, idx)
+    idx = torch.where(idx > Fq - 1, 2 * (Fq - 1) - idx, idx)
+    out = x[:, :, idx, :]  # [B,C,F,K,T]
+    return out.permute(0, 2, 1, 3, 4).contiguous()
+
+
+def drop_band(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """feature.py:254-285: [B,C,F,T] -> [B,C,F//G,T]; asserts B > G *before* the G<=1 early-out."""
+    B, _, Fq, _ = x.shape
+    assert B > groups, f"Batch size = {B}, num_groups = {groups}. The batch size should larger than the num_groups."
+    if groups <= 1:
+        return x
+    Fq -= Fq % groups
+    return torch.cat([x[g::groups, :, g:Fq:groups, :] for g in range(groups)], dim=0)
+
+
+# --------------------------------------------------------------------------------------------
+# a7  sub-band LSTM (2 layers) + fc
+# --------------------------------------------------------------------------------------------
+def lstm_fc(x: torch.Tensor, p: Params, pre: str, fast: bool = False) -> torch.Tensor:
+    """sequence_model.py:113-123 (LSTM branch): x [N,I,T] -> [N,O,T].
+
+    nn.LSTM semantics: gates ordered i,f,g,o; z = W_ih x + b_ih + W_hh h + b_hh; zero initial state.
+    fast=True calls ATen's fused CPU LSTM (what nn.LSTM itself dispatches to) — used only for the
+    timed CPU baseline so that the baseline is as fast as the reference's own nn.LSTM.
+    """
+    seq = x.transpose(1, 2)  # [N,T,I]
+    lp = f"{pre}.sequence_model"
+    if fast:
+        N = seq.shape[0]
+        H = p[f"{lp}.weight_hh_l0"].shape[1]
+        flat = [p[f"{lp}.{k}_l{l}"] for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        z = torch.zeros(2, N, H, dtype=seq.dtype)
+        seq = torch.lstm(seq.contiguous(), (z, z), flat, True, 2, 0.0, False, False, True)[0]
+    else:
+        for layer in (0, 1):
+            w_ih, w_hh = p[f"{lp}.weight_ih_l{layer}"], p[f"{lp}.weight_hh_l{layer}"]
+            b = p[f"{lp}.bias_ih_l{layer}"] + p[f"{lp}.bias_hh_l{layer}"]
+            N, T, _ = seq.shape
+            H = w_hh.shape[1]
+            zx = seq @ w_ih.T + b  # [N,T,4H]
+            h = torch.zeros(N, H, dtype=seq.dtype)
+            c = torch.zeros(N, H, dtype=seq.dtype)
+            outs = []
+            for t in range(T):
+                z = zx[:, t] + h @ w_hh.T
+                i, f, g, o = z.split(H, dim=1)
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                outs.append(h)
+            seq = torch.stack(outs, dim=1)
+    y = seq @ p[f"{pre}.fc_output_layer.weight"].T + p[f"{pre}.fc_output_layer.bias"]
+    return y.transpose(1, 2).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# a8  FullSubNet+ backbone,  a11  multi-direction PC head
+# --------------------------------------------------------------------------------------------
+def _sub(p: Params, prefix: str) -> Params:
+    n = len(prefix)
+    return {k[n:]: v for k, v in p.items() if k.startswith(prefix)}
+
+
+def fullsubnet_plus(p: Params, mag, real, imag, *, look_ahead=2, sb_n=15, fb_n=0, groups=1,
+                    norm_type="offline_laplace_norm", output_size=2, fast=False, taps: Optional[dict] = None):
+    """fullsubnet_plus.py:143-230 FullSubNet_Plus.forward. inputs [B,1,F,T] -> compressed cRM [B,O,F',T]."""
+    norm = NORMS[norm_type]
+    mag, real, imag = (F.pad(v, (0, look_ahead)) for v in (mag, real, imag))
+    B, C, Fq, T = mag.shape
+    assert C == 1
+    fb_in = tsse(norm(mag).reshape(B, Fq, T), p, "channel_attention")
+    fb_out = tcn_sequence_model(fb_in, p, "fb_model").reshape(B, 1, Fq, T)
+    fbr_in = tsse(norm(real).reshape(B, Fq, T), p, "channel_attention_real")
+    fbr_out = tcn_sequence_model(fbr_in, p, "fb_model_real").reshape(B, 1, Fq, T)
+    fbi_in = tsse(norm(imag).reshape(B, Fq, T), p, "channel_attention_imag")
+    fbi_out = tcn_sequence_model(fbi_in, p, "fb_model_imag").reshape(B, 1, Fq, T)
+    parts = [unfold(fb_in.reshape(B, 1, Fq, T), sb_n).reshape(B, Fq, 2 * sb_n + 1, T)]
+    parts += [unfold(v, fb_n).reshape(B, Fq, 2 * fb_n + 1, T) for v in (fb_out, fbr_out, fbi_out)]
+    sb_in = norm(torch.cat(parts, dim=2))  # [B,F,S,T]
+    if taps is not None:
+        taps.update(fb_in=fb_in, fb_out=fb_out, fbr_out=fbr_out, fbi_out=fbi_out, sb_in=sb_in)
+    if B > 1:
+        sb_in = drop_band(sb_in.permute(0, 2, 1, 3), groups).permute(0, 2, 1, 3)
+        Fq = sb_in.shape[1]
+    S = sb_in.shape[2]
+    y = lstm_fc(sb_in.reshape(B * Fq, S, T), p, "sb_model", fast=fast)  # [B*F', O, T]
+    y = y.reshape(B, Fq, output_size, T).permute(0, 2, 1, 3).contiguous()
+    return y[..., look_ahead:]
+
+
+def multidir_fullsubnet_plus(p: Params, nmag, nreal, nimag, emag, ereal, eimag, *, n_dirs, look_ahead=2,
+                             sb_n=15, fb_n=0, groups=1, norm_type="offline_laplace_norm", fast=False,
+                             taps: Optional[dict] = None):
+    """networks.py:63-163 MultiDirectionFullSubNet_Plus.forward -> [B, 2*n_dirs, F', T]."""
+    norm = NORMS[norm_type]
+    nmag, nreal, nimag, emag, ereal, eimag = (F.pad(v, (0, look_ahead)) for v in
+                                              (nmag, nreal, nimag, emag, ereal, eimag))
+    B, C, Fq, T = nmag.shape
+
+    def stream(noisy, enh, att, model):
+        a = tsse(norm(noisy).reshape(B, Fq, T), p, att)
+        b = tsse(norm(enh).reshape(B, Fq, T), p, att)
+        return tcn_sequence_model(torch.cat([a, b], dim=1), p, model).reshape(B, 1, Fq, T)
+
+    fb_out = stream(nmag, emag, "channel_attention", "fb_model")
+    fbr_out = stream(nreal, ereal, "channel_attention_real", "fb_model_real")
+    fbi_out = stream(nimag, eimag, "channel_attention_imag", "fb_model_imag")
+    # NOTE networks.py:133 — the sub-band block uses the RAW padded noisy magnitude, not the attended one.
+    parts = [unfold(nmag, sb_n).reshape(B, Fq, 2 * sb_n + 1, T)]
+    parts += [unfold(v, fb_n).reshape(B, Fq, 2 * fb_n + 1, T) for v in (fb_out, fbr_out, fbi_out)]
+    sb_in = norm(torch.cat(parts, dim=2))
+    if taps is not None:
+        taps.update(h_fb_out=fb_out, h_fbr_out=fbr_out, h_fbi_out=fbi_out, h_sb_in=sb_in)
+    if B > 1:
+        sb_in = drop_band(sb_in.permute(0, 2, 1, 3), groups).permute(0, 2, 1, 3)
+        Fq = sb_in.shape[1]
+    S = sb_in.shape[2]
+    y = lstm_fc(sb_in.reshape(B * Fq, S, T), p, "sb_model", fast=fast)  # [B*F', 2n, T]
+    y = y.reshape(B, Fq, n_dirs, 2, T).permute(0, 2, 3, 1, 4)[..., look_ahead:]
+    return y.reshape(B, 2 * n_dirs, Fq, -1)
+
+
+# --------------------------------------------------------------------------------------------
+# a9 / a10  cIRM (de)compression, mask application
+# --------------------------------------------------------------------------------------------
+def decompress_cirm(m: torch.Tensor, K: float = 10.0, limit: float = 9.9) -> torch.Tensor:
+    """mask.py:57-60."""
+    m = limit * (m >= limit) - limit * (m <= -limit) + m * (m.abs() < limit)
+    return -K * torch.log((K - m) / (K + m))
+
+
+def compress_cirm(m: torch.Tensor, K: float = 10.0, C: float = 0.1) -> torch.Tensor:
+    """mask.py:44-50."""
+    m = -100.0 * (m <= -100) + m * (m > -100)
+    return K * (1 - torch.exp(-C * m)) / (1 + torch.exp(-C * m))
+
+
+def build_cirm(nr, ni, cr, ci) -> torch.Tensor:
+    """mask.py:24-41 build_complex_ideal_ratio_mask -> [..., 2] compressed."""
+    den = nr * nr + ni * ni + EPSILON
+    return compress_cirm(torch.stack(((nr * cr + ni * ci) / den, (nr * ci - ni * cr) / den), dim=-1))
+
+
+def crm_apply(m0, m1, real, imag, conj: bool):
+    """conj=True: utils.py:241-249 via :75-79 (argument-order quirk => conj(M)*N);
+    conj=False: the correct M*N used everywhere else (utils.py:54, :252-256). Returns (mag, real, imag)."""
+    if conj:
+        er = m0 * real + m1 * imag
+        ei = m0 * imag - m1 * real
+    else:
+        er = m0 * real - m1 * imag
+        ei = m1 * real + m0 * imag
+    return torch.sqrt(er ** 2 + ei ** 2), er, ei
+
+
+# --------------------------------------------------------------------------------------------
+# a12  Gram-Schmidt
+# --------------------------------------------------------------------------------------------
+def gram_schmidt_complex(x: torch.Tensor) -> torch.Tensor:
+    """nppc_audio/pc_wrapper.py:8-44: x [B,n,2,F,T]; MGS with the CONJUGATED coefficient
+    sum(conj(w) * w_hat_j) (quirk); returns the un-normalised w_i."""
+    B, n, _, Fq, T = x.shape
+    v = torch.complex(x[:, :, 0], x[:, :, 1]).reshape(B, n, -1)
+    outs, hats = [], []
+    for i in range(n):
+        w = v[:, i]
+        for wh in hats:
+            w = w - wh * (w.conj() * wh).sum(dim=1, keepdim=True)
+        hats.append(w / torch.linalg.vector_norm(w, dim=1, keepdim=True))
+        outs.append(w)
+    out = torch.stack(outs, dim=1).reshape(B, n, Fq, T)
+    return torch.stack([out.real, out.imag], dim=2)
+
+
+def gram_schmidt_real(x: torch.Tensor) -> torch.Tensor:
+    """nppc_audio/inpainting/nppc/pc_wrapper.py:43-59 (== nppc/nppc.py:189-205): x [B,n,...] real MGS."""
+    shp = x.shape
+    v = x.reshape(shp[0], shp[1], -1)
+    outs, hats = [], []
+    for i in range(shp[1]):
+        w = v[:, i]
+        for wh in hats:
+            w = w - wh * (w * wh).sum(dim=1, keepdim=True)
+        hats.append(w / torch.linalg.vector_norm(w, dim=1, keepdim=True))
+        outs.append(w)
+    return torch.stack(outs, dim=1).reshape(shp)
+
+
+# --------------------------------------------------------------------------------------------
+# a13  NPPCModel.forward / get_pred_crm,  enhance-only pipeline
+# --------------------------------------------------------------------------------------------
+def get_pred_crm(p: Params, wave, *, n_fft=512, hop=256, win=512, fast=False, taps=None, **bb):
+    """nppc_model.py:117-132: compressed cRM [B,2,F,T] of the frozen backbone."""
+    mag, real, imag = stft_mri(wave, n_fft, hop, win)
+    return fullsubnet_plus(_sub(p, "pretrained_restoration_model."), mag, real, imag, fast=fast, taps=taps, **bb)
+
+
+def nppc_forward(p: Params, wave, *, n_dirs: int, head_groups: int = 1, n_fft=512, hop=256, win=512,
+                 norm_type="offline_laplace_norm", fast=False, taps: Optional[dict] = None):
+    """nppc_model.py:58-115 NPPCModel.forward: wave [B,L] -> w_mat [B,n_dirs,2,F',T]."""
+    mag, real, imag = stft_mri(wave, n_fft, hop, win)
+    crm = fullsubnet_plus(_sub(p, "pretrained_restoration_model."), mag, real, imag,
+                          norm_type=norm_type, fast=fast, taps=taps)
+    m = decompress_cirm(crm.permute(0, 2, 3, 1))
+    emag, ereal, eimag = crm_apply(m[..., 0], m[..., 1], real[:, 0], imag[:, 0], conj=True)
+    head = multidir_fullsubnet_plus(_sub(p, "audio_pc_wrapper.net."), mag, real, imag,
+                                    emag[:, None], ereal[:, None], eimag[:, None],
+                                    n_dirs=n_dirs, groups=head_groups, norm_type=norm_type, fast=fast, taps=taps)
+    B, _, Fq, T = head.shape
+    w = gram_schmidt_complex(head.reshape(B, n_dirs, 2, Fq, T))
+    if taps is not None:
+        taps.update(mag=mag, real=real, imag=imag, pred_crm=crm, emag=emag, ereal=ereal, eimag=eimag, head=head)
+    return w
+
+
+def enhance(p_backbone: Params, wave, *, n_fft=512, hop=256, win=512, fast=False):
+    """Enhance-only pipeline (BASELINE config #2): use_pre_trained_model/model_validator/model_validator.py:84-133
+    == utils.py:37-72: STFT -> FullSubNet+ -> decompress -> M*N -> iSTFT(length=L)."""
+    mag, real, imag = stft_mri(wave, n_fft, hop, win)
+    crm = fullsubnet_plus(p_backbone, mag, real, imag, fast=fast)
+    m = decompress_cirm(crm.permute(0, 2, 3, 1))
+    _, er, ei = crm_apply(m[..., 0], m[..., 1], real[:, 0], imag[:, 0], conj=False)
+    return istft(er, ei, wave.shape[-1], n_fft, hop)
+
+
+# --------------------------------------------------------------------------------------------
+# a14  NPPC projection / second-moment loss
+# --------------------------------------------------------------------------------------------
+def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
+    """trainer.py:337-340."""
+    return max(min(-1 + 2 * step / grace, 1), 1e-6) * lambda0
+
+
+def nppc_loss(w_mat, gt_crm, pred_crm, *, step: int, grace: float, lambda0: float):
+    """trainer.py:259-298 + :337-342. w_mat [B,n,2,F,T]; gt/pred [B,2,F,T] (compressed-cIRM domain)."""
+    B, n = w_mat.shape[:2]
+    W = w_mat.reshape(B, n, 2, -1)
+    w_norms = torch.linalg.vector_norm(W, dim=(2, 3))
+    w_hat = W / (w_norms[..., None, None] + 1e-8)
+    err = (gt_crm - pred_crm).reshape(B, 2, -1)
+    err_norm = torch.linalg.vector_norm(err, dim=(1, 2))
+    err = err / (err_norm[:, None, None] + 1e-8)
+    w_norms = w_norms / (err_norm[:, None] + 1e-8)
+    ec = torch.complex(err[:, 0], err[:, 1])
+    wc = torch.complex(w_hat[:, :, 0], w_hat[:, :, 1])
+    err_proj = (wc.conj() * ec[:, None]).sum(-1)
+    err_proj_mag = err_proj.abs()
+    reconst_err = 1 - (err_proj_mag ** 2).sum(dim=1)
+    second_moment_mse = (w_norms ** 2 - err_proj_mag.detach() ** 2) ** 2
+    lam = second_moment_lambda(step, grace, lambda0)
+    objective = reconst_err.mean() + lam * second_moment_mse.mean()
+    return dict(err_norm=err_norm, err_proj=err_proj, err_proj_mag=err_proj_mag, w_norms=w_norms,
+                reconst_err=reconst_err, second_moment_mse=second_moment_mse, objective=objective)
+
+
+def base_step(p: Params, noisy, clean, *, n_dirs, head_groups, step, grace, lambda0, fast=False):
+    """trainer.py:234-317 NPPCAudioTrainer.base_step (+ _get_true_and_pred_crm :344-371)."""
+    w_mat = nppc_forward(p, noisy, n_dirs=n_dirs, head_groups=head_groups, fast=fast)
+    _, nr, ni = stft_mri(noisy)
+    _, cr, ci = stft_mri(clean)
+    gt = build_cirm(nr[:, 0], ni[:, 0], cr[:, 0], ci[:, 0]).permute(0, 3, 1, 2)
+    gt = drop_band(gt, head_groups)
+    pred = drop_band(get_pred_crm(p, noisy, fast=fast), head_groups)
+    out = nppc_loss(w_mat, gt, pred, step=step, grace=grace, lambda0=lambda0)
+    out.update(w_mat=w_mat, pred_crm=pred, gt_crm=gt)
+    return out
