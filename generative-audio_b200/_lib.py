@@ -1,0 +1,80 @@
+"""ctypes binding of libnppc_b200.so (C ABI declared in include/nppc_b200.h).
+
+The product path has NO fallback: if the shared library is missing it is built with nvcc (build.py); if that
+fails, or the symbols are missing, importing raises.  Nothing here touches oracle/.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnppc_b200.so")
+
+_p, _i, _ll, _sz, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/nppc_b200.h
+PROTOTYPES = {
+    "nppc_last_error": (C.c_char_p, []),
+    "nppc_version": (C.c_char_p, []),
+    "nppc_launch_count": (_ll, []),
+    "nppc_reset_launch_count": (None, []),
+    "nppc_stft_mri": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_istft": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_crm_decompress_apply": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_decompress_cirm": (_i, [_p, _ll, _p, _p]),
+    "nppc_build_cirm": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
+    "nppc_offline_laplace_norm": (_i, [_p, _i, _ll, _p, _p, _p]),
+    "nppc_pad_offline_laplace_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "nppc_cumulative_laplace_norm": (_i, [_p, _i, _i, _i, _p, _p]),
+    "nppc_unfold": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_drop_band": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_gs_scratch_bytes": (_sz, [_i, _i]),
+    "nppc_gram_schmidt_complex": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
+    "nppc_gram_schmidt_real": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
+    "nppc_gs_loss_fused": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "nppc_projection_loss": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_lstm_plan_create": (_i, [C.POINTER(_p), _i, _i, _i] + [_p] * 10 + [_p]),
+    "nppc_lstm_plan_destroy": (None, [_p]),
+    "nppc_lstm_workspace_bytes": (_sz, [_p, _i, _i, _i]),
+    "nppc_lstm_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
+}
+
+_lib = None
+
+
+class NppcError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_nppc_build", os.path.join(HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    if not os.path.exists(LIB_PATH):
+        raise NppcError(f"{LIB_PATH} is missing and could not be built; the CUDA path has no fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise NppcError(f"{LIB_PATH} does not export {name}; rebuild with generative-audio_b200/build.py --force")
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().nppc_last_error().decode(errors="replace")
+        # the reference raises AssertionError for its shape/argument checks (feature.py:263, fullsubnet_plus.py:157)
+        if rc == -1:
+            raise AssertionError(msg)
+        raise NppcError(f"{what} failed ({rc}): {msg}")

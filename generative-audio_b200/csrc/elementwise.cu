@@ -1,0 +1,438 @@
+// HBM-bound elementwise / indexing kernels: cIRM (de)compression + mask apply (a9, a10), laplace norms (a2),
+// sub-band unfold (a5), drop_band (a6), fused sub-band feature packing for the LSTM, output assembly (a8/a11).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ float decompress1(float m) {
+    // mask.py:57-60: limit*(m>=limit) - limit*(m<=-limit) + m*(|m|<limit); -K*log((K-m)/(K+m)), K=10, limit=9.9
+    float c = (m >= 9.9f) ? 9.9f : ((m <= -9.9f) ? -9.9f : m);
+    return -10.0f * logf((10.0f - c) / (10.0f + c));
+}
+
+__device__ __forceinline__ float compress1(float m) {
+    // mask.py:44-50: m <- -100 where m <= -100 ; K*(1-exp(-C m))/(1+exp(-C m)), K=10, C=0.1
+    m = (m <= -100.0f) ? -100.0f : m;
+    float e = expf(-0.1f * m);
+    return 10.0f * (1.0f - e) / (1.0f + e);
+}
+
+__global__ void __launch_bounds__(TPB) crm_apply_kernel(const float* __restrict__ crm, const float* __restrict__ re,
+                                                       const float* __restrict__ im, int FT, int conj,
+                                                       float* __restrict__ omag, float* __restrict__ ore,
+                                                       float* __restrict__ oim) {
+    const int b = blockIdx.y;
+    const float* m0p = crm + (size_t)b * 2 * FT;
+    const float* m1p = m0p + FT;
+    const size_t off = (size_t)b * FT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FT; i += gridDim.x * blockDim.x) {
+        float m0 = decompress1(m0p[i]), m1 = decompress1(m1p[i]);
+        float r = re[off + i], q = im[off + i];
+        float er, ei;
+        if (conj) {  // utils.py:241-249 through the swapped-argument call of :75-79  => conj(M) * N
+            er = m0 * r + m1 * q;
+            ei = m0 * q - m1 * r;
+        } else {     // utils.py:54,75-79 => M * N
+            er = m0 * r - m1 * q;
+            ei = m1 * r + m0 * q;
+        }
+        ore[off + i] = er;
+        oim[off + i] = ei;
+        if (omag) omag[off + i] = sqrtf(er * er + ei * ei);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) decompress_kernel(const float* __restrict__ m, long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = decompress1(m[i]);
+}
+
+__global__ void __launch_bounds__(TPB) build_cirm_kernel(const float* __restrict__ nr, const float* __restrict__ ni,
+                                                        const float* __restrict__ cr, const float* __restrict__ ci,
+                                                        int FT, float* __restrict__ gt) {
+    const int b = blockIdx.y;
+    const size_t off = (size_t)b * FT;
+    float* g0 = gt + (size_t)b * 2 * FT;
+    float* g1 = g0 + FT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FT; i += gridDim.x * blockDim.x) {
+        float a = nr[off + i], bb = ni[off + i], c = cr[off + i], d = ci[off + i];
+        float den = a * a + bb * bb + 1.1920928955078125e-07f;  // EPSILON = finfo(float32).eps (constant.py:8)
+        g0[i] = compress1((a * c + bb * d) / den);
+        g1[i] = compress1((a * d - bb * c) / den);
+    }
+}
+
+// ---- norms --------------------------------------------------------------------------------------------
+// per-sample sum in fp64 (the reference's divisor is a cancelling sum for signed re/im planes)
+__global__ void __launch_bounds__(TPB) sample_sum_kernel(const float* __restrict__ x, long long n, double* __restrict__ sums) {
+    __shared__ double red[32];
+    const int b = blockIdx.y;
+    const float* xb = x + (size_t)b * n;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += (double)xb[i];
+    acc = nppc::block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(&sums[b], acc);
+}
+
+__global__ void __launch_bounds__(TPB) offline_norm_kernel(const float* __restrict__ x, long long n,
+                                                          const double* __restrict__ sums, double count,
+                                                          float* __restrict__ y) {
+    const int b = blockIdx.y;
+    const float mu = (float)(sums[b] / count);
+    const float den = mu + 1e-5f;
+    const float* xb = x + (size_t)b * n;
+    float* yb = y + (size_t)b * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        yb[i] = xb[i] / den;
+}
+
+// x [B,F,T] -> y [B,F,T+la] = pad + norm (mean counts the zero look-ahead frames, fullsubnet_plus.py:158-165)
+__global__ void __launch_bounds__(TPB) pad_norm_kernel(const float* __restrict__ x, int F, int T, int la,
+                                                      const double* __restrict__ sums, float* __restrict__ y) {
+    const int b = blockIdx.y;
+    const int Tp = T + la;
+    const float mu = (float)(sums[b] / ((double)F * Tp));
+    const float den = mu + 1e-5f;
+    const float* xb = x + (size_t)b * F * T;
+    float* yb = y + (size_t)b * F * Tp;
+    const int n = F * Tp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int f = i / Tp, t = i - f * Tp;
+        yb[i] = (t < T) ? xb[f * T + t] / den : 0.0f / den;
+    }
+}
+
+// cumulative_laplace_norm: one CTA per (b*c) plane [F,T]: column sums -> block scan over T -> scale.
+__global__ void __launch_bounds__(TPB) cumulative_norm_kernel(const float* __restrict__ x, int F, int T,
+                                                             float* __restrict__ y) {
+    extern __shared__ float sh[];  // [T] cumulative means, + 32 warp totals
+    float* cmean = sh;
+    float* wtot = sh + T;
+    __shared__ float carry;
+    const float* xb = x + (size_t)blockIdx.x * F * T;
+    float* yb = y + (size_t)blockIdx.x * F * T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0.f;
+    __syncthreads();
+    for (int tb = 0; tb < T; tb += blockDim.x) {
+        int t = tb + threadIdx.x;
+        float s = 0.f;
+        if (t < T)
+            for (int f = 0; f < F; ++f) s += xb[(size_t)f * T + t];  // coalesced across threads
+        // inclusive warp scan (shuffle), then block-level carry
+        float v = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) wtot[warp] = v;
+        __syncthreads();
+        float base = carry;
+        for (int w = 0; w < warp; ++w) base += wtot[w];
+        v += base;
+        if (t < T) cmean[t] = v / ((float)F * (float)(t + 1)) + 1.1920928955078125e-07f;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = v;
+        __syncthreads();
+    }
+    (void)nw;
+    const int n = F * T;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int t = i % T;
+        yb[i] = xb[i] / cmean[t];
+    }
+}
+
+// ---- unfold / drop_band (bit-exact copies) -------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int p, int F) {
+    if (p < 0) p = -p;
+    if (p > F - 1) p = 2 * (F - 1) - p;
+    return p;
+}
+
+// out [B,F,C,K,T]; one CTA per (b, f, c) writes K rows of T; source rows are contiguous T-rows -> coalesced both ways.
+__global__ void __launch_bounds__(TPB) unfold_kernel(const float* __restrict__ x, int C, int F, int T, int nn,
+                                                    float* __restrict__ out) {
+    const int K = 2 * nn + 1;
+    long long row = blockIdx.x;  // (b*F + f)*C + c
+    int c = (int)(row % C);
+    long long bf = row / C;
+    int f = (int)(bf % F);
+    int b = (int)(bf / F);
+    const float* src = x + ((size_t)b * C + c) * F * T;
+    float* dst = out + (size_t)row * K * T;
+    const int n = K * T;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int k = i / T, t = i - k * T;
+        dst[i] = src[(size_t)reflect_idx(f + k - nn, F) * T + t];
+    }
+}
+
+// out [B,C,F/G,T]: out[ob, c, j, t] = x[g + G*(ob - start_g), c, g + G*j, t] where group g owns a run of batches
+__global__ void __launch_bounds__(TPB) drop_band_kernel(const float* __restrict__ x, int B, int C, int F, int T,
+                                                       int G, float* __restrict__ out) {
+    const int Fg = F / G;
+    long long row = blockIdx.x;  // (ob*C + c)*Fg + j
+    int j = (int)(row % Fg);
+    long long oc = row / Fg;
+    int c = (int)(oc % C);
+    int ob = (int)(oc / C);
+    // group g has ceil((B-g)/G) samples, laid out group after group
+    int g = 0, start = 0;
+    for (; g < G; ++g) {
+        int cnt = (B - g + G - 1) / G;
+        if (ob < start + cnt) break;
+        start += cnt;
+    }
+    int sb = g + G * (ob - start);
+    const float* src = x + (((size_t)sb * C + c) * F + (g + G * j)) * T;
+    float* dst = out + (size_t)row * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) dst[t] = src[t];
+}
+
+// ---- fused sub-band packing ---------------------------------------------------------------------------
+__device__ __forceinline__ int count_f(int q, int F, int nn) {
+    int lo = max(0, q - nn), hi = min(F - 1, q + nn);
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
+// Per-sample sum of the (never materialised) [F,S,T'] sub-band input: sum_{f,k} unfold(nbr)[f,k,:] + fb + fbr + fbi.
+// Row p of nbr_src appears cnt(p) = #{(f,k): reflect(f+k-N) == p} times.
+__global__ void __launch_bounds__(TPB) subband_sum_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
+                                                         const float* __restrict__ fbr, const float* __restrict__ fbi,
+                                                         int F, int Tp, int nn, double* __restrict__ sums) {
+    __shared__ double red[32];
+    const int b = blockIdx.y;
+    const size_t off = (size_t)b * F * Tp;
+    const int n = F * Tp;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int p = i / Tp;
+        // multiplicity of source row p: #f in [0,F) with |f-q| <= N, summed over the positions q that reflect onto p
+        int cnt = count_f(p, F, nn);
+        if (p >= 1) cnt += count_f(-p, F, nn);
+        if (p <= F - 2) cnt += count_f(2 * (F - 1) - p, F, nn);
+        acc += (double)cnt * (double)nbr[off + i] + (double)fb[off + i] + (double)fbr[off + i] + (double)fbi[off + i];
+    }
+    acc = nppc::block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(&sums[b], acc);
+}
+
+// xs[t][row][k], row = ob*Fg + j  (drop_band order), k < S real features, zero padded to KP.
+// One CTA per (row-tile of 8 rows, time-tile of 32 frames): reads are T'-contiguous, writes are KP-contiguous;
+// transposed through shared memory.
+constexpr int PK_ROWS = 4;
+constexpr int PK_T = 32;
+__global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
+                                                          const float* __restrict__ fbr, const float* __restrict__ fbi,
+                                                          int B, int F, int Tp, int nn, int G, int KP,
+                                                          const double* __restrict__ sums, float* __restrict__ xs_f32,
+                                                          __nv_bfloat16* __restrict__ xs_bf16) {
+    extern __shared__ float tile[];  // [PK_ROWS][KP][PK_T+1]
+    const int S = 2 * nn + 1 + 3;
+    const int Fg = F / G;
+    const long long R = (long long)B * Fg;
+    const long long row0 = (long long)blockIdx.x * PK_ROWS;
+    const int t0 = blockIdx.y * PK_T;
+    const double count = (double)F * S * Tp;
+    for (int idx = threadIdx.x; idx < PK_ROWS * KP * PK_T; idx += blockDim.x) {
+        int tt = idx % PK_T;
+        int k = (idx / PK_T) % KP;
+        int r = idx / (PK_T * KP);
+        long long row = row0 + r;
+        int t = t0 + tt;
+        float v = 0.f;
+        if (row < R && t < Tp && k < S) {
+            int ob = (int)(row / Fg), j = (int)(row % Fg);
+            int g = 0, start = 0, sb = ob, f = j;
+            if (G > 1) {
+                for (; g < G; ++g) {
+                    int cnt = (B - g + G - 1) / G;
+                    if (ob < start + cnt) break;
+                    start += cnt;
+                }
+                sb = g + G * (ob - start);
+                f = g + G * j;
+            }
+            const size_t off = (size_t)sb * F * Tp;
+            float raw;
+            if (k < 2 * nn + 1) raw = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp + t];
+            else if (k == 2 * nn + 1) raw = fb[off + (size_t)f * Tp + t];
+            else if (k == 2 * nn + 2) raw = fbr[off + (size_t)f * Tp + t];
+            else raw = fbi[off + (size_t)f * Tp + t];
+            float den = (float)(sums[sb] / count) + 1e-5f;
+            v = raw / den;
+        }
+        tile[(r * KP + k) * (PK_T + 1) + tt] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PK_ROWS * KP * PK_T; idx += blockDim.x) {
+        int k = idx % KP;
+        int r = (idx / KP) % PK_ROWS;
+        int tt = idx / (KP * PK_ROWS);
+        long long row = row0 + r;
+        int t = t0 + tt;
+        if (row < R && t < Tp) {
+            float v = tile[(r * KP + k) * (PK_T + 1) + tt];
+            size_t o = ((size_t)t * R + row) * KP + k;
+            if (xs_f32) xs_f32[o] = v;
+            if (xs_bf16) xs_bf16[o] = __float2bfloat16(v);
+        }
+    }
+}
+
+// y [B*Fp, O, Tp] -> out [B, O, Fp, Tp-la] (drop first `la` frames)
+__global__ void __launch_bounds__(TPB) assemble_kernel(const float* __restrict__ y, int Fp, int O, int Tp, int la,
+                                                      float* __restrict__ out) {
+    long long row = blockIdx.x;  // (b*O + o)*Fp + f
+    int f = (int)(row % Fp);
+    long long bo = row / Fp;
+    int o = (int)(bo % O);
+    int b = (int)(bo / O);
+    const float* src = y + (((size_t)b * Fp + f) * O + o) * Tp + la;
+    float* dst = out + (size_t)row * (Tp - la);
+    for (int t = threadIdx.x; t < Tp - la; t += blockDim.x) dst[t] = src[t];
+}
+
+int grid_for(long long n, int cap_mult = 8) {
+    long long g = (n + TPB - 1) / TPB;
+    long long cap = (long long)nppc::sm_count() * cap_mult;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int nppc_crm_decompress_apply(const float* crm, const float* real, const float* imag, int B, int FT,
+                                         int conj, float* out_mag, float* out_real, float* out_imag, void* stream) {
+    NPPC_CHECK_ARG(crm && real && imag && out_real && out_imag, "nppc_crm_decompress_apply: null pointer");
+    NPPC_CHECK_ARG(B > 0 && FT > 0, "nppc_crm_decompress_apply: bad sizes B=%d FT=%d", B, FT);
+    int gx = grid_for(FT, 8);
+    int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
+    if (gx > per && per >= 1) gx = per;
+    crm_apply_kernel<<<dim3(gx, B), TPB, 0, (cudaStream_t)stream>>>(crm, real, imag, FT, conj, out_mag, out_real, out_imag);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_decompress_cirm(const float* m, long long n, float* out, void* stream) {
+    NPPC_CHECK_ARG(m && out && n > 0, "nppc_decompress_cirm: bad arguments");
+    decompress_kernel<<<grid_for(n), TPB, 0, (cudaStream_t)stream>>>(m, n, out);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_build_cirm(const float* nr, const float* ni, const float* cr, const float* ci, int B, int FT,
+                               float* gt, void* stream) {
+    NPPC_CHECK_ARG(nr && ni && cr && ci && gt && B > 0 && FT > 0, "nppc_build_cirm: bad arguments");
+    int gx = grid_for(FT, 8);
+    build_cirm_kernel<<<dim3(gx, B), TPB, 0, (cudaStream_t)stream>>>(nr, ni, cr, ci, FT, gt);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+static int per_sample_grid(long long n, int B) {
+    int gx = grid_for(n, 8);
+    int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
+    if (per < 1) per = 1;
+    return gx > per ? per : gx;
+}
+
+extern "C" int nppc_offline_laplace_norm(const float* x, int B, long long n, double* sums, float* y, void* stream) {
+    NPPC_CHECK_ARG(x && y && sums && B > 0 && n > 0, "nppc_offline_laplace_norm: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    NPPC_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * B, s));
+    int gx = per_sample_grid(n, B);
+    sample_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, n, sums);
+    offline_norm_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, n, sums, (double)n, y);
+    NPPC_COUNT_LAUNCH(2);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_pad_offline_laplace_norm(const float* x, int B, int F, int T, int look_ahead, double* sums,
+                                             float* y, void* stream) {
+    NPPC_CHECK_ARG(x && y && sums && B > 0 && F > 0 && T > 0 && look_ahead >= 0, "nppc_pad_offline_laplace_norm: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    NPPC_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * B, s));
+    int gx = per_sample_grid((long long)F * T, B);
+    sample_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, (long long)F * T, sums);
+    pad_norm_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, F, T, look_ahead, sums, y);
+    NPPC_COUNT_LAUNCH(2);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_cumulative_laplace_norm(const float* x, int BC, int F, int T, float* y, void* stream) {
+    NPPC_CHECK_ARG(x && y && BC > 0 && F > 0 && T > 0, "nppc_cumulative_laplace_norm: bad arguments");
+    size_t smem = sizeof(float) * (T + 32);
+    NPPC_CHECK_ARG(smem <= 200 * 1024, "nppc_cumulative_laplace_norm: T=%d too large for the single-CTA scan", T);
+    if (smem > 48 * 1024)
+        NPPC_CUDA_OK(cudaFuncSetAttribute(cumulative_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cumulative_norm_kernel<<<BC, TPB, smem, (cudaStream_t)stream>>>(x, F, T, y);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_unfold(const float* x, int B, int C, int F, int T, int num_neighbor, float* out, void* stream) {
+    NPPC_CHECK_ARG(x && out && B > 0 && C > 0 && F > 0 && T > 0 && num_neighbor >= 0, "nppc_unfold: bad arguments");
+    NPPC_CHECK_ARG(num_neighbor < F, "nppc_unfold: reflect padding needs num_neighbor < F (%d >= %d)", num_neighbor, F);
+    unfold_kernel<<<(unsigned)((long long)B * F * C), TPB, 0, (cudaStream_t)stream>>>(x, C, F, T, num_neighbor, out);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_drop_band(const float* x, int B, int C, int F, int T, int groups, float* out, void* stream) {
+    NPPC_CHECK_ARG(x && out && C > 0 && F > 0 && T > 0, "nppc_drop_band: bad arguments");
+    // feature.py:263 asserts before the num_groups<=1 early-out
+    NPPC_CHECK_ARG(B > groups, "Batch size = %d, num_groups = %d. The batch size should larger than the num_groups.", B, groups);
+    int G = groups <= 1 ? 1 : groups;
+    int Fg = F / G;
+    drop_band_kernel<<<(unsigned)((long long)B * C * Fg), 128, 0, (cudaStream_t)stream>>>(x, B, C, F, T, G, out);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B,
+                                 int F, int Tp, int num_neighbor, int groups, int KP, double* sums, float* xs_f32,
+                                 void* xs_bf16, void* stream) {
+    NPPC_CHECK_ARG(nbr_src && fb && fbr && fbi && sums, "nppc_subband_pack: null pointer");
+    NPPC_CHECK_ARG(xs_f32 || xs_bf16, "nppc_subband_pack: no output requested");
+    int S = 2 * num_neighbor + 4;
+    NPPC_CHECK_ARG(B > 0 && F > 0 && Tp > 0 && num_neighbor >= 1 && num_neighbor < F && KP >= S,
+                   "nppc_subband_pack: bad sizes (B=%d F=%d Tp=%d N=%d KP=%d)", B, F, Tp, num_neighbor, KP);
+    int G = groups <= 1 ? 1 : groups;
+    if (B > 1) NPPC_CHECK_ARG(B > groups, "Batch size = %d, num_groups = %d. The batch size should larger than the num_groups.", B, groups);
+    else G = 1;  // fullsubnet_plus.py:213: drop_band only runs when batch_size > 1
+    cudaStream_t s = (cudaStream_t)stream;
+    NPPC_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * B, s));
+    int gx = per_sample_grid((long long)F * Tp, B);
+    subband_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(nbr_src, fb, fbr, fbi, F, Tp, num_neighbor, sums);
+    long long R = (long long)B * (F / G);
+    size_t smem = sizeof(float) * PK_ROWS * KP * (PK_T + 1);
+    if (smem > 48 * 1024)
+        NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)nppc::cdiv(R, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));
+    subband_pack_kernel<<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, KP, sums, xs_f32,
+                                                (__nv_bfloat16*)xs_bf16);
+    NPPC_COUNT_LAUNCH(2);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_assemble_mask(const float* y, int B, int Fp, int O, int Tp, int look_ahead, float* out, void* stream) {
+    NPPC_CHECK_ARG(y && out && B > 0 && Fp > 0 && O > 0 && Tp > look_ahead && look_ahead >= 0, "nppc_assemble_mask: bad arguments");
+    assemble_kernel<<<(unsigned)((long long)B * O * Fp), 128, 0, (cudaStream_t)stream>>>(y, Fp, O, Tp, look_ahead, out);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}

@@ -1,0 +1,333 @@
+// a12 Gram-Schmidt (complex, with the reference's conjugated coefficient; real variant for inpainting) and
+// a14 NPPC projection / second-moment loss statistics, as TWO HBM passes:
+//   pass 1  gram_kernel : one read of the n (+1: err = gt - pred) vectors -> Hermitian Gram matrix, fp32 per-thread
+//                         partials over short runs, fp64 block reduction + fp64 atomics  (fp64 Gram)
+//   solve   gs_solve    : per sample, replay the reference's MGS recurrences symbolically on coefficient vectors
+//                         (w_i = sum_k a_i[k] x_k) in fp64 -> lower-triangular A, norms, projections, loss terms
+//   pass 2  apply_kernel: out_i = sum_{k<=i} A[i][k] x_k  (fp32 streaming FMA), one read + one write
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int NV_MAX = 13;       // up to 12 directions + err
+constexpr int RUN = 16;          // elements per thread accumulated in fp32 before the fp64 reduction
+
+struct SampleScratch {
+    double G[NV_MAX * NV_MAX * 2];   // Hermitian Gram, row-major complex (re,im); real variant uses .re only
+    float A[12 * 12 * 2];            // coefficient matrix (complex float), row i = direction i
+};
+
+// vector v of sample b: v < n -> x[b][v] ([2][P] for complex, [P] for real); v == n -> err = gt - pred
+template <bool COMPLEX>
+__device__ __forceinline__ void load_vec(const float* __restrict__ x, const float* __restrict__ gt,
+                                         const float* __restrict__ pred, int b, int n, int v, long long P,
+                                         long long p, float& re, float& im) {
+    if (v < n) {
+        const float* base = x + ((size_t)b * n + v) * (COMPLEX ? 2 : 1) * P;
+        re = base[p];
+        im = COMPLEX ? base[P + p] : 0.f;
+    } else {
+        const float* g = gt + (size_t)b * (COMPLEX ? 2 : 1) * P;
+        const float* q = pred + (size_t)b * (COMPLEX ? 2 : 1) * P;
+        re = g[p] - q[p];
+        im = COMPLEX ? (g[P + p] - q[P + p]) : 0.f;
+    }
+}
+
+// Gram rows J0..J1-1 (upper triangle, k >= j) of NV vectors. grid (chunks, B).
+template <bool COMPLEX, int NV, int J0, int J1>
+__global__ void __launch_bounds__(TPB) gram_kernel(const float* __restrict__ x, const float* __restrict__ gt,
+                                                  const float* __restrict__ pred, int n, long long P,
+                                                  SampleScratch* __restrict__ scr) {
+    constexpr int NPAIR = (J1 - J0) * NV - (J1 * (J1 - 1) / 2 - J0 * (J0 - 1) / 2);
+    constexpr int NACC = NPAIR * (COMPLEX ? 2 : 1);
+    __shared__ double red[32];
+    const int b = blockIdx.y;
+    double dacc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) dacc[i] = 0.0;
+    const long long chunk = (long long)TPB * RUN;
+    for (long long base = (long long)blockIdx.x * chunk; base < P; base += (long long)gridDim.x * chunk) {
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+#pragma unroll 2
+        for (int r = 0; r < RUN; ++r) {
+            long long p = base + (long long)r * TPB + threadIdx.x;
+            if (p < P) {
+                float vr[NV], vi[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) load_vec<COMPLEX>(x, gt, pred, b, n, v, P, p, vr[v], vi[v]);
+                int a = 0;
+#pragma unroll
+                for (int j = J0; j < J1; ++j) {
+#pragma unroll
+                    for (int k = j; k < NV; ++k) {
+                        if (COMPLEX) {
+                            acc[a] += vr[j] * vr[k] + vi[j] * vi[k];      // Re conj(x_j) x_k
+                            acc[a + 1] += vr[j] * vi[k] - vi[j] * vr[k];  // Im conj(x_j) x_k
+                            a += 2;
+                        } else {
+                            acc[a] += vr[j] * vr[k];
+                            a += 1;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dacc[i] += (double)acc[i];
+    }
+    // block reduce each accumulator, one atomic per CTA per entry
+    int a = 0;
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+#pragma unroll
+        for (int k = j; k < NV; ++k) {
+            double re = nppc::block_sum(dacc[a], red);
+            double im = 0.0;
+            if (COMPLEX) im = nppc::block_sum(dacc[a + 1], red);
+            a += COMPLEX ? 2 : 1;
+            if (threadIdx.x == 0) {
+                atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2], re);
+                if (COMPLEX) atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2 + 1], im);
+            }
+        }
+    }
+}
+
+struct cd { double x, y; };
+__device__ __forceinline__ cd cmul(cd a, cd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cd cconj(cd a) { return {a.x, -a.y}; }
+
+// One thread per sample. mode: do_gs (orthogonalise; else A = identity), has_err (loss statistics).
+template <bool COMPLEX>
+__global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n, int do_gs, int has_err,
+                                float* __restrict__ err_norm, float* __restrict__ err_proj,
+                                float* __restrict__ w_norms, float* __restrict__ reconst_err,
+                                float* __restrict__ second_moment) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    SampleScratch& s = scr[b];
+    auto G = [&](int j, int k) -> cd {  // full Hermitian access from the stored upper triangle
+        if (j <= k) return cd{s.G[(j * NV_MAX + k) * 2], s.G[(j * NV_MAX + k) * 2 + 1]};
+        return cd{s.G[(k * NV_MAX + j) * 2], -s.G[(k * NV_MAX + j) * 2 + 1]};
+    };
+    cd ahat[12][12];  // normalised coefficient vectors of the previous directions
+    cd v[12][12];     // v_j = G * ahat_j
+    double nu[12];
+    for (int i = 0; i < n; ++i) {
+        cd a[12];
+        for (int k = 0; k < n; ++k) a[k] = cd{k == i ? 1.0 : 0.0, 0.0};
+        if (do_gs) {
+            for (int j = 0; j < i; ++j) {
+                // reference coefficient: c = sum_p conj(w[p]) * what_j[p] = sum_k conj(a[k]) (G ahat_j)[k]
+                cd c{0.0, 0.0};
+                for (int k = 0; k <= i; ++k) { cd t = cmul(cconj(a[k]), v[j][k]); c.x += t.x; c.y += t.y; }
+                for (int k = 0; k <= j; ++k) { cd t = cmul(ahat[j][k], c); a[k].x -= t.x; a[k].y -= t.y; }
+            }
+        }
+        // ||w_i||^2 = a^H G a
+        double nrm2 = 0.0;
+        for (int k = 0; k <= i; ++k) {
+            cd gk{0.0, 0.0};
+            for (int l = 0; l <= i; ++l) { cd t = cmul(G(k, l), a[l]); gk.x += t.x; gk.y += t.y; }
+            cd t = cmul(cconj(a[k]), gk);
+            nrm2 += t.x;
+        }
+        double nrm = sqrt(nrm2 > 0.0 ? nrm2 : 0.0);
+        nu[i] = nrm;
+        for (int k = 0; k < n; ++k) {
+            ahat[i][k] = (k <= i) ? cd{a[k].x / nrm, a[k].y / nrm} : cd{0.0, 0.0};  // no epsilon (pc_wrapper.py:37)
+            s.A[(i * 12 + k) * 2] = (k <= i) ? (float)a[k].x : 0.f;
+            s.A[(i * 12 + k) * 2 + 1] = (k <= i) ? (float)a[k].y : 0.f;
+        }
+        for (int k = 0; k < n; ++k) {
+            cd gk{0.0, 0.0};
+            for (int l = 0; l <= i; ++l) { cd t = cmul(G(k, l), ahat[i][l]); gk.x += t.x; gk.y += t.y; }
+            v[i][k] = gk;
+        }
+        if (has_err) {
+            // trainer.py:270-295
+            double eps_n = sqrt(fmax(G(n, n).x, 0.0));
+            cd pr{0.0, 0.0};
+            for (int k = 0; k <= i; ++k) { cd t = cmul(cconj(a[k]), G(k, n)); pr.x += t.x; pr.y += t.y; }
+            double den = (nrm + 1e-8) * (eps_n + 1e-8);
+            pr.x /= den; pr.y /= den;
+            err_proj[((size_t)b * n + i) * 2] = (float)pr.x;
+            err_proj[((size_t)b * n + i) * 2 + 1] = (float)pr.y;
+            double wn = nrm / (eps_n + 1e-8);
+            w_norms[(size_t)b * n + i] = (float)wn;
+            double pm2 = pr.x * pr.x + pr.y * pr.y;
+            double d = wn * wn - pm2;
+            second_moment[(size_t)b * n + i] = (float)(d * d);
+            nu[i] = pm2;
+        }
+    }
+    if (has_err) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += nu[i];
+        reconst_err[b] = (float)(1.0 - acc);
+        err_norm[b] = (float)sqrt(fmax(G(n, n).x, 0.0));
+    }
+    (void)COMPLEX;
+}
+
+// out_i[p] = sum_{k<=i} A[i][k] x_k[p]. grid (chunks, B)
+template <bool COMPLEX, int N>
+__global__ void __launch_bounds__(TPB) apply_kernel(const float* __restrict__ x, long long P,
+                                                   const SampleScratch* __restrict__ scr, float* __restrict__ out) {
+    __shared__ float2 A[N][N];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+        int r = i / N, c = i % N;
+        A[r][c] = make_float2(scr[b].A[(r * 12 + c) * 2], scr[b].A[(r * 12 + c) * 2 + 1]);
+    }
+    __syncthreads();
+    const size_t vs = (size_t)(COMPLEX ? 2 : 1) * P;
+    const float* xb = x + (size_t)b * N * vs;
+    float* ob = out + (size_t)b * N * vs;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        float xr[N], xi[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            xr[k] = xb[k * vs + p];
+            xi[k] = COMPLEX ? xb[k * vs + P + p] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float wr = 0.f, wi = 0.f;
+#pragma unroll
+            for (int k = 0; k <= i; ++k) {
+                float2 a = A[i][k];
+                if (COMPLEX) {
+                    wr += a.x * xr[k] - a.y * xi[k];
+                    wi += a.x * xi[k] + a.y * xr[k];
+                } else {
+                    wr += a.x * xr[k];
+                }
+            }
+            if (i == 0) { wr = xr[0]; wi = xi[0]; }  // direction 0 is returned untouched (bit-exact)
+            ob[i * vs + p] = wr;
+            if (COMPLEX) ob[i * vs + P + p] = wi;
+        }
+    }
+}
+
+int chunks_for(long long P, int B) {
+    long long per = ((long long)TPB * RUN);
+    long long c = (P + per - 1) / per;
+    long long want = (2LL * nppc::sm_count() + B - 1) / B;  // ~2 CTAs per SM overall
+    if (c > want) c = want;
+    return (int)(c < 1 ? 1 : c);
+}
+
+template <bool COMPLEX, int NV>
+int launch_gram(const float* x, const float* gt, const float* pred, int B, int n, long long P, SampleScratch* scr,
+                cudaStream_t s) {
+    dim3 grid(chunks_for(P, B), B);
+    constexpr int NPAIR = NV * (NV + 1) / 2;
+    if constexpr (NPAIR * (COMPLEX ? 2 : 1) <= 72) {
+        gram_kernel<COMPLEX, NV, 0, NV><<<grid, TPB, 0, s>>>(x, gt, pred, n, P, scr);
+        NPPC_COUNT_LAUNCH(1);
+    } else {  // split the upper triangle in two row bands to stay in registers
+        constexpr int JM = NV / 3 > 0 ? NV / 3 : 1;
+        gram_kernel<COMPLEX, NV, 0, JM><<<grid, TPB, 0, s>>>(x, gt, pred, n, P, scr);
+        gram_kernel<COMPLEX, NV, JM, NV><<<grid, TPB, 0, s>>>(x, gt, pred, n, P, scr);
+        NPPC_COUNT_LAUNCH(2);
+    }
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+template <bool COMPLEX>
+int dispatch_gram(int NV, const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                  SampleScratch* scr, cudaStream_t s) {
+    switch (NV) {
+#define C(v) case v: return launch_gram<COMPLEX, v>(x, gt, pred, B, n, P, scr, s);
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13)
+#undef C
+    }
+    nppc::set_error("gram: unsupported vector count %d", NV);
+    return NPPC_ERR_UNSUPPORTED;
+}
+
+template <bool COMPLEX>
+int dispatch_apply(int n, const float* x, int B, long long P, const SampleScratch* scr, float* out, cudaStream_t s) {
+    long long c = (P + TPB - 1) / TPB;
+    long long want = (4LL * nppc::sm_count() + B - 1) / B;
+    if (c > want) c = want;
+    dim3 grid((unsigned)(c < 1 ? 1 : c), B);
+    switch (n) {
+#define C(v) case v: apply_kernel<COMPLEX, v><<<grid, TPB, 0, s>>>(x, P, scr, out); break;
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12)
+#undef C
+        default:
+            nppc::set_error("gram_schmidt: unsupported n_dirs %d (1..12)", n);
+            return NPPC_ERR_UNSUPPORTED;
+    }
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+template <bool COMPLEX>
+int run(const float* x, const float* gt, const float* pred, int B, int n, long long P, void* scratch, int do_gs,
+        float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
+        cudaStream_t s) {
+    const int has_err = gt != nullptr;
+    SampleScratch* scr = (SampleScratch*)scratch;
+    NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
+    int rc = dispatch_gram<COMPLEX>(n + has_err, x, gt, pred, B, n, P, scr, s);
+    if (rc) return rc;
+    gs_solve_kernel<COMPLEX><<<nppc::cdiv(B, 32), 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms,
+                                                           reconst_err, second_moment);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    if (out) return dispatch_apply<COMPLEX>(n, x, B, P, scr, out, s);
+    return NPPC_OK;
+}
+
+}  // namespace
+
+extern "C" size_t nppc_gs_scratch_bytes(int B, int n) {
+    (void)n;
+    return sizeof(SampleScratch) * (size_t)(B > 0 ? B : 0);
+}
+
+#define GS_ARGS_OK(name)                                                                          \
+    NPPC_CHECK_ARG(x && scratch && B > 0 && P > 0, name ": bad arguments");                        \
+    NPPC_CHECK_ARG(n >= 1 && n <= 12, name ": n_dirs must be in 1..12 (got %d)", n)
+
+extern "C" int nppc_gram_schmidt_complex(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream) {
+    GS_ARGS_OK("nppc_gram_schmidt_complex");
+    NPPC_CHECK_ARG(out != nullptr, "nppc_gram_schmidt_complex: null output");
+    return run<true>(x, nullptr, nullptr, B, n, P, scratch, 1, out, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int nppc_gram_schmidt_real(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream) {
+    GS_ARGS_OK("nppc_gram_schmidt_real");
+    NPPC_CHECK_ARG(out != nullptr, "nppc_gram_schmidt_real: null output");
+    return run<false>(x, nullptr, nullptr, B, n, P, scratch, 1, out, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int nppc_gs_loss_fused(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                                  void* scratch, float* w_mat, float* err_norm, float* err_proj, float* w_norms,
+                                  float* reconst_err, float* second_moment_mse, void* stream) {
+    GS_ARGS_OK("nppc_gs_loss_fused");
+    NPPC_CHECK_ARG(gt && pred && w_mat && err_norm && err_proj && w_norms && reconst_err && second_moment_mse,
+                   "nppc_gs_loss_fused: null pointer");
+    return run<true>(x, gt, pred, B, n, P, scratch, 1, w_mat, err_norm, err_proj, w_norms, reconst_err, second_moment_mse,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int nppc_projection_loss(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                                    void* scratch, float* err_norm, float* err_proj, float* w_norms,
+                                    float* reconst_err, float* second_moment_mse, void* stream) {
+    GS_ARGS_OK("nppc_projection_loss");
+    NPPC_CHECK_ARG(gt && pred && err_norm && err_proj && w_norms && reconst_err && second_moment_mse,
+                   "nppc_projection_loss: null pointer");
+    return run<true>(x, gt, pred, B, n, P, scratch, 0, nullptr, err_norm, err_proj, w_norms, reconst_err, second_moment_mse,
+                     (cudaStream_t)stream);
+}

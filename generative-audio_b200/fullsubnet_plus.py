@@ -1,0 +1,105 @@
+"""FullSubNet+ backbone (a8) on B200: mirrors FullSubNet_Plus (fullsubnet_plus.py:45-230).
+
+Data flow per forward (all device-resident, fp32 unless noted):
+  pad+offline-norm (1 fused kernel per plane) -> TSSE -> TCN (torch library ops, "next" row N2)
+  -> fused sub-band pack (unfold ++ cat ++ norm ++ drop_band, written time-major [T',R,64]; bf16 for the
+     tensor-core LSTM) -> 2-layer LSTM + fc kernels -> mask assembly kernel.
+The [B,F,34,T'] sub-band tensor of the reference is never materialised."""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import FullSubNetPlusConfig
+from .modules import ChannelTimeSenseSELayer, SequenceModel
+
+KP = 64  # padded feature width of the packed LSTM input (34 real features)
+_IMPL = {"f32": 0, "tc": 1}
+
+
+class FullSubNet_Plus(nn.Module):
+    def __init__(self, config: Optional[FullSubNetPlusConfig] = None, lstm_impl: str = "tc"):
+        super().__init__()
+        if config is None:
+            config = FullSubNetPlusConfig()
+        self.num_freqs = config.num_freqs
+        self.look_ahead = config.look_ahead
+        self.sequence_model = config.sequence_model
+        self.fb_num_neighbors = config.fb_num_neighbors
+        self.sb_num_neighbors = config.sb_num_neighbors
+        self.norm_type = config.norm_type
+        self.num_groups_in_drop_band = config.num_groups_in_drop_band
+        self.output_size = config.output_size
+        self.kersize = config.kersize
+        self.lstm_impl = lstm_impl
+        assert self.sequence_model in ("GRU", "LSTM", "TCN"), f"{self.__class__.__name__} only support GRU, LSTM and TCN."
+        if self.sequence_model != "LSTM":
+            raise NotImplementedError("only the LSTM sub-band model (every shipped config) is built")
+        if config.subband_num != 1 or config.channel_attention_model != "TSSE" or config.fb_num_neighbors != 0:
+            raise NotImplementedError("only subband_num=1, TSSE attention, fb_num_neighbors=0 (every shipped config) are built")
+        if self.norm_type not in ("offline_laplace_norm", "cumulative_laplace_norm"):
+            raise NotImplementedError(f"norm_type {self.norm_type}")
+        if 2 * self.sb_num_neighbors + 4 > KP:
+            raise NotImplementedError("sb_num_neighbors too large for the packed LSTM input")
+        C = self.num_freqs
+        self.channel_attention = ChannelTimeSenseSELayer(C, kersize=self.kersize)
+        self.channel_attention_real = ChannelTimeSenseSELayer(C, kersize=self.kersize)
+        self.channel_attention_imag = ChannelTimeSenseSELayer(C, kersize=self.kersize)
+        self.fb_input_size = C
+        self._build_fullband(C)
+        self.sb_model = SequenceModel(input_size=(self.sb_num_neighbors * 2 + 1) + 3 * (self.fb_num_neighbors * 2 + 1),
+                                      output_size=self.output_size, hidden_size=config.sb_model_hidden_size, num_layers=2,
+                                      bidirectional=False, sequence_model="LSTM",
+                                      output_activate_function=config.sb_output_activate_function)
+
+    def _build_fullband(self, input_size):
+        kw = dict(input_size=input_size, output_size=self.num_freqs, hidden_size=512, num_layers=2, bidirectional=False,
+                  sequence_model="TCN", output_activate_function="ReLU")
+        self.fb_model = SequenceModel(**kw)
+        self.fb_model_real = SequenceModel(**kw)
+        self.fb_model_imag = SequenceModel(**kw)
+
+    # -- helpers --------------------------------------------------------------------------------------
+    def _pad_norm(self, x):
+        """F.pad(x,[0,look_ahead]) + self.norm(x), x [B,1,F,T] -> [B,F,T']."""
+        if self.norm_type == "offline_laplace_norm":
+            return ops.pad_offline_laplace_norm(x, self.look_ahead)
+        xp = torch.nn.functional.pad(x, [0, self.look_ahead]).contiguous()
+        return ops.cumulative_laplace_norm(xp)[:, 0]
+
+    def _subband(self, nbr_src, fb, fbr, fbi):
+        """-> (y [R,O,T'], F') from the four [B,F,T'] planes."""
+        B, F, Tp = fb.shape
+        impl = _IMPL[self.lstm_impl]
+        dt = torch.bfloat16 if impl == 1 else torch.float32
+        G = self.num_groups_in_drop_band
+        if self.norm_type == "offline_laplace_norm":
+            xs = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt)
+            Fp = xs.shape[1] // B
+        else:
+            # explicit route through the standalone kernels (cumulative norm is not fused into the packer)
+            n = self.sb_num_neighbors
+            parts = [ops.unfold(nbr_src[:, None].contiguous(), n).reshape(B, F, 2 * n + 1, Tp)]
+            parts += [v.reshape(B, F, 1, Tp) for v in (fb, fbr, fbi)]
+            sb = ops.cumulative_laplace_norm(torch.cat(parts, dim=2).contiguous())
+            if B > 1:
+                sb = ops.drop_band(sb.permute(0, 2, 1, 3).contiguous(), G).permute(0, 2, 1, 3)
+            Fp = sb.shape[1]
+            S = sb.shape[2]
+            xs = torch.zeros(Tp, B * Fp, KP, device=fb.device, dtype=dt)
+            xs[:, :, :S] = sb.reshape(B * Fp, S, Tp).permute(2, 0, 1).to(dt)
+        return self.sb_model.lstm_forward(xs, impl), Fp
+
+    @torch.no_grad()
+    def forward(self, noisy_mag, noisy_real, noisy_imag):
+        """[B,1,F,T] x3 -> compressed cRM [B,2,F',T] (fullsubnet_plus.py:143-230)."""
+        assert noisy_mag.dim() == 4
+        B, Cc, F, T = noisy_mag.shape
+        assert Cc == 1, f"{self.__class__.__name__} takes the mag feature as inputs."
+        fb_in = self.channel_attention(self._pad_norm(noisy_mag))
+        fb_out = self.fb_model(fb_in)
+        fbr_out = self.fb_model_real(self.channel_attention_real(self._pad_norm(noisy_real)))
+        fbi_out = self.fb_model_imag(self.channel_attention_imag(self._pad_norm(noisy_imag)))
+        y, Fp = self._subband(fb_in.contiguous(), fb_out.contiguous(), fbr_out.contiguous(), fbi_out.contiguous())
+        return ops.assemble_mask(y, B, Fp, self.look_ahead)

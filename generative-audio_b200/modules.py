@@ -1,0 +1,120 @@
+"""Full-band modules of FullSubNet+ (TSSE attention a3, TCN sequence model a4) and the parameter container of
+the sub-band LSTM (a7), with the reference's parameter names so state_dicts are interchangeable.
+
+Round-1 status: a3/a4 run on stock torch CUDA ops (cuDNN/cuBLAS library calls — the reference's own GPU path,
+≈2-3 % of the FLOPs; SURVEY.md §7 step 6, §8f row N2 "next").  The LSTM is never run through nn.LSTM: its
+weights feed the hand-written kernels via ops.LstmPlan."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+TCN_DILATIONS = (1, 2, 5, 9, 1, 2, 5, 9)  # sequence_model.py:48-57
+
+
+class _ConvPoolRelu(nn.Sequential):
+    """Keeps the reference's `smallConv1d.0.weight` key layout (attention_model.py:57-71)."""
+
+    def __init__(self, channels, k):
+        super().__init__(nn.Conv1d(channels, channels, kernel_size=k, groups=channels))
+
+
+class ChannelTimeSenseSELayer(nn.Module):
+    """attention_model.py:43-98."""
+
+    def __init__(self, num_channels, reduction_ratio=2, kersize=(3, 5, 10)):
+        super().__init__()
+        self.smallConv1d = _ConvPoolRelu(num_channels, kersize[0])
+        self.middleConv1d = _ConvPoolRelu(num_channels, kersize[1])
+        self.largeConv1d = _ConvPoolRelu(num_channels, kersize[2])
+        self.feature_concate_fc = nn.Linear(3, 1, bias=True)
+        self.fc1 = nn.Linear(num_channels, num_channels // reduction_ratio, bias=True)
+        self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
+
+    def forward(self, x):  # [B,C,T]
+        feats = [torch.relu(m[0](x).mean(dim=-1)) for m in (self.smallConv1d, self.middleConv1d, self.largeConv1d)]
+        s = self.feature_concate_fc(torch.stack(feats, dim=-1))[..., 0]
+        g = torch.sigmoid(self.fc2(torch.relu(self.fc1(s))))
+        return x * g[:, :, None]
+
+
+class TCNBlock(nn.Module):
+    """causal_conv.py:67-108 (use_skip_connection=True, causal=False)."""
+
+    def __init__(self, in_channels=257, hidden_channel=512, out_channels=257, kernel_size=3, dilation=1):
+        super().__init__()
+        self.conv1x1 = nn.Conv1d(in_channels, hidden_channel, 1)
+        self.prelu1 = nn.PReLU()
+        self.norm1 = nn.GroupNorm(1, hidden_channel, eps=1e-8)
+        self.depthwise_conv = nn.Conv1d(hidden_channel, hidden_channel, kernel_size=kernel_size, stride=1,
+                                        groups=hidden_channel, padding=(dilation * (kernel_size - 1)) // 2,
+                                        dilation=dilation)
+        self.prelu2 = nn.PReLU()
+        self.norm2 = nn.GroupNorm(1, hidden_channel, eps=1e-8)
+        self.sconv = nn.Conv1d(hidden_channel, out_channels, 1)
+
+    def forward(self, x):
+        y = self.norm1(self.prelu1(self.conv1x1(x)))
+        y = self.norm2(self.prelu2(self.depthwise_conv(y)))
+        return x + self.sconv(y)
+
+
+class SequenceModel(nn.Module):
+    """sequence_model.py:5-123.  "TCN": runnable module.  "LSTM": parameter container whose forward goes through
+    the hand-written kernels (input must already be packed time-major by ops.subband_pack)."""
+
+    def __init__(self, input_size, output_size, hidden_size, num_layers, bidirectional, sequence_model="GRU",
+                 output_activate_function="Tanh"):
+        super().__init__()
+        self.sequence_model_type = sequence_model
+        if sequence_model == "LSTM":
+            if bidirectional or num_layers != 2:
+                raise NotImplementedError("only the 2-layer unidirectional LSTM of FullSubNet+ is built")
+            self.sequence_model = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
+                                          batch_first=True, bidirectional=False)
+            self.fc_output_layer = nn.Linear(hidden_size, output_size)
+        elif sequence_model == "TCN":
+            self.sequence_model = nn.Sequential(*[TCNBlock(input_size, 512, input_size, dilation=d) for d in TCN_DILATIONS],
+                                                nn.ReLU())
+            self.fc_output_layer = nn.Linear(input_size, output_size)
+        else:
+            raise NotImplementedError(f"Not implemented {sequence_model}")
+        if output_activate_function:
+            if output_activate_function == "ReLU":
+                self.activate_function = nn.ReLU()
+            elif output_activate_function == "Tanh":
+                self.activate_function = nn.Tanh()
+            elif output_activate_function == "ReLU6":
+                self.activate_function = nn.ReLU6()
+            else:
+                raise NotImplementedError(f"Not implemented activation function {output_activate_function}")
+        self.output_activate_function = output_activate_function
+        self._plan = None
+        self._plan_key = None
+
+    # ---- TCN path ----
+    def forward(self, x):
+        if self.sequence_model_type != "TCN":
+            raise RuntimeError("the LSTM SequenceModel runs through lstm_forward(xs) on packed input")
+        o = self.fc_output_layer(self.sequence_model(x).permute(0, 2, 1))
+        if self.output_activate_function:
+            o = self.activate_function(o)
+        return o.permute(0, 2, 1)
+
+    # ---- LSTM path ----
+    def _lstm_plan(self):
+        ps = [getattr(self.sequence_model, f"{k}_l{l}") for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        ps += [self.fc_output_layer.weight, self.fc_output_layer.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._plan is None or key != self._plan_key:
+            l0, l1 = ps[0:4], ps[4:8]
+            self._plan = ops.LstmPlan(l0[0], l0[1], l0[2], l0[3], l1[0], l1[1], l1[2], l1[3], ps[8], ps[9])
+            self._plan_key = key
+        return self._plan
+
+    def lstm_forward(self, xs, impl: int):
+        """xs [T', R, KP] -> [R, O, T'] (the layout SequenceModel.forward returns, sequence_model.py:122)."""
+        if self.output_activate_function:
+            raise NotImplementedError("sb_output_activate_function is False in every reference config")
+        return self._lstm_plan().forward(xs, impl)

@@ -1,0 +1,71 @@
+"""NPPCModel (a13): drop-in for nppc_audio/nppc_model.py:25-132 — same constructor config, forward /
+get_pred_crm signatures, sub-module attribute names and state_dict keys; CUDA only (no CPU fallback)."""
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import NPPCModelConfig
+from .fullsubnet_plus import FullSubNet_Plus
+from .pc_wrapper import AudioPCWrapper
+
+
+def load_pretrained_model(model_path, model_config, lstm_impl="tc") -> FullSubNet_Plus:
+    """utils.load_pretrained_model / preload_model (utils.py:82-104): `{"model": state_dict}` .tar, strict=False."""
+    model = FullSubNet_Plus(model_config, lstm_impl=lstm_impl)
+    p = Path(model_path).expanduser().absolute()
+    assert p.exists(), f"The file {p.as_posix()} is not exist. please check path."
+    ck = torch.load(p.as_posix(), map_location="cpu")
+    model.load_state_dict(ck["model"], strict=False)
+    return model
+
+
+class NPPCModel(nn.Module):
+    def __init__(self, config: NPPCModelConfig):
+        super().__init__()
+        self.config = config
+        if config.device != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("generative-audio_b200.NPPCModel runs on CUDA (sm_100a) only: there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.pretrained_restoration_model = load_pretrained_model(
+            config.pretrained_restoration_model_path, config.pretrained_restoration_model_configuration, config.lstm_impl)
+        self.pretrained_restoration_model.to(self.device).eval()
+        self.audio_pc_wrapper = AudioPCWrapper(config.audio_pc_wrapper_configuration, lstm_impl=config.lstm_impl)
+        self.audio_pc_wrapper.to(self.device)
+
+    def _stft(self, wave):
+        c = self.config.stft_configuration
+        return ops.stft_mri(wave.to(self.device, non_blocking=True), c.nfft, c.hop_length, c.win_length)
+
+    @torch.no_grad()
+    def forward_stages(self, noisy_waveform: torch.Tensor):
+        """STFT -> frozen backbone -> decompress + conj(M)*N (utils.py:241-249 quirk) -> PC head (pre-Gram-Schmidt).
+        Returns (head [B,n,2,F',T], pred_crm [B,2,F,T])."""
+        mag, real, imag = self._stft(noisy_waveform)
+        pred_crm = self.pretrained_restoration_model(mag, real, imag)
+        emag, ereal, eimag = ops.crm_decompress_apply(pred_crm, real, imag, conj=True)
+        head = self.audio_pc_wrapper.head(mag, real, imag, emag[:, None], ereal[:, None], eimag[:, None])
+        return head, pred_crm
+
+    @torch.no_grad()
+    def forward(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
+        """noisy_waveform [B, L] -> w_mat [B, n_dirs, 2, F', T]."""
+        head, _ = self.forward_stages(noisy_waveform)
+        return ops.gram_schmidt_complex(head)
+
+    @torch.no_grad()
+    def get_pred_crm(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
+        """compressed cRM of the frozen backbone, [B,2,F,T] (nppc_model.py:117-132)."""
+        mag, real, imag = self._stft(noisy_waveform)
+        return self.pretrained_restoration_model(mag, real, imag)
+
+    @torch.no_grad()
+    def enhance(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
+        """Enhance-only pipeline (BASELINE config #2; model_validator.py:84-133 == utils.py:37-72):
+        STFT -> backbone -> decompress -> M*N -> iSTFT(length=L)."""
+        c = self.config.stft_configuration
+        mag, real, imag = self._stft(noisy_waveform)
+        crm = self.pretrained_restoration_model(mag, real, imag)
+        _, er, ei = ops.crm_decompress_apply(crm, real, imag, conj=False, want_mag=False)
+        return ops.istft(er, ei, noisy_waveform.shape[-1], c.nfft, c.hop_length)

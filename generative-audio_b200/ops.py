@@ -1,0 +1,303 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the current stream (plumbing);
+every op below is one or more hand-written sm_100a kernels.  CUDA tensors only — CPU tensors raise."""
+import torch
+
+from . import _lib
+
+_BF16 = torch.bfloat16
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("generative-audio_b200 ops are CUDA-only (no CPU fallback); got a CPU tensor")
+        if not t.is_contiguous():
+            raise RuntimeError("generative-audio_b200 ops need contiguous tensors")
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(_lib.load().nppc_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().nppc_reset_launch_count()
+
+
+def stft_mri(wave: torch.Tensor, n_fft: int = 512, hop: int = 256, win: int = 512):
+    """utils.prepare_input_from_waveform (utils.py:107-147): wave [B,L] -> mag, real, imag each [B,1,F,T]."""
+    if wave.dim() == 1:
+        wave = wave[None]
+    if win != n_fft:
+        raise AssertionError("win_length must equal n_fft (all reference configs do)")
+    wave = _f32(wave)
+    _chk(wave)
+    B, L = wave.shape
+    F, T = n_fft // 2 + 1, 1 + L // hop
+    out = torch.empty(3, B, 1, F, T, device=wave.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_stft_mri(wave.data_ptr(), B, L, n_fft, hop, out[0].data_ptr(), out[1].data_ptr(),
+                                         out[2].data_ptr(), _stream()), "nppc_stft_mri")
+    return out[0], out[1], out[2]
+
+
+def istft(real: torch.Tensor, imag: torch.Tensor, length: int, n_fft: int = 512, hop: int = 256):
+    """torch.istft(center=True, window=hann, length=length) (utils.py:60-70): [B,F,T] x2 -> [B,length]."""
+    real, imag = _f32(real), _f32(imag)
+    _chk(real, imag)
+    B, F, T = real.shape
+    out = torch.empty(B, length, device=real.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_istft(real.data_ptr(), imag.data_ptr(), B, T, n_fft, hop, length, out.data_ptr(),
+                                      _stream()), "nppc_istft")
+    return out
+
+
+def crm_decompress_apply(crm: torch.Tensor, real: torch.Tensor, imag: torch.Tensor, conj: bool, want_mag=True):
+    """decompress_cIRM + mask apply. crm [B,2,F,T] compressed; real/imag [B,(1,)F,T] -> (mag, real, imag) [B,F,T]."""
+    crm, real, imag = _f32(crm), _f32(real), _f32(imag)
+    _chk(crm, real, imag)
+    B, two, F, T = crm.shape
+    assert two == 2
+    out = torch.empty(3, B, F, T, device=crm.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_crm_decompress_apply(crm.data_ptr(), real.data_ptr(), imag.data_ptr(), B, F * T,
+                                                     1 if conj else 0, out[0].data_ptr() if want_mag else 0,
+                                                     out[1].data_ptr(), out[2].data_ptr(), _stream()),
+               "nppc_crm_decompress_apply")
+    return out[0], out[1], out[2]
+
+
+def decompress_cirm(m: torch.Tensor):
+    m = _f32(m)
+    _chk(m)
+    out = torch.empty_like(m)
+    _lib.check(_lib.load().nppc_decompress_cirm(m.data_ptr(), m.numel(), out.data_ptr(), _stream()), "nppc_decompress_cirm")
+    return out
+
+
+def build_cirm(nr, ni, cr, ci):
+    """build_complex_ideal_ratio_mask (mask.py:24-41): [B,F,T] x4 -> compressed gt [B,2,F,T]."""
+    nr, ni, cr, ci = (_f32(v) for v in (nr, ni, cr, ci))
+    _chk(nr, ni, cr, ci)
+    B, F, T = nr.shape
+    gt = torch.empty(B, 2, F, T, device=nr.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_build_cirm(nr.data_ptr(), ni.data_ptr(), cr.data_ptr(), ci.data_ptr(), B, F * T,
+                                           gt.data_ptr(), _stream()), "nppc_build_cirm")
+    return gt
+
+
+def offline_laplace_norm(x: torch.Tensor):
+    """BaseModel.offline_laplace_norm (base_model.py:210-224) for x [B, ...]."""
+    x = _f32(x)
+    _chk(x)
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    sums = torch.empty(B, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_offline_laplace_norm(x.data_ptr(), B, x.numel() // B, sums.data_ptr(), y.data_ptr(),
+                                                     _stream()), "nppc_offline_laplace_norm")
+    return y
+
+
+def pad_offline_laplace_norm(x: torch.Tensor, look_ahead: int):
+    """F.pad(x,[0,la]) + offline_laplace_norm fused: x [B,1,F,T] or [B,F,T] -> [B,F,T+la]."""
+    x = _f32(x)
+    _chk(x)
+    if x.dim() == 4:
+        x = x[:, 0]
+    B, F, T = x.shape
+    y = torch.empty(B, F, T + look_ahead, device=x.device, dtype=torch.float32)
+    sums = torch.empty(B, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_pad_offline_laplace_norm(x.data_ptr(), B, F, T, look_ahead, sums.data_ptr(),
+                                                         y.data_ptr(), _stream()), "nppc_pad_offline_laplace_norm")
+    return y
+
+
+def cumulative_laplace_norm(x: torch.Tensor):
+    """BaseModel.cumulative_laplace_norm (base_model.py:227-257): x [B,C,F,T]."""
+    x = _f32(x)
+    _chk(x)
+    B, Cc, F, T = x.shape
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().nppc_cumulative_laplace_norm(x.data_ptr(), B * Cc, F, T, y.data_ptr(), _stream()),
+               "nppc_cumulative_laplace_norm")
+    return y
+
+
+def unfold(x: torch.Tensor, num_neighbor: int):
+    """BaseModel.unfold (base_model.py:15-46): [B,C,F,T] -> [B,F,C,2n+1,T], bit-exact."""
+    assert x.dim() == 4, f"The dim of input is {x.dim()}. It should be four dim."
+    x = _f32(x)
+    _chk(x)
+    B, Cc, F, T = x.shape
+    out = torch.empty(B, F, Cc, 2 * num_neighbor + 1, T, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_unfold(x.data_ptr(), B, Cc, F, T, num_neighbor, out.data_ptr(), _stream()), "nppc_unfold")
+    return out
+
+
+def drop_band(x: torch.Tensor, num_groups: int = 2):
+    """drop_band (feature.py:254-285): [B,C,F,T] -> [B,C,F//G,T], bit-exact; asserts B > G."""
+    x = _f32(x)
+    _chk(x)
+    B, Cc, F, T = x.shape
+    G = max(num_groups, 1)
+    out = torch.empty(B, Cc, F // G, T, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_drop_band(x.data_ptr(), B, Cc, F, T, num_groups, out.data_ptr(), _stream()), "nppc_drop_band")
+    return out
+
+
+def _gs_scratch(B, n, device):
+    nbytes = _lib.load().nppc_gs_scratch_bytes(B, n)
+    return torch.empty(nbytes, device=device, dtype=torch.uint8)
+
+
+def gram_schmidt_complex(x: torch.Tensor):
+    """gram_schmidt_to_crm (pc_wrapper.py:8-44): x [B,n,2,F,T] -> same."""
+    x = _f32(x)
+    _chk(x)
+    B, n = x.shape[:2]
+    assert x.shape[2] == 2
+    P = x[0, 0, 0].numel()
+    out = torch.empty_like(x)
+    scr = _gs_scratch(B, n, x.device)
+    _lib.check(_lib.load().nppc_gram_schmidt_complex(x.data_ptr(), B, n, P, scr.data_ptr(), out.data_ptr(), _stream()),
+               "nppc_gram_schmidt_complex")
+    return out
+
+
+def gram_schmidt_real(x: torch.Tensor):
+    """gram_schmidt_to_spec_mag (inpainting/nppc/pc_wrapper.py:43-59): x [B,n,...] -> same."""
+    x = _f32(x)
+    _chk(x)
+    B, n = x.shape[:2]
+    P = x[0, 0].numel()
+    out = torch.empty_like(x)
+    scr = _gs_scratch(B, n, x.device)
+    _lib.check(_lib.load().nppc_gram_schmidt_real(x.data_ptr(), B, n, P, scr.data_ptr(), out.data_ptr(), _stream()),
+               "nppc_gram_schmidt_real")
+    return out
+
+
+def _loss_outputs(B, n, device):
+    f = dict(device=device, dtype=torch.float32)
+    return (torch.empty(B, **f), torch.empty(B, n, 2, **f), torch.empty(B, n, **f), torch.empty(B, **f),
+            torch.empty(B, n, **f))
+
+
+def gs_loss_fused(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """Gram-Schmidt + loss statistics in two HBM passes. head [B,n,2,F,T]; gt/pred [B,2,F,T]."""
+    head, gt, pred = _f32(head), _f32(gt), _f32(pred)
+    _chk(head, gt, pred)
+    B, n = head.shape[:2]
+    P = head[0, 0, 0].numel()
+    assert gt.shape == pred.shape and gt[0, 0].numel() == P
+    w = torch.empty_like(head)
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs(B, n, head.device)
+    scr = _gs_scratch(B, n, head.device)
+    _lib.check(_lib.load().nppc_gs_loss_fused(head.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, scr.data_ptr(),
+                                              w.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(), w_norms.data_ptr(),
+                                              reconst.data_ptr(), sm.data_ptr(), _stream()), "nppc_gs_loss_fused")
+    return w, dict(err_norm=err_norm, err_proj=torch.view_as_complex(err_proj), w_norms=w_norms, reconst_err=reconst,
+                   second_moment_mse=sm)
+
+
+def projection_loss(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """Loss statistics of NPPCAudioTrainer.base_step (trainer.py:259-298) for an explicit w_mat."""
+    w_mat, gt, pred = _f32(w_mat), _f32(gt), _f32(pred)
+    _chk(w_mat, gt, pred)
+    B, n = w_mat.shape[:2]
+    P = w_mat[0, 0, 0].numel()
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs(B, n, w_mat.device)
+    scr = _gs_scratch(B, n, w_mat.device)
+    _lib.check(_lib.load().nppc_projection_loss(w_mat.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, scr.data_ptr(),
+                                                err_norm.data_ptr(), err_proj.data_ptr(), w_norms.data_ptr(),
+                                                reconst.data_ptr(), sm.data_ptr(), _stream()), "nppc_projection_loss")
+    return dict(err_norm=err_norm, err_proj=torch.view_as_complex(err_proj), w_norms=w_norms, reconst_err=reconst,
+                second_moment_mse=sm)
+
+
+def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int = 64, dtype=torch.float32):
+    """Fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> time-major LSTM input [T', R, KP]."""
+    nbr_src, fb, fbr, fbi = (_f32(v) for v in (nbr_src, fb, fbr, fbi))
+    _chk(nbr_src, fb, fbr, fbi)
+    B, F, Tp = nbr_src.shape
+    G = groups if (groups > 1 and B > 1) else 1
+    R = B * (F // G)
+    xs = torch.empty(Tp, R, KP, device=fb.device, dtype=dtype)
+    sums = torch.empty(B, device=fb.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_subband_pack(nbr_src.data_ptr(), fb.data_ptr(), fbr.data_ptr(), fbi.data_ptr(), B, F, Tp,
+                                             num_neighbor, groups, KP, sums.data_ptr(),
+                                             xs.data_ptr() if dtype == torch.float32 else 0,
+                                             xs.data_ptr() if dtype == _BF16 else 0, _stream()), "nppc_subband_pack")
+    return xs
+
+
+class LstmPlan:
+    """Owns the re-packed weight caches of one 2-layer LSTM + fc (sequence_model.py:31-38,79)."""
+
+    def __init__(self, w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, fc_w, fc_b):
+        import ctypes as C
+        ts = [_f32(t.detach()) for t in (w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, fc_w, fc_b)]
+        _chk(*ts)
+        self.H = ts[1].shape[1]
+        self.I = ts[0].shape[1]
+        self.O = ts[8].shape[0]
+        h = C.c_void_p()
+        _lib.check(_lib.load().nppc_lstm_plan_create(C.byref(h), self.I, self.H, self.O, *[t.data_ptr() for t in ts],
+                                                     _stream()), "nppc_lstm_plan_create")
+        torch.cuda.current_stream().synchronize()  # the source tensors may be temporaries
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().nppc_lstm_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def forward(self, xs: torch.Tensor, impl: int):
+        """xs [T', R, KP] (fp32 for impl 0, bf16 for impl 1) -> y [R, O, T'] fp32."""
+        _chk(xs)
+        Tp, R, KP = xs.shape
+        if impl == 0 and xs.dtype != torch.float32 or impl == 1 and xs.dtype != _BF16:
+            raise RuntimeError("LstmPlan.forward: xs dtype does not match impl")
+        lib = _lib.load()
+        nbytes = lib.nppc_lstm_workspace_bytes(self._h, R, Tp, impl)
+        ws = torch.empty(max(nbytes, 16), device=xs.device, dtype=torch.uint8)
+        y = torch.empty(R, self.O, Tp, device=xs.device, dtype=torch.float32)
+        _lib.check(lib.nppc_lstm_forward(self._h, xs.data_ptr(), R, Tp, KP, impl, ws.data_ptr(), nbytes, y.data_ptr(),
+                                         _stream()), "nppc_lstm_forward")
+        return y
+
+
+def assemble_mask(y: torch.Tensor, B: int, Fp: int, look_ahead: int):
+    """y [B*F', O, T'] -> [B, O, F', T'-la] (fullsubnet_plus.py:227-229)."""
+    _chk(y)
+    R, O, Tp = y.shape
+    assert R == B * Fp
+    out = torch.empty(B, O, Fp, Tp - look_ahead, device=y.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_assemble_mask(y.data_ptr(), B, Fp, O, Tp, look_ahead, out.data_ptr(), _stream()),
+               "nppc_assemble_mask")
+    return out
+
+
+def gemm_bf16_tn(a: torch.Tensor, w: torch.Tensor, bias=None):
+    """C[M,N] bf16 = A[M,K] bf16 @ W[N,K]^T bf16 + bias (tcgen05)."""
+    _chk(a, w, bias)
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty(M, N, device=a.device, dtype=_BF16)
+    _lib.check(_lib.load().nppc_gemm_bf16_tn(a.data_ptr(), w.data_ptr(), _ptr(bias), c.data_ptr(), M, N, K, _stream()),
+               "nppc_gemm_bf16_tn")
+    return c

@@ -1,0 +1,6 @@
+"""Import alias: the package directory is `generative-audio_b200/` (hyphen, not importable by name)."""
+import os as _os
+
+__path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "generative-audio_b200")]
+with open(_os.path.join(__path__[0], "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))

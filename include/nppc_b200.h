@@ -1,0 +1,147 @@
+/*
+ * nppc_b200.h — C-ABI of libnppc_b200.so: hand-written sm_100a CUDA kernels for the NPPC-over-FullSubNet+
+ * speech-restoration hot path of kfirc1503/generative-audio.
+ *
+ * The reference has NO native code / FFI: its boundary for this path is a set of Python
+ * functions that land in ATen library kernels.  Each entry point below replaces one of those call sites
+ * (cited as path:line under /root/reference).  Conventions:
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are dense, row-major, fp32 unless stated; shapes are given in the comment of each function;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); kernels are enqueued
+ *     asynchronously on it, no host synchronisation, no internal streams;
+ *   - return value: 0 on success, <0 on error (NPPC_ERR_*); nppc_last_error() gives the message
+ *     (thread-local).  Errors mirror the reference's Python `assert`/`raise` sites.
+ *   - inputs are borrowed, outputs are caller-allocated; the library owns no tensor memory except
+ *     the opaque plan objects created by *_create and released by *_destroy.
+ */
+#ifndef NPPC_B200_H_
+#define NPPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPPC_OK 0
+#define NPPC_ERR_INVALID_ARGUMENT (-1)
+#define NPPC_ERR_CUDA (-2)
+#define NPPC_ERR_UNSUPPORTED (-3)
+
+const char* nppc_last_error(void);
+/* Library / build identification: "nppc_b200 <version> sm_100a". */
+const char* nppc_version(void);
+/* Number of kernel launches issued by this library since the last reset (for bench.py's gpu_launches). */
+long long nppc_launch_count(void);
+void nppc_reset_launch_count(void);
+
+/* ---- a1: STFT front end -------------------------------------------------------------------------
+ * Replaces utils.prepare_input_from_waveform (utils.py:107-147): torch.hann_window + torch.stft(center=True,
+ * reflect) + sqrt(re^2+im^2).  wave [B,L] -> mag, real, imag each [B,F,T], F = n_fft/2+1, T = 1 + L/hop.
+ * Only n_fft == win == 512 with hop == 256 is compiled (every reference config: utils.py:14-17). */
+int nppc_stft_mri(const float* wave, int B, int L, int n_fft, int hop, float* mag, float* real, float* imag,
+                  void* stream);
+
+/* ---- a15: iSTFT back end ------------------------------------------------------------------------
+ * Replaces torch.istft(n_fft=512, hop=256, win=hann(512), center=True, length=length) as called at
+ * utils.py:60-70, nppc_audio/validator.py:136-143.  real/imag [B,F,T] -> wave [B,length]. */
+int nppc_istft(const float* real, const float* imag, int B, int T, int n_fft, int hop, int length, float* wave,
+               void* stream);
+
+/* ---- a9 + a10: cIRM decompress + mask apply -----------------------------------------------------
+ * Replaces decompress_cIRM (audio_zen/acoustics/mask.py:57-60) followed by utils.crm_to_stft_components
+ * (utils.py:241-249; conj != 0 reproduces its argument-order quirk: enhanced = conj(M)*N) or the correct
+ * M*N of utils.noisy_to_enhanced / model_outputs_to_waveforms (utils.py:54,75-79; conj == 0).
+ * crm [B,2,F,T] (compressed), real/imag [B,F,T] -> out_mag/out_real/out_imag [B,F,T] (out_mag may be NULL). */
+int nppc_crm_decompress_apply(const float* crm, const float* real, const float* imag, int B, int FT, int conj,
+                              float* out_mag, float* out_real, float* out_imag, void* stream);
+/* decompress_cIRM alone (mask.py:57-60), elementwise over n values. */
+int nppc_decompress_cirm(const float* m, long long n, float* out, void* stream);
+/* build_complex_ideal_ratio_mask + compress_cIRM (mask.py:24-54): noisy/clean re,im [n] -> gt [n,2]->stored
+ * planar as gt0[n], gt1[n] (the [B,2,F,T] layout the trainer permutes to, trainer.py:359). */
+int nppc_build_cirm(const float* nr, const float* ni, const float* cr, const float* ci, int B, int FT,
+                    float* gt /* [B,2,FT] */, void* stream);
+
+/* ---- a2: laplace norms --------------------------------------------------------------------------
+ * offline_laplace_norm (audio_zen/model/base_model.py:210-224): y = x / (mean_{per sample}(x) + 1e-5).
+ * x [B, n] -> y [B, n] (n = C*F*T).  `sums` is a [B] fp64 scratch (device). In-place (y == x) allowed. */
+int nppc_offline_laplace_norm(const float* x, int B, long long n, double* sums, float* y, void* stream);
+/* Fused F.pad(x,[0,look_ahead]) (fullsubnet_plus.py:158-160) + offline_laplace_norm: x [B,F,T] -> y [B,F,T+la]. */
+int nppc_pad_offline_laplace_norm(const float* x, int B, int F, int T, int look_ahead, double* sums, float* y,
+                                  void* stream);
+/* cumulative_laplace_norm (base_model.py:227-257): x [BC,F,T] -> y; y[f,t] = x[f,t]/(cumsum_t(sum_f x)/(F(t+1)) + eps). */
+int nppc_cumulative_laplace_norm(const float* x, int BC, int F, int T, float* y, void* stream);
+
+/* ---- a5 + a6: sub-band unfold, drop_band (bit-exact index kernels) ------------------------------
+ * BaseModel.unfold (base_model.py:15-46): x [B,C,F,T] -> out [B,F,C,2n+1,T], out[b,f,c,k,t] = x[b,c,reflect(f+k-n),t]. */
+int nppc_unfold(const float* x, int B, int C, int F, int T, int num_neighbor, float* out, void* stream);
+/* drop_band (audio_zen/acoustics/feature.py:254-285): x [B,C,F,T] -> out [B,C,F/G,T]; requires B > G. */
+int nppc_drop_band(const float* x, int B, int C, int F, int T, int groups, float* out, void* stream);
+
+/* ---- a12: Gram-Schmidt --------------------------------------------------------------------------
+ * gram_schmidt_to_crm (nppc_audio/pc_wrapper.py:8-44): x [B,n,2,P] -> out [B,n,2,P]; complex MGS with the
+ * reference's conjugated coefficient.  gram_schmidt_to_spec_mag (nppc_audio/inpainting/nppc/pc_wrapper.py:43-59):
+ * x [B,n,P] real.  `scratch` must hold nppc_gs_scratch_bytes(B,n) bytes (fp64 Gram + coefficients). */
+size_t nppc_gs_scratch_bytes(int B, int n);
+int nppc_gram_schmidt_complex(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream);
+int nppc_gram_schmidt_real(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream);
+
+/* ---- a12 + a14 fused: Gram-Schmidt + NPPC projection / second-moment loss (forward) --------------
+ * head [B,n,2,P] (PC-head output before orthogonalisation), gt/pred [B,2,P] (compressed-cIRM domain, already
+ * drop_band-ed) -> w_mat [B,n,2,P] and the per-sample statistics of NPPCAudioTrainer.base_step
+ * (nppc_audio/trainer.py:259-298): err_norm [B], err_proj [B,n,2] (re,im), w_norms [B,n] (already divided by
+ * err_norm), reconst_err [B], second_moment_mse [B,n]. One Gram pass over head+err, one apply pass. */
+int nppc_gs_loss_fused(const float* head, const float* gt, const float* pred, int B, int n, long long P,
+                       void* scratch, float* w_mat, float* err_norm, float* err_proj, float* w_norms,
+                       float* reconst_err, float* second_moment_mse, void* stream);
+/* Loss statistics for an explicit w_mat (trainer.py:259-298), same outputs as above. */
+int nppc_projection_loss(const float* w_mat, const float* gt, const float* pred, int B, int n, long long P,
+                         void* scratch, float* err_norm, float* err_proj, float* w_norms, float* reconst_err,
+                         float* second_moment_mse, void* stream);
+
+/* ---- a5+a2 fused for the sub-band LSTM: feature packing ------------------------------------------
+ * Builds the sub-band model input of fullsubnet_plus.py:203-223 / networks.py:133-151 without materialising
+ * the [B,F,34,T'] tensor: unfold(nbr_src, N) ++ fb ++ fbr ++ fbi, offline_laplace_norm over (F,S,T') per
+ * sample, drop_band(groups) row selection, written TIME-MAJOR as xs [T', R, KP] (KP >= S, zero padded),
+ * R = B*F' rows ordered like the reference's reshape(B*F', S, T').  nbr_src/fb/fbr/fbi are [B,F,T'].
+ * xs_f32 (fp32) and/or xs_bf16 may be NULL.  `sums` [B] fp64 scratch. */
+int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B, int F,
+                      int Tp, int num_neighbor, int groups, int KP, double* sums, float* xs_f32,
+                      void* xs_bf16, void* stream);
+
+/* ---- a7: sub-band LSTM (2 layers) + fc -----------------------------------------------------------
+ * Replaces nn.LSTM(I->H, 2 layers, batch_first) + nn.Linear(H->O) of SequenceModel
+ * (audio_zen/model/module/sequence_model.py:31-38,79,113-123).  Gate order i,f,g,o; z = W_ih x + b_ih + W_hh h + b_hh.
+ * Plan objects own the re-packed weight caches (derived from the fp32 master weights, never serialised). */
+typedef struct nppc_lstm_plan nppc_lstm_plan;
+/* weights are DEVICE pointers in the nn.LSTM state_dict layout: w_ih0 [4H,I], w_hh* [4H,H], w_ih1 [4H,H],
+ * b_* [4H], fc_w [O,H], fc_b [O]. */
+int nppc_lstm_plan_create(nppc_lstm_plan** plan, int I, int H, int O, const float* w_ih0, const float* w_hh0,
+                          const float* b_ih0, const float* b_hh0, const float* w_ih1, const float* w_hh1,
+                          const float* b_ih1, const float* b_hh1, const float* fc_w, const float* fc_b,
+                          void* stream);
+void nppc_lstm_plan_destroy(nppc_lstm_plan* plan);
+/* Workspace bytes needed by nppc_lstm_forward for R rows x Tp steps with the given implementation
+ * (impl: 0 = fp32 SIMT reference-precision path, 1 = bf16 tcgen05 tensor-core path). */
+size_t nppc_lstm_workspace_bytes(const nppc_lstm_plan* plan, int R, int Tp, int impl);
+/* xs: time-major input [Tp, R, KP] (fp32 for impl 0, bf16 for impl 1; KP as given to nppc_subband_pack).
+ * y: [R, O, Tp] fp32 — the layout SequenceModel.forward returns (sequence_model.py:122). */
+int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int Tp, int KP, int impl,
+                      void* workspace, size_t workspace_bytes, float* y, void* stream);
+
+/* ---- a8/a11 output assembly -----------------------------------------------------------------------
+ * y [B*F', O, T'] -> out [B, O, F', T'-la] dropping the first `look_ahead` frames
+ * (fullsubnet_plus.py:227-229; networks.py:156-161 is the same memory layout with O = 2*n_dirs). */
+int nppc_assemble_mask(const float* y, int B, int Fp, int O, int Tp, int look_ahead, float* out, void* stream);
+
+/* ---- tensor-core GEMM (used by the LSTM input projections) ----------------------------------------
+ * C[M,N] (bf16, row-major) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16, row-major) + bias[N] (fp32, may be NULL).
+ * tcgen05.mma + TMA + TMEM. K % 64 == 0, N % 128 == 0. */
+int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPPC_B200_H_ */
