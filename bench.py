@@ -1,0 +1,243 @@
+#!/usr/bin/env python
+"""bench.py — NPPC-audio inference throughput (audio-seconds / second, 16 kHz, 5 PCs) on N B200s.
+
+One "step" = one pass of the hot path (NPPCModel.forward: STFT -> frozen FullSubNet+ -> cRM -> PC head ->
+Gram-Schmidt) over one batch of synthetic 4 s utterances per GPU.  Prints ONE JSON line (contract in the task
+statement): value = whole-job audio-s/s with inputs resident in HBM; e2e = same through the public
+NPPCModel.forward call with pinned HOST input and the w_mat result copied back to the host inside the timed region;
+roofline = tensor-pipe fraction of the dominant kernel (the sub-band LSTM), timed live with CUDA events;
+cpu_baseline = the oracle port of the reference's CPU path on this box's host cores (bounded sample).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--lstm-impl tc|f32]
+  python bench.py --impl reference ...      # the reference's CPU path (oracle port), rank 0 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SR = 16000
+L = 64000          # 4 s
+N_DIRS = 5
+F, T, TP, H = 257, 251, 253, 384
+METRIC = "audio-sec/sec NPPC-audio inference (16 kHz, 5 PCs)"
+# 3.645 MFLOP per (sequence, step) for the 2-layer sub-band LSTM + fc
+LSTM_FLOP_PER_SEQ_STEP = 2 * 1536 * (34 + 384) + 2 * 1536 * 768
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, batch_cpu):
+    """The reference's CPU path for this metric, restated by oracle/nppc_oracle.py (fast=True -> ATen's fused CPU LSTM,
+    i.e. exactly what the reference's nn.LSTM runs), on all host threads."""
+    import torch
+
+    import nppc_oracle as O
+    import weights
+    from helpers import wave
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = weights.synth_state_dict(N_DIRS, 0)
+    x = wave(batch_cpu, L, 100)
+    for _ in range(warmup):
+        O.nppc_forward(sd, x, n_dirs=N_DIRS, fast=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.nppc_forward(sd, x, n_dirs=N_DIRS, fast=True)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=batch_cpu * L / SR / dt, ms_per_step=dt * 1e3, cores=cores,
+                sample=f"{steps} x NPPCModel.forward on {batch_cpu} synthetic 4 s utterances, fp32, torch CPU, {cores} threads")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--lstm-impl", default=os.environ.get("NPPC_LSTM_IMPL", "tc"), choices=["tc", "f32"])
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"NPPC-audio inference, {args.batch} x 4 s 16 kHz synthetic utterances per GPU per step, "
+                          f"n_dirs={N_DIRS}, random-init FullSubNet+ + PC head (BASELINE configs[4] per-GPU micro-batch)",
+              "batch_per_gpu": args.batch, "n_dirs": N_DIRS, "seconds_per_utterance": L / SR,
+              "parallelism": f"utterance-sharded x{world} (no data-path collective)",
+              "l2": "256 MiB scratch write between timed steps (L2 flush); per-step working set (GBs) also exceeds L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+        r = cpu_reference_run(steps, warmup, args.cpu_batch)
+        line = {"metric": METRIC, "value": r["value"], "unit": "audio-s/s", "impl": "reference", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, reference_arm="reference CPU path via the oracle port (reference is Python; "
+                                                      "/root/reference does not travel to the GPU box)"),
+                "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import generative_audio_b200 as G
+    from helpers import build_model, wave
+    ops = G.ops
+    model, _ = build_model(N_DIRS, 1, args.lstm_impl)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    x_host = wave(B, L, 1000 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty(B, N_DIRS, 2, F, T, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # live CUDA-event timing of the dominant kernel (the LSTM launches) inside the timed region
+    lstm_events = []
+    orig_forward = ops.LstmPlan.forward
+
+    def timed_forward(self, xs, impl):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = orig_forward(self, xs, impl)
+        e1.record()
+        lstm_events.append((e0, e1, xs.shape[1], xs.shape[0]))
+        return y
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, fn, timed):
+        total = 0.0
+        for _ in range(n):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    def step_device():
+        return model(x_dev)
+
+    def step_e2e():
+        w = model(x_host.to(dev, non_blocking=True))
+        out_host.copy_(w, non_blocking=True)
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    run_steps(args.warmup, step_device, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.LstmPlan.forward = timed_forward
+    ops.reset_launch_count()
+    ms_total = run_steps(args.steps, step_device, True)
+    launches = ops.launch_count()
+    ops.LstmPlan.forward = orig_forward
+    barrier()
+    # ---- end-to-end (host buffers) --------------------------------------------------------------------
+    run_steps(1, step_e2e, False)
+    barrier()
+    ms_e2e = run_steps(args.steps, step_e2e, True)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e_step = (t / args.steps).tolist()
+    audio_s = B * world * L / SR
+    lstm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in lstm_events) / max(len(lstm_events), 1)
+    R, Tp = (lstm_events[0][2], lstm_events[0][3]) if lstm_events else (B * F, TP)
+    flops = LSTM_FLOP_PER_SEQ_STEP * R * Tp
+    pk = peaks()
+    achieved = flops / (lstm_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": f"sub-band LSTM (2 layers + fc), impl={args.lstm_impl}, per nppc_lstm_forward call",
+                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                "traffic": None, "peak_source": f"{pk['src']} (sustained bf16, kernel timed inside a long step)",
+                "ms_per_call": lstm_ms, "calls_per_step": len(lstm_events) / max(args.steps, 1),
+                "algorithmic_flops_per_call": flops, "share_of_step": lstm_ms * len(lstm_events) / max(args.steps, 1) / ms_step}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {"metric": METRIC, "value": audio_s / (ms_step * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.lstm_impl == "tc" else "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": audio_s / (ms_e2e_step * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_step,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary()}
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(2, 1, args.cpu_batch)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,10 +54,15 @@ def test_training_step_stats_groups2_f32():
 
 
 def test_cumulative_norm_model_matches_oracle():
+    """cumulative_laplace_norm divides the signed re/im planes by a running mean that crosses zero: the model is
+    ill-conditioned there and the reference's OWN fp32 run differs from fp64 by several percent.  The fp64 oracle
+    arbitrates: our error must not exceed twice the fp32 oracle's error (floor 2e-3)."""
     m, sd = build_model(5, 1, "f32", norm_type="cumulative_laplace_norm")
     x = wave(2, 4096, 21)
-    ref = O.nppc_forward(sd, x, n_dirs=5, norm_type="cumulative_laplace_norm")
-    assert rel_err(m(x.cuda()).cpu(), ref) < 2e-3
+    ref32 = O.nppc_forward(sd, x, n_dirs=5, norm_type="cumulative_laplace_norm")
+    ref64 = O.nppc_forward({k: v.double() for k, v in sd.items()}, x.double(), n_dirs=5, norm_type="cumulative_laplace_norm")
+    budget = max(2e-3, 2.0 * rel_err(ref32, ref64))
+    assert rel_err(m(x.cuda()).cpu(), ref64) < budget
 
 
 def test_batch_of_one_skips_drop_band_assert():
