@@ -1,0 +1,180 @@
+// bf16 tensor-core GEMM on tcgen05 + TMA + TMEM:  C[M,N] (bf16) = A[M,K] * W[N,K]^T + bias[N]
+// Used for the LSTM input projections (M = T'*R up to ~4.2 M rows, N = 4H = 1536, K = 64 / 384).
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM -> registers -> +bias -> bf16 -> global).  128 x BN output tiles,
+// 64-wide K slabs in a 4-stage shared-memory ring (128-byte swizzle), two TMEM accumulator stages so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Consecutive CTAs take the n-tiles of the same m-block so A is read from
+// HBM once and re-used out of L2.
+#include "tc_common.cuh"
+
+namespace {
+using namespace nppc::tc;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, long long M, int N, int K) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using S = GemmSmem<BN>;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = N / BN, kb_count = K / BK;
+    const long long num_tiles = (long long)m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char* sb = sa + S::A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                    uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        int as = 0; uint32_t aphase = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
+            mbar_wait(&tfull[as], aphase);
+            tcgen05_fence_after();
+            const long long row = (long long)m_blk * BM + ew * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+            __nv_bfloat16* crow = C + (size_t)row * N + (size_t)n_blk * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c * 32, v);
+                tmem_wait_ld();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+                    if (bias) {
+                        a += __ldg(bias + n_blk * BN + c * 32 + 2 * i);
+                        b += __ldg(bias + n_blk * BN + c * 32 + 2 * i + 1);
+                    }
+                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (row < M) {
+                    uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+template <int BN>
+int launch_gemm(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, BM, BK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, BK);
+    if (rc) return rc;
+    using S = GemmSmem<BN>;
+    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    long long tiles = ((M + BM - 1) / BM) * (N / BN);
+    int grid = (int)(tiles < nppc::sm_count() ? tiles : nppc::sm_count());
+    gemm_bf16_tn_kernel<BN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, bias, (__nv_bfloat16*)C, M, N, K);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+}  // namespace
+
+namespace nppc {
+int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
+    NPPC_CHECK_ARG(A && W && C, "nppc_gemm_bf16_tn: null pointer");
+    NPPC_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % BK == 0 && N % 128 == 0,
+                   "nppc_gemm_bf16_tn: need K %% 64 == 0 and N %% 128 == 0 (M=%lld N=%d K=%d)", M, N, K);
+    NPPC_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                   "nppc_gemm_bf16_tn: pointers must be 16-byte aligned");
+    if (N % 256 == 0) return launch_gemm<256>(A, W, bias, C, M, N, K, s);
+    return launch_gemm<128>(A, W, bias, C, M, N, K, s);
+}
+}  // namespace nppc
+
+extern "C" int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
+                                 void* stream) {
+    return nppc::gemm_bf16_tn(A, W, bias, C, M, N, K, (cudaStream_t)stream);
+}
