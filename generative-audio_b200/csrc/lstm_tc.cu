@@ -29,18 +29,20 @@ constexpr int ROWS = 128;           // sequences per CTA
 constexpr int CH = 32;              // hidden units per chunk
 constexpr int NCHUNK = H / CH;      // 12
 constexpr int NSLAB = H / 64;       // 6 K-slabs of 64
-constexpr int NST = 6;              // W ring stages
 constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have the same shape: 128 x 64 bf16)
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
 constexpr int OPMAX = 24;
 
-struct RecSmem {
+template <int OP>
+struct RecSmemT {
+    static constexpr int NST = OP > 16 ? 5 : 6;                          // W ring stages (227 KB budget)
     static constexpr int A_OFF = 0;
     static constexpr int W_OFF = NSLAB * SLAB_BYTES;
     static constexpr int FC_OFF = W_OFF + NST * SLAB_BYTES;              // float [OP][H]
-    static constexpr int XCH_OFF = FC_OFF + OPMAX * H * 4;               // float [128][OPMAX]
-    static constexpr int BAR_OFF = XCH_OFF + ROWS * OPMAX * 4;
+    static constexpr int XCH_OFF = FC_OFF + OP * H * 4;                  // float [128][OP]
+    static constexpr int BAR_OFF = XCH_OFF + ROWS * OP * 4;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const __nv_bfloat16* __restrict__ zx, __nv_bfloat16* __restrict__ hseq, int R, int Tp,
                 const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O, float* __restrict__ y) {
+    using RecSmem = RecSmemT<OP>;
+    constexpr int NST = RecSmem::NST;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RecSmem::BAR_OFF);
@@ -235,7 +239,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (OP > 0) {
                 if (half == 1) {
 #pragma unroll
-                    for (int o = 0; o < OP; ++o) xch[rloc * OPMAX + o] = fcacc[o];
+                    for (int o = 0; o < OP; ++o) xch[rloc * (OP > 0 ? OP : 1) + o] = fcacc[o];
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (half == 0 && valid) {
@@ -243,7 +247,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         float v = 0.f;
 #pragma unroll
                         for (int oo = 0; oo < OP; ++oo) if (oo == o) v = fcacc[oo];
-                        y[((size_t)row * O + o) * Tp + t] = v + xch[rloc * OPMAX + o] + fc_b[o];
+                        y[((size_t)row * O + o) * Tp + t] = v + xch[rloc * (OP > 0 ? OP : 1) + o] + fc_b[o];
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -279,6 +283,7 @@ __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ o
 template <int OP>
 int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloat16* zx, __nv_bfloat16* hseq, int R, int Tp,
                const float* fc_w, const float* fc_b, int O, float* y, cudaStream_t s) {
+    using RecSmem = RecSmemT<OP>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_rec_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
     lstm_rec_kernel<OP><<<nppc::cdiv(R, ROWS), NTHREADS, RecSmem::TOTAL, s>>>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y);
     NPPC_COUNT_LAUNCH(1);
