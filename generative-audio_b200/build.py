@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnppc_b200.so")
 CUTLASS_INC = "/opt/prime-rl/.venv/lib/python3.12/site-packages/flashinfer/data/cutlass/include"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+FLAGS = (["-DNPPC_REC_TRACE"] if os.environ.get("NPPC_REC_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 

@@ -2,7 +2,7 @@
 // Used for the LSTM input projections (M = T'*R up to ~4.2 M rows, N = 4H = 1536, K = 64 / 384).
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM -> registers -> +bias -> bf16 -> global).  128 x BN output tiles,
+// allocator, warps 4-7 = epilogue (TMEM -> registers -> +bias -> bf16 -> swizzled smem -> TMA store).  128 x BN output tiles,
 // 64-wide K slabs in a 4-stage shared-memory ring (128-byte swizzle), two TMEM accumulator stages so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  Consecutive CTAs take the n-tiles of the same m-block so A is read from
 // HBM once and re-used out of L2.
@@ -13,7 +13,7 @@ using namespace nppc::tc;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int NTHREADS = 256;
 
 template <int BN>
@@ -21,14 +21,17 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int C_OFFSET = STAGES * STAGE_BYTES;       // epilogue staging: BN/64 boxes of [128 rows][64 cols] bf16
+    static constexpr int C_BYTES = BM * BN * 2;
+    static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, long long M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, long long M, int N, int K) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     using S = GemmSmem<BN>;
@@ -45,6 +48,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_c);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -104,9 +108,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
             mbar_wait(&tfull[as], aphase);
             tcgen05_fence_after();
-            const long long row = (long long)m_blk * BM + ew * 32 + lane;
+            const int rloc = ew * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
-            __nv_bfloat16* crow = C + (size_t)row * N + (size_t)n_blk * BN;
+            unsigned char* cs = smem + S::C_OFFSET;
+            // the previous tile's TMA stores must have finished reading the staging buffer
+            if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -123,17 +130,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
                     packed[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                if (row < M) {
-                    uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+                // staging layout = TMA SWIZZLE_128B box [128 rows][64 cols]: 16-byte chunk q of row r lives at q ^ (r & 7)
+                unsigned char* box = cs + (c >> 1) * (BM * 128) + rloc * 128;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) {
+                    int chunk = ((c & 1) * 4 + q) ^ (rloc & 7);
+                    *reinterpret_cast<uint4*>(box + chunk * 16) =
+                        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
                 }
             }
+            // accumulator stage is free as soon as it is in shared memory
             tcgen05_fence_before();
             mbar_arrive(&tempty[as]);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 128) {
+#pragma unroll
+                for (int cb = 0; cb < BN / 64; ++cb)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_c),
+                                 "r"(smem_u32(cs + cb * (BM * 128))), "r"(n_blk * BN + cb * 64), "r"(m_blk * BM)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -150,11 +171,14 @@ int launch_gemm(const void* A, const void* W, const float* bias, void* C, long l
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, BK);
     if (rc) return rc;
+    CUtensorMap tcm;
+    rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, BM, 64);
+    if (rc) return rc;
     using S = GemmSmem<BN>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     long long tiles = ((M + BM - 1) / BM) * (N / BN);
     int grid = (int)(tiles < nppc::sm_count() ? tiles : nppc::sm_count());
-    gemm_bf16_tn_kernel<BN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, bias, (__nv_bfloat16*)C, M, N, K);
+    gemm_bf16_tn_kernel<BN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

@@ -12,6 +12,7 @@
 //                 L2 acts as the double buffer that shared memory has no room for); last layer: fc partial sums.
 // Gate columns are permuted at pack time so that a thread's 4 gates x 16 units are contiguous in Zx and in TMEM:
 //   packed column = chunk*128 + half*64 + gate*16 + u   <->   nn.LSTM row gate*H + chunk*32 + half*16 + u.
+#include <stdlib.h>
 #include <string.h>
 #include "lstm_plan.cuh"
 #include "tc_common.cuh"
@@ -33,6 +34,13 @@ constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have th
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
 constexpr int OPMAX = 24;
 
+#ifdef NPPC_REC_TRACE
+__device__ unsigned long long g_trace[8 * 12 * 16];
+#define TRACE(t, j, slot) do { if (blockIdx.x == 0 && (t) >= 2 && (t) < 10) g_trace[(((t) - 2) * 12 + (j)) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(t, j, slot) do { } while (0)
+#endif
+
 template <int OP>
 struct RecSmemT {
     static constexpr int NST = OP > 16 ? 5 : 6;                          // W ring stages (227 KB budget)
@@ -52,11 +60,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-template <int OP>
+// CL = cluster size: the CL CTAs of a cluster share ONE W_hh stream — slab s is fetched from L2 by CTA (s % CL) and
+// multicast into every CTA's ring, so L2->SM traffic for the weights drops by CL (the kernel is L2-bandwidth-bound).
+template <int OP, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const __nv_bfloat16* __restrict__ zx, __nv_bfloat16* __restrict__ hseq, int R, int Tp,
-                const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O, float* __restrict__ y) {
+                const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O, float* __restrict__ y, int dbg) {
     using RecSmem = RecSmemT<OP>;
     constexpr int NST = RecSmem::NST;
     extern __shared__ unsigned char smem_raw[];
@@ -85,7 +95,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         tma_prefetch_desc(&tmap_h);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
         for (int i = 0; i < NSLAB; ++i) mbar_init(&a_full[i], 1);
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 256);
@@ -95,36 +105,49 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     if (warp == 2) tmem_alloc<512>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         // ---- W_hh producer: 72 slabs per step, independent of t (runs ahead across step boundaries) ----
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            uint32_t s = 0;
             for (int t = 0; t < Tp; ++t)
                 for (int j = 0; j < NCHUNK; ++j)
-                    for (int k = 0; k < NSLAB; ++k) {
-                        mbar_wait(&w_empty[stage], phase ^ 1);
+                    for (int k = 0; k < NSLAB; ++k, ++s) {
+                        if ((dbg & 1) && s >= (uint32_t)NST) continue;  // timing experiment: W ring filled once, never refilled
+                        mbar_wait(&w_empty[stage], phase ^ 1);   // every CTA of the cluster has released this slot
                         mbar_arrive_expect_tx(&w_full[stage], SLAB_BYTES);
-                        tma_load_2d(smem + RecSmem::W_OFF + stage * SLAB_BYTES, &tmap_w, &w_full[stage], k * 64, j * 128);
+                        unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
+                        if (CL == 1) tma_load_2d(dst, &tmap_w, &w_full[stage], k * 64, j * 128);
+                        else if (s % CL == crank) tma_load_2d_mcast(dst, &tmap_w, &w_full[stage], k * 64, j * 128, CMASK);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
         }
     } else if (warp == 3) {
         // ---- A producer: reload h_t (written to global by the epilogue) as the A operand of step t+1 ----
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             for (int k = 0; k < NSLAB; ++k) mbar_arrive(&a_full[k]);  // step 0: zeros already in place
             for (int t = 1; t < Tp; ++t) {
                 mbar_wait(h_ready, (t - 1) & 1);
+                TRACE(t, 0, 13);
                 for (int k = 0; k < NSLAB; ++k) {
                     mbar_arrive_expect_tx(&a_full[k], SLAB_BYTES);
                     tma_load_2d(smem + RecSmem::A_OFF + k * SLAB_BYTES, &tmap_h, &a_full[k], k * 64, (t - 1) * R + row0);
                 }
             }
         }
+    } else if (warp == 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     } else if (warp == 1) {
         // ---- MMA issuer ----
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(ROWS, 128);
             int stage = 0; uint32_t phase = 0;
@@ -134,24 +157,31 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             for (int t = 0; t < Tp; ++t) {
                 for (int j = 0; j < NCHUNK; ++j, ++it) {
                     mbar_wait(acc_empty, (it & 1) ^ 1);
+                    TRACE(t, j, 0);
                     tcgen05_fence_after();
                     for (int k = 0; k < NSLAB; ++k) {
                         if (j == 0) mbar_wait(&a_full[k], t & 1);
-                        mbar_wait(&w_full[stage], phase);
+                        if (j == 0 && k == 0) TRACE(t, j, 8);
+                        if (!(dbg & 1) || it == 0) mbar_wait(&w_full[stage], phase);
+                        TRACE(t, j, 1 + k);
                         tcgen05_fence_after();
                         uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
                         uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
-                        umma_commit(&w_empty[stage]);
+                        if (dbg & 1) { }
+                        else if (CL == 1) umma_commit(&w_empty[stage]);
+                        else umma_commit_mcast(&w_empty[stage], CMASK);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(acc_full);
+                    TRACE(t, j, 7);
                 }
             }
         }
     } else if (warp >= 4) {
         // ---- epilogue: thread = (row = 32*(warp%4) + lane, half = (warp-4)/4) ----
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int ew = warp & 3, half = (warp - 4) >> 2;
         const int rloc = ew * 32 + lane;
         const int row = row0 + rloc;
@@ -167,20 +197,26 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             tmem_wait_st();
         }
         uint32_t it = 0;
+        // software-pipelined Zx stream: this thread's 64 pre-activations (i,f,g,o x 16 units = 128 contiguous bytes) of
+        // chunk it+1 are requested while chunk it is being computed; chunk it+3 is pulled into L2 ahead of that.
+        auto zx_ptr = [&](int t, int j) -> const uint4* {
+            return reinterpret_cast<const uint4*>(zx + ((size_t)t * R + (valid ? row : 0)) * H4 + half * 64 + j * 128);
+        };
+        uint4 zraw[8];
+        {
+            const uint4* zp = zx_ptr(0, 0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) zraw[q] = valid ? __ldg(zp + q) : make_uint4(0, 0, 0, 0);
+        }
         for (int t = 0; t < Tp; ++t) {
             float fcacc[OP > 0 ? OP : 1];
 #pragma unroll
             for (int o = 0; o < (OP > 0 ? OP : 1); ++o) fcacc[o] = 0.f;
-            const __nv_bfloat16* zrow = zx + ((size_t)t * R + (valid ? row : 0)) * H4 + half * 64;
             __nv_bfloat16* hrow = hseq + ((size_t)t * R + (valid ? row : 0)) * H + half * 16;
 #pragma unroll 1
             for (int j = 0; j < NCHUNK; ++j, ++it) {
-                // prefetch this thread's 64 pre-activations (i,f,g,o x 16 units) = 128 contiguous bytes
-                uint4 zraw[8];
-                const uint4* zp = reinterpret_cast<const uint4*>(zrow + j * 128);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) zraw[q] = valid ? __ldg(zp + q) : make_uint4(0, 0, 0, 0);
                 mbar_wait(acc_full, it & 1);
+                if (threadIdx.x == 128) TRACE(t, j, 9);
                 tcgen05_fence_after();
                 uint32_t gi[16], gf[16], gg[16], go[16], cc[16];
                 tmem_ld16(t_acc + 0, gi);
@@ -191,9 +227,29 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 tmem_wait_ld();
                 tcgen05_fence_before();
                 mbar_arrive(acc_empty);  // accumulator is in registers: the next chunk's MMAs may start
-                const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(zraw);
+                if (threadIdx.x == 128) TRACE(t, j, 10);
+                uint4 zcur[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) zcur[q] = zraw[q];
+                {
+                    int jn = j + 1, tn = t;
+                    if (jn == NCHUNK) { jn = 0; tn = t + 1; }
+                    if (tn < Tp && valid && !(dbg & 4)) {
+                        const uint4* zp = zx_ptr(tn, jn);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q);
+                        int jp = j + 3, tp = t;
+                        if (jp >= NCHUNK) { jp -= NCHUNK; tp = t + 1; }
+                        if (tp < Tp) asm volatile("prefetch.global.L2 [%0];" ::"l"(zx_ptr(tp, jp)));
+                    }
+                }
+                const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(zcur);
                 uint32_t hp[8];
                 float hv[16];
+                if (dbg & 2) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) hv[u] = __uint_as_float(gi[u]) + __bfloat162float(zb[u]);
+                } else
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     float zi = __uint_as_float(gi[u]) + __bfloat162float(zb[u]);
@@ -215,6 +271,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                 }
+                if (threadIdx.x == 128) TRACE(t, j, 11);
                 if (OP > 0) {
                     const float* wf = fc_s + j * CH + half * 16;
 #pragma unroll
@@ -236,6 +293,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             __threadfence();
             fence_proxy_async_all();
             mbar_arrive(h_ready);
+            if (threadIdx.x == 128) TRACE(t, 11, 12);
             if (OP > 0) {
                 if (half == 1) {
 #pragma unroll
@@ -256,6 +314,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -280,15 +339,49 @@ __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ o
     }
 }
 
+template <int OP, int CL>
+int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloat16* zx, __nv_bfloat16* hseq, int R, int Tp,
+                  const float* fc_w, const float* fc_b, int O, float* y, cudaStream_t s) {
+    using RecSmem = RecSmemT<OP>;
+    auto kern = lstm_rec_kernel<OP, CL>;
+    NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
+    int tiles = nppc::cdiv(R, ROWS);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nppc::cdiv(tiles, CL) * CL));  // padded CTAs own no valid rows but keep the cluster protocol
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = RecSmem::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int dbg = getenv("NPPC_REC_DBG") ? atoi(getenv("NPPC_REC_DBG")) : 0;
+    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, dbg));
+    NPPC_COUNT_LAUNCH(1);
+    return NPPC_OK;
+}
+
+int rec_cluster_size() {
+    static int cl = -1;
+    if (cl < 0) {
+        const char* e = getenv("NPPC_LSTM_CLUSTER");
+        cl = e ? atoi(e) : 4;
+        if (cl != 1 && cl != 2 && cl != 4) cl = 4;
+    }
+    return cl;
+}
+
 template <int OP>
 int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloat16* zx, __nv_bfloat16* hseq, int R, int Tp,
                const float* fc_w, const float* fc_b, int O, float* y, cudaStream_t s) {
-    using RecSmem = RecSmemT<OP>;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_rec_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
-    lstm_rec_kernel<OP><<<nppc::cdiv(R, ROWS), NTHREADS, RecSmem::TOTAL, s>>>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y);
-    NPPC_COUNT_LAUNCH(1);
-    NPPC_LAUNCH_OK();
-    return NPPC_OK;
+    switch (rec_cluster_size()) {
+        case 1: return launch_rec_cl<OP, 1>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
+        case 2: return launch_rec_cl<OP, 2>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
+        default: return launch_rec_cl<OP, 4>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
+    }
 }
 
 }  // namespace
@@ -359,3 +452,9 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int Tp, int 
 }
 
 }  // namespace nppc
+
+#ifdef NPPC_REC_TRACE
+extern "C" int nppc_debug_rec_trace(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(g_trace)) == cudaSuccess ? 0 : -2;
+}
+#endif
