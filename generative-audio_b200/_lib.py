@@ -32,11 +32,11 @@ PROTOTYPES = {
     "nppc_gram_schmidt_real": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
     "nppc_gs_loss_fused": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "nppc_projection_loss": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
-    "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_lstm_plan_create": (_i, [C.POINTER(_p), _i, _i, _i] + [_p] * 10 + [_p]),
     "nppc_lstm_plan_destroy": (None, [_p]),
     "nppc_lstm_workspace_bytes": (_sz, [_p, _i, _i, _i]),
-    "nppc_lstm_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "nppc_lstm_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
 }

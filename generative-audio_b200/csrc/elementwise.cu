@@ -1,5 +1,6 @@
 // HBM-bound elementwise / indexing kernels: cIRM (de)compression + mask apply (a9, a10), laplace norms (a2),
 // sub-band unfold (a5), drop_band (a6), fused sub-band feature packing for the LSTM, output assembly (a8/a11).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -229,9 +230,9 @@ constexpr int PK_ROWS = 4;
 constexpr int PK_T = 32;
 __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
                                                           const float* __restrict__ fbr, const float* __restrict__ fbi,
-                                                          int B, int F, int Tp, int nn, int G, int KP,
+                                                          int B, int F, int Tp, int nn, int G, int KP, int RS,
                                                           const double* __restrict__ sums, float* __restrict__ xs_f32,
-                                                          __nv_bfloat16* __restrict__ xs_bf16) {
+                                                          __half* __restrict__ xs_f16) {
     extern __shared__ float tile[];  // [PK_ROWS][KP][PK_T+1]
     const int S = 2 * nn + 1 + 3;
     const int Fg = F / G;
@@ -276,11 +277,11 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
         int tt = idx / (KP * PK_ROWS);
         long long row = row0 + r;
         int t = t0 + tt;
-        if (row < R && t < Tp) {
+        if (row < RS && t < Tp) {
             float v = tile[(r * KP + k) * (PK_T + 1) + tt];
-            size_t o = ((size_t)t * R + row) * KP + k;
+            size_t o = ((size_t)t * RS + row) * KP + k;
             if (xs_f32) xs_f32[o] = v;
-            if (xs_bf16) xs_bf16[o] = __float2bfloat16(v);
+            if (xs_f16) xs_f16[o] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));  // saturating
         }
     }
 }
@@ -403,10 +404,10 @@ extern "C" int nppc_drop_band(const float* x, int B, int C, int F, int T, int gr
 }
 
 extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B,
-                                 int F, int Tp, int num_neighbor, int groups, int KP, double* sums, float* xs_f32,
-                                 void* xs_bf16, void* stream) {
+                                 int F, int Tp, int num_neighbor, int groups, int KP, int R_stride, double* sums,
+                                 float* xs_f32, void* xs_f16, void* stream) {
     NPPC_CHECK_ARG(nbr_src && fb && fbr && fbi && sums, "nppc_subband_pack: null pointer");
-    NPPC_CHECK_ARG(xs_f32 || xs_bf16, "nppc_subband_pack: no output requested");
+    NPPC_CHECK_ARG(xs_f32 || xs_f16, "nppc_subband_pack: no output requested");
     int S = 2 * num_neighbor + 4;
     NPPC_CHECK_ARG(B > 0 && F > 0 && Tp > 0 && num_neighbor >= 1 && num_neighbor < F && KP >= S,
                    "nppc_subband_pack: bad sizes (B=%d F=%d Tp=%d N=%d KP=%d)", B, F, Tp, num_neighbor, KP);
@@ -418,12 +419,13 @@ extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const fl
     int gx = per_sample_grid((long long)F * Tp, B);
     subband_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(nbr_src, fb, fbr, fbi, F, Tp, num_neighbor, sums);
     long long R = (long long)B * (F / G);
+    NPPC_CHECK_ARG(R_stride >= R, "nppc_subband_pack: R_stride (%d) < rows (%lld)", R_stride, R);
     size_t smem = sizeof(float) * PK_ROWS * KP * (PK_T + 1);
     if (smem > 48 * 1024)
         NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)nppc::cdiv(R, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));
-    subband_pack_kernel<<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, KP, sums, xs_f32,
-                                                (__nv_bfloat16*)xs_bf16);
+    dim3 grid((unsigned)nppc::cdiv(R_stride, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));
+    subband_pack_kernel<<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, KP, R_stride, sums, xs_f32,
+                                                (__half*)xs_f16);
     NPPC_COUNT_LAUNCH(2);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

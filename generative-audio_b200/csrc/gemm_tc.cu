@@ -6,6 +6,7 @@
 // 64-wide K slabs in a 4-stage shared-memory ring (128-byte swizzle), two TMEM accumulator stages so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  Consecutive CTAs take the n-tiles of the same m-block so A is read from
 // HBM once and re-used out of L2.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -28,7 +29,7 @@ struct GemmSmem {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int BN>
+template <int BN, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, long long M, int N, int K) {
@@ -79,7 +80,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = F16 ? umma_idesc_f16(BM, BN) : umma_idesc_bf16(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -127,8 +128,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         a += __ldg(bias + n_blk * BN + c * 32 + 2 * i);
                         b += __ldg(bias + n_blk * BN + c * 32 + 2 * i + 1);
                     }
-                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                    if (F16) {  // saturating: fp16 has the mantissa the LSTM pre-activations need, not the range
+                        __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+                        packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                    } else {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
                 }
                 // staging layout = TMA SWIZZLE_128B box [128 rows][64 cols]: 16-byte chunk q of row r lives at q ^ (r & 7)
                 unsigned char* box = cs + (c >> 1) * (BM * 128) + rloc * 128;
@@ -164,7 +170,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
-template <int BN>
+template <int BN, bool F16>
 int launch_gemm(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, BM, BK);
@@ -175,10 +181,10 @@ int launch_gemm(const void* A, const void* W, const float* bias, void* C, long l
     rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, BM, 64);
     if (rc) return rc;
     using S = GemmSmem<BN>;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     long long tiles = ((M + BM - 1) / BM) * (N / BN);
     int grid = (int)(tiles < nppc::sm_count() ? tiles : nppc::sm_count());
-    gemm_bf16_tn_kernel<BN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
+    gemm_bf16_tn_kernel<BN, F16><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -187,18 +193,20 @@ int launch_gemm(const void* A, const void* W, const float* bias, void* C, long l
 }  // namespace
 
 namespace nppc {
-int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
+// f16 != 0: A, W and C are IEEE fp16 instead of bf16 (same kernel, other tcgen05 operand format)
+int gemm_16bit_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, int f16,
+                  cudaStream_t s) {
     NPPC_CHECK_ARG(A && W && C, "nppc_gemm_bf16_tn: null pointer");
     NPPC_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % BK == 0 && N % 128 == 0,
                    "nppc_gemm_bf16_tn: need K %% 64 == 0 and N %% 128 == 0 (M=%lld N=%d K=%d)", M, N, K);
     NPPC_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)C % 16 == 0),
                    "nppc_gemm_bf16_tn: pointers must be 16-byte aligned");
-    if (N % 256 == 0) return launch_gemm<256>(A, W, bias, C, M, N, K, s);
-    return launch_gemm<128>(A, W, bias, C, M, N, K, s);
+    if (f16) return N % 256 == 0 ? launch_gemm<256, true>(A, W, bias, C, M, N, K, s) : launch_gemm<128, true>(A, W, bias, C, M, N, K, s);
+    return N % 256 == 0 ? launch_gemm<256, false>(A, W, bias, C, M, N, K, s) : launch_gemm<128, false>(A, W, bias, C, M, N, K, s);
 }
 }  // namespace nppc
 
 extern "C" int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
                                  void* stream) {
-    return nppc::gemm_bf16_tn(A, W, bias, C, M, N, K, (cudaStream_t)stream);
+    return nppc::gemm_16bit_tn(A, W, bias, C, M, N, K, 0, (cudaStream_t)stream);
 }

@@ -12,7 +12,7 @@ constexpr int RT = 16;
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // xs [Tp][R][KP] fp32 (first Kin columns used); hseq_out [Tp][R][H] or null; y [R][O][Tp] or null (last layer)
-__global__ void __launch_bounds__(384) lstm_layer_f32_kernel(const float* __restrict__ xs, int R, int Tp, int KP,
+__global__ void __launch_bounds__(384) lstm_layer_f32_kernel(const float* __restrict__ xs, int R, int RS, int Tp, int KP,
                                                              int Kin, int H, const float* __restrict__ w_ihT,
                                                              const float* __restrict__ w_hhT,
                                                              const float* __restrict__ bias, float* __restrict__ hseq_out,
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(384) lstm_layer_f32_kernel(const float* __rest
         for (int idx = threadIdx.x; idx < RT * Kin; idx += blockDim.x) {
             int r = idx / Kin, k = idx - r * Kin;
             int row = row0 + r;
-            xsm[k * RT + r] = (row < R) ? xs[((size_t)t * R + row) * KP + k] : 0.f;
+            xsm[k * RT + r] = (row < R) ? xs[((size_t)t * RS + row) * KP + k] : 0.f;
         }
         __syncthreads();
         float acc[4][RT];
@@ -115,7 +115,7 @@ namespace nppc {
 
 size_t lstm_workspace_f32(const nppc_lstm_plan* p, int R, int Tp) { return sizeof(float) * (size_t)Tp * R * p->H; }
 
-int lstm_forward_f32(const nppc_lstm_plan* p, const float* xs, int R, int Tp, int KP, void* ws, size_t ws_bytes,
+int lstm_forward_f32(const nppc_lstm_plan* p, const float* xs, int R, int RS, int Tp, int KP, void* ws, size_t ws_bytes,
                      float* y, cudaStream_t s) {
     NPPC_CHECK_ARG(ws_bytes >= lstm_workspace_f32(p, R, Tp), "nppc_lstm_forward: workspace too small (%zu < %zu)", ws_bytes,
                    lstm_workspace_f32(p, R, Tp));
@@ -126,9 +126,9 @@ int lstm_forward_f32(const nppc_lstm_plan* p, const float* xs, int R, int Tp, in
     int grid = cdiv(R, RT);
     size_t smem0 = sizeof(float) * RT * (p->H + p->I), smem1 = sizeof(float) * RT * (2 * p->H);
     NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_layer_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    lstm_layer_f32_kernel<<<grid, p->H, smem0, s>>>(xs, R, Tp, KP, p->I, p->H, p->w_ihT[0], p->w_hhT[0], p->bias[0], hseq,
+    lstm_layer_f32_kernel<<<grid, p->H, smem0, s>>>(xs, R, RS, Tp, KP, p->I, p->H, p->w_ihT[0], p->w_hhT[0], p->bias[0], hseq,
                                                    nullptr, nullptr, 0, nullptr);
-    lstm_layer_f32_kernel<<<grid, p->H, smem1, s>>>(hseq, R, Tp, p->H, p->H, p->H, p->w_ihT[1], p->w_hhT[1], p->bias[1],
+    lstm_layer_f32_kernel<<<grid, p->H, smem1, s>>>(hseq, R, R, Tp, p->H, p->H, p->H, p->w_ihT[1], p->w_hhT[1], p->bias[1],
                                                    nullptr, p->fc_w, p->fc_b, p->O, y);
     NPPC_COUNT_LAUNCH(2);
     NPPC_LAUNCH_OK();
@@ -188,12 +188,12 @@ extern "C" size_t nppc_lstm_workspace_bytes(const nppc_lstm_plan* plan, int R, i
     return impl == 0 ? nppc::lstm_workspace_f32(plan, R, Tp) : nppc::lstm_workspace_tc(plan, R, Tp);
 }
 
-extern "C" int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int Tp, int KP, int impl,
+extern "C" int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int R_stride, int Tp, int KP, int impl,
                                  void* workspace, size_t workspace_bytes, float* y, void* stream) {
     NPPC_CHECK_ARG(plan && xs && y && workspace, "nppc_lstm_forward: null pointer");
-    NPPC_CHECK_ARG(R > 0 && Tp > 0, "nppc_lstm_forward: bad sizes R=%d Tp=%d", R, Tp);
-    if (impl == 0) return nppc::lstm_forward_f32(plan, (const float*)xs, R, Tp, KP, workspace, workspace_bytes, y, (cudaStream_t)stream);
-    if (impl == 1) return nppc::lstm_forward_tc(plan, xs, R, Tp, KP, workspace, workspace_bytes, y, (cudaStream_t)stream);
+    NPPC_CHECK_ARG(R > 0 && Tp > 0 && R_stride >= R, "nppc_lstm_forward: bad sizes R=%d R_stride=%d Tp=%d", R, R_stride, Tp);
+    if (impl == 0) return nppc::lstm_forward_f32(plan, (const float*)xs, R, R_stride, Tp, KP, workspace, workspace_bytes, y, (cudaStream_t)stream);
+    if (impl == 1) return nppc::lstm_forward_tc(plan, xs, R, R_stride, Tp, KP, workspace, workspace_bytes, y, (cudaStream_t)stream);
     nppc::set_error("nppc_lstm_forward: unknown impl %d", impl);
     return NPPC_ERR_INVALID_ARGUMENT;
 }

@@ -19,10 +19,10 @@ struct nppc_lstm_plan {
 };
 
 namespace nppc {
-int lstm_forward_f32(const nppc_lstm_plan* p, const float* xs, int R, int Tp, int KP, void* ws, size_t ws_bytes,
+int lstm_forward_f32(const nppc_lstm_plan* p, const float* xs, int R, int RS, int Tp, int KP, void* ws, size_t ws_bytes,
                      float* y, cudaStream_t s);
 size_t lstm_workspace_f32(const nppc_lstm_plan* p, int R, int Tp);
-int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int Tp, int KP, void* ws, size_t ws_bytes,
+int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int Tp, int KP, void* ws, size_t ws_bytes,
                     float* y, cudaStream_t s);
 size_t lstm_workspace_tc(const nppc_lstm_plan* p, int R, int Tp);
 int lstm_plan_pack_tc(nppc_lstm_plan* p, const float* w_ih0, const float* w_hh0, const float* w_ih1,

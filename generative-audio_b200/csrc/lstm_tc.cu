@@ -14,11 +14,13 @@
 //   packed column = chunk*128 + half*64 + gate*16 + u   <->   nn.LSTM row gate*H + chunk*32 + half*16 + u.
 #include <stdlib.h>
 #include <string.h>
+#include <cuda_fp16.h>
 #include "lstm_plan.cuh"
 #include "tc_common.cuh"
 
 namespace nppc {
-int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s);
+int gemm_16bit_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, int f16,
+                  cudaStream_t s);
 }
 
 namespace {
@@ -32,26 +34,31 @@ constexpr int NCHUNK = H / CH;      // 12
 constexpr int NSLAB = H / 64;       // 6 K-slabs of 64
 constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have the same shape: 128 x 64 bf16)
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
-constexpr int OPMAX = 24;
+constexpr int OPMAX = 64;
 
+constexpr int HST_BYTES = ROWS * CH * 2;   // one chunk of h_t for the CTA's rows: [128][32] bf16 = 8 KB
+
+struct RecSmem {
+    static constexpr int NST = 6;                                        // W ring stages
+    static constexpr int A_OFF = 0;                                      // h_{t-1}: 6 slabs [128][64] bf16, SW128
+    static constexpr int W_OFF = NSLAB * SLAB_BYTES;                     // W_hh ring
+    static constexpr int HST_OFF = W_OFF + NST * SLAB_BYTES;             // 2 x [128][32] bf16 staging for the TMA store of h_t
+    static constexpr int BAR_OFF = HST_OFF + 2 * HST_BYTES;
 #ifdef NPPC_REC_TRACE
-__device__ unsigned long long g_trace[8 * 12 * 16];
-#define TRACE(t, j, slot) do { if (blockIdx.x == 0 && (t) >= 2 && (t) < 10) g_trace[(((t) - 2) * 12 + (j)) * 16 + (slot)] = clock64(); } while (0)
+    static constexpr int TRACE_OFF = BAR_OFF + 256;
+    static constexpr int TOTAL = TRACE_OFF + 4 * 12 * 16 * 8 + 1024;
 #else
-#define TRACE(t, j, slot) do { } while (0)
-#endif
-
-template <int OP>
-struct RecSmemT {
-    static constexpr int NST = OP > 16 ? 5 : 6;                          // W ring stages (227 KB budget)
-    static constexpr int A_OFF = 0;
-    static constexpr int W_OFF = NSLAB * SLAB_BYTES;
-    static constexpr int FC_OFF = W_OFF + NST * SLAB_BYTES;              // float [OP][H]
-    static constexpr int XCH_OFF = FC_OFF + OP * H * 4;                  // float [128][OP]
-    static constexpr int BAR_OFF = XCH_OFF + ROWS * OP * 4;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+#endif
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
+
+#ifdef NPPC_REC_TRACE
+__device__ long long g_trace[4 * 12 * 16];
+#define TRACE(slot) do { if ((t) >= 5 && (t) < 9 && (threadIdx.x & 31) == 0) trace_s[(((t) - 5) * 12 + (j)) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;
@@ -61,13 +68,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // CL = cluster size: the CL CTAs of a cluster share ONE W_hh stream — slab s is fetched from L2 by CTA (s % CL) and
-// multicast into every CTA's ring, so L2->SM traffic for the weights drops by CL (the kernel is L2-bandwidth-bound).
-template <int OP, int CL>
+// multicast into every CTA's ring.
+// Buffers are time-major with RS (multiple of 128) rows per step:  zx in the interleaved layout written by the GEMM
+// ([m_blk][chunk][warp-quad][half][piece][lane][8 bf16], m_blk = t*tiles + tile), hseq row-major [T'*RS][H].
+template <int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                const __nv_bfloat16* __restrict__ zx, __nv_bfloat16* __restrict__ hseq, int R, int Tp,
-                const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O, float* __restrict__ y, int dbg) {
-    using RecSmem = RecSmemT<OP>;
+                const __grid_constant__ CUtensorMap tmap_hst, const uint4* __restrict__ zx, int RS, int Tp) {
     constexpr int NST = RecSmem::NST;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,28 +85,33 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint64_t* acc_empty = acc_full + 1;
     uint64_t* h_ready = acc_empty + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(h_ready + 1);
-    float* fc_s = reinterpret_cast<float*>(smem + RecSmem::FC_OFF);
-    float* xch = reinterpret_cast<float*>(smem + RecSmem::XCH_OFF);
+#ifdef NPPC_REC_TRACE
+    long long* trace_s = reinterpret_cast<long long*>(smem + RecSmem::TRACE_OFF);
+    for (int i = threadIdx.x; i < 4 * 12 * 16; i += NTHREADS) trace_s[i] = 0;
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * ROWS;
+    const int tiles = RS / ROWS;
+    const int tile = blockIdx.x;          // CTAs beyond `tiles` (cluster padding) redo the last tile's loads, store nothing
+    const bool live = tile < tiles;
+    const int tile_c = live ? tile : tiles - 1;
+    const int row0 = tile_c * ROWS;
 
-    // zero the A operand (h_{-1} = 0) and stage the fc weights
+    // zero the A operand (h_{-1} = 0)
     for (int i = threadIdx.x; i < NSLAB * SLAB_BYTES / 16; i += NTHREADS)
         reinterpret_cast<uint4*>(smem + RecSmem::A_OFF)[i] = make_uint4(0, 0, 0, 0);
-    if (OP > 0)
-        for (int i = threadIdx.x; i < OP * H; i += NTHREADS) fc_s[i] = (i / H < O) ? fc_w[i] : 0.f;
     fence_proxy_async_smem();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_h);
+        tma_prefetch_desc(&tmap_hst);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
         for (int i = 0; i < NSLAB; ++i) mbar_init(&a_full[i], 1);
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 256);
-        mbar_init(h_ready, 256);
+        mbar_init(h_ready, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_ptr);
@@ -120,7 +132,6 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             for (int t = 0; t < Tp; ++t)
                 for (int j = 0; j < NCHUNK; ++j)
                     for (int k = 0; k < NSLAB; ++k, ++s) {
-                        if ((dbg & 1) && s >= (uint32_t)NST) continue;  // timing experiment: W ring filled once, never refilled
                         mbar_wait(&w_empty[stage], phase ^ 1);   // every CTA of the cluster has released this slot
                         mbar_arrive_expect_tx(&w_full[stage], SLAB_BYTES);
                         unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
@@ -130,26 +141,26 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     }
         }
     } else if (warp == 3) {
-        // ---- A producer: reload h_t (written to global by the epilogue) as the A operand of step t+1 ----
+        // ---- A producer: reload h_t (TMA-stored by the epilogue) as the A operand of step t+1 ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             for (int k = 0; k < NSLAB; ++k) mbar_arrive(&a_full[k]);  // step 0: zeros already in place
             for (int t = 1; t < Tp; ++t) {
                 mbar_wait(h_ready, (t - 1) & 1);
-                TRACE(t, 0, 13);
                 for (int k = 0; k < NSLAB; ++k) {
                     mbar_arrive_expect_tx(&a_full[k], SLAB_BYTES);
-                    tma_load_2d(smem + RecSmem::A_OFF + k * SLAB_BYTES, &tmap_h, &a_full[k], k * 64, (t - 1) * R + row0);
+                    tma_load_2d(smem + RecSmem::A_OFF + k * SLAB_BYTES, &tmap_h, &a_full[k], k * 64, (t - 1) * RS + row0);
                 }
             }
         }
     } else if (warp == 2) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     } else if (warp == 1) {
-        // ---- MMA issuer ----
+        // ---- MMA issuer: the whole warp runs the (warp-uniform) control flow so descriptors stay in uniform registers;
+        //      one elected lane issues tcgen05.mma / tcgen05.commit ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(ROWS, 128);
+        {
+            constexpr uint32_t idesc = umma_idesc_f16(ROWS, 128);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;  // chunk counter for the acc_empty parity
             const uint32_t a_base = smem_u32(smem + RecSmem::A_OFF);
@@ -157,25 +168,28 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             for (int t = 0; t < Tp; ++t) {
                 for (int j = 0; j < NCHUNK; ++j, ++it) {
                     mbar_wait(acc_empty, (it & 1) ^ 1);
-                    TRACE(t, j, 0);
+                    TRACE(0);
                     tcgen05_fence_after();
                     for (int k = 0; k < NSLAB; ++k) {
                         if (j == 0) mbar_wait(&a_full[k], t & 1);
-                        if (j == 0 && k == 0) TRACE(t, j, 8);
-                        if (!(dbg & 1) || it == 0) mbar_wait(&w_full[stage], phase);
-                        TRACE(t, j, 1 + k);
+                        mbar_wait(&w_full[stage], phase);
+                        if (k == 0) TRACE(1);
+                        if (k == 3) TRACE(2);
+                        if (k == 5) TRACE(3);
                         tcgen05_fence_after();
-                        uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
-                        uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
+                        const uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
+                        const uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
-                        if (dbg & 1) { }
-                        else if (CL == 1) umma_commit(&w_empty[stage]);
-                        else umma_commit_mcast(&w_empty[stage], CMASK);
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
+                            if (CL == 1) umma_commit(&w_empty[stage]);
+                            else umma_commit_mcast(&w_empty[stage], CMASK);
+                            if (k == NSLAB - 1) umma_commit(acc_full);
+                        }
+                        __syncwarp();
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(acc_full);
-                    TRACE(t, j, 7);
+                    TRACE(4);
                 }
             }
         }
@@ -184,10 +198,9 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int ew = warp & 3, half = (warp - 4) >> 2;
         const int rloc = ew * 32 + lane;
-        const int row = row0 + rloc;
-        const bool valid = row < R;
         const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
         const uint32_t t_acc = t_lane + half * 64;
+        unsigned char* hst = smem + RecSmem::HST_OFF;
         // c_0 = 0
         {
             uint32_t z[16];
@@ -197,26 +210,24 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             tmem_wait_st();
         }
         uint32_t it = 0;
-        // software-pipelined Zx stream: this thread's 64 pre-activations (i,f,g,o x 16 units = 128 contiguous bytes) of
-        // chunk it+1 are requested while chunk it is being computed; chunk it+3 is pulled into L2 ahead of that.
+        // software-pipelined Zx stream: this thread's 64 pre-activations (i,f,g,o x 16 units) of chunk j are the 128
+        // contiguous bytes at zx[(t*RS + row)*4H + j*128 + half*64] (row-major fp16, gate-permuted columns).  The loads
+        // for chunk it+1 are issued while chunk it is computed.
         auto zx_ptr = [&](int t, int j) -> const uint4* {
-            return reinterpret_cast<const uint4*>(zx + ((size_t)t * R + (valid ? row : 0)) * H4 + half * 64 + j * 128);
+            return zx + ((((size_t)t * RS + row0 + rloc) * H4 + j * 128 + half * 64) >> 3);
         };
         uint4 zraw[8];
         {
             const uint4* zp = zx_ptr(0, 0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) zraw[q] = valid ? __ldg(zp + q) : make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q);
         }
         for (int t = 0; t < Tp; ++t) {
-            float fcacc[OP > 0 ? OP : 1];
-#pragma unroll
-            for (int o = 0; o < (OP > 0 ? OP : 1); ++o) fcacc[o] = 0.f;
-            __nv_bfloat16* hrow = hseq + ((size_t)t * R + (valid ? row : 0)) * H + half * 16;
 #pragma unroll 1
             for (int j = 0; j < NCHUNK; ++j, ++it) {
                 mbar_wait(acc_full, it & 1);
-                if (threadIdx.x == 128) TRACE(t, j, 9);
+                if (threadIdx.x == 128) TRACE(5);
+                if (threadIdx.x == 352) TRACE(10);
                 tcgen05_fence_after();
                 uint32_t gi[16], gf[16], gg[16], go[16], cc[16];
                 tmem_ld16(t_acc + 0, gi);
@@ -227,93 +238,76 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 tmem_wait_ld();
                 tcgen05_fence_before();
                 mbar_arrive(acc_empty);  // accumulator is in registers: the next chunk's MMAs may start
-                if (threadIdx.x == 128) TRACE(t, j, 10);
+                if (threadIdx.x == 128) TRACE(6);
+                if (threadIdx.x == 352) TRACE(11);
                 uint4 zcur[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) zcur[q] = zraw[q];
                 {
                     int jn = j + 1, tn = t;
                     if (jn == NCHUNK) { jn = 0; tn = t + 1; }
-                    if (tn < Tp && valid && !(dbg & 4)) {
+                    if (tn < Tp) {
                         const uint4* zp = zx_ptr(tn, jn);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q);
-                        int jp = j + 3, tp = t;
-                        if (jp >= NCHUNK) { jp -= NCHUNK; tp = t + 1; }
-                        if (tp < Tp) asm volatile("prefetch.global.L2 [%0];" ::"l"(zx_ptr(tp, jp)));
                     }
                 }
-                const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(zcur);
-                uint32_t hp[8];
+                const __half2* zh = reinterpret_cast<const __half2*>(zcur);  // zh[gate*8 + u/2] = fp16 pair (u, u+1)
                 float hv[16];
-                if (dbg & 2) {
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) hv[u] = __uint_as_float(gi[u]) + __bfloat162float(zb[u]);
-                } else
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                    float zi = __uint_as_float(gi[u]) + __bfloat162float(zb[u]);
-                    float zf = __uint_as_float(gf[u]) + __bfloat162float(zb[16 + u]);
-                    float zg = __uint_as_float(gg[u]) + __bfloat162float(zb[32 + u]);
-                    float zo = __uint_as_float(go[u]) + __bfloat162float(zb[48 + u]);
+                    const float2 pi = __half22float2(zh[u >> 1]), pf = __half22float2(zh[8 + (u >> 1)]);
+                    const float2 pg = __half22float2(zh[16 + (u >> 1)]), po = __half22float2(zh[24 + (u >> 1)]);
+                    float zi = __uint_as_float(gi[u]) + ((u & 1) ? pi.y : pi.x);
+                    float zf = __uint_as_float(gf[u]) + ((u & 1) ? pf.y : pf.x);
+                    float zg = __uint_as_float(gg[u]) + ((u & 1) ? pg.y : pg.x);
+                    float zo = __uint_as_float(go[u]) + ((u & 1) ? po.y : po.x);
                     float c = sigmoid_fast(zf) * __uint_as_float(cc[u]) + sigmoid_fast(zi) * tanh_fast(zg);
                     cc[u] = __float_as_uint(c);
                     hv[u] = sigmoid_fast(zo) * tanh_fast(c);
                 }
                 tmem_st16(t_lane + 128 + j * CH + half * 16, cc);
+                if (threadIdx.x == 128) TRACE(7);
+                if (threadIdx.x == 352) TRACE(12);
+                // h_t chunk -> staging tile [128 rows][32 units] bf16 -> one TMA store per chunk (full-line writes)
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging buffer (j & 1) is free
+                {
+                    uint32_t hp[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    __nv_bfloat162 p = __floats2bfloat162_rn(hv[2 * u], hv[2 * u + 1]);
-                    hp[u] = *reinterpret_cast<uint32_t*>(&p);
-                }
-                if (valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(hrow + j * CH);
+                    for (int u = 0; u < 8; ++u) {
+                        __half2 p = __floats2half2_rn(hv[2 * u], hv[2 * u + 1]);
+                        hp[u] = *reinterpret_cast<uint32_t*>(&p);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(hst + (j & 1) * HST_BYTES + rloc * (CH * 2) + half * 32);
                     dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                     dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                 }
-                if (threadIdx.x == 128) TRACE(t, j, 11);
-                if (OP > 0) {
-                    const float* wf = fc_s + j * CH + half * 16;
-#pragma unroll
-                    for (int o = 0; o < OP; ++o) {
-                        const float4* w4 = reinterpret_cast<const float4*>(wf + o * H);
-                        float a = fcacc[o];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float4 w = w4[q];
-                            a = fmaf(hv[4 * q], w.x, a); a = fmaf(hv[4 * q + 1], w.y, a);
-                            a = fmaf(hv[4 * q + 2], w.z, a); a = fmaf(hv[4 * q + 3], w.w, a);
-                        }
-                        fcacc[o] = a;
-                    }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (threadIdx.x == 128 && live) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_hst),
+                                 "r"(smem_u32(hst + (j & 1) * HST_BYTES)), "r"(j * CH), "r"(t * RS + row0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                if (threadIdx.x == 128) TRACE(8);
+                if (threadIdx.x == 352) TRACE(13);
             }
-            // end of step: publish h_t to the async proxy (TMA reload), then the fc output of this step
+            // end of step: h_t fully written (async proxy) -> let the A producer reload it for step t+1
             tmem_wait_st();
-            __threadfence();
-            fence_proxy_async_all();
-            mbar_arrive(h_ready);
-            if (threadIdx.x == 128) TRACE(t, 11, 12);
-            if (OP > 0) {
-                if (half == 1) {
-#pragma unroll
-                    for (int o = 0; o < OP; ++o) xch[rloc * (OP > 0 ? OP : 1) + o] = fcacc[o];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && valid) {
-                    for (int o = 0; o < O; ++o) {
-                        float v = 0.f;
-#pragma unroll
-                        for (int oo = 0; oo < OP; ++oo) if (oo == o) v = fcacc[oo];
-                        y[((size_t)row * O + o) * Tp + t] = v + xch[rloc * (OP > 0 ? OP : 1) + o] + fc_b[o];
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 128) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                fence_proxy_async_all();
+                mbar_arrive(h_ready);
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
+#ifdef NPPC_REC_TRACE
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < 4 * 12 * 16; i += NTHREADS) g_trace[i] = trace_s[i];
+#endif
     if (CL > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
     if (warp == 2) {
         tcgen05_fence_after();
@@ -322,13 +316,13 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 }
 
 // fp32 [4H][K] (nn.LSTM row order) -> bf16 [4H][KP] with permuted rows, zero-padded K
-__global__ void pack_w_kernel(const float* __restrict__ w, int K, int KP, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_w_kernel(const float* __restrict__ w, int K, int KP, __half* __restrict__ out) {
     long long n = (long long)H4 * KP;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int p = (int)(i / KP), k = (int)(i - (long long)p * KP);
         int chunk = p >> 7, half = (p >> 6) & 1, gate = (p >> 4) & 3, u = p & 15;
         int src = gate * H + chunk * CH + half * 16 + u;
-        out[i] = __float2bfloat16(k < K ? w[(size_t)src * K + k] : 0.f);
+        out[i] = __float2half_rn(k < K ? fminf(fmaxf(w[(size_t)src * K + k], -65504.f), 65504.f) : 0.f);
     }
 }
 __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ out) {
@@ -339,15 +333,53 @@ __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ o
     }
 }
 
-template <int OP, int CL>
-int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloat16* zx, __nv_bfloat16* hseq, int R, int Tp,
-                  const float* fc_w, const float* fc_b, int O, float* y, cudaStream_t s) {
-    using RecSmem = RecSmemT<OP>;
-    auto kern = lstm_rec_kernel<OP, CL>;
+// fc_output_layer over the h sequence of the last layer: y[row][o][t] = b[o] + sum_k W[o][k] * h[t][row][k]
+// (sequence_model.py:79,119). HBM-bound: one read of hseq (bf16), O*4 bytes written per (row, t).
+constexpr int FC_ROWS = 64;
+__global__ void __launch_bounds__(256) lstm_fc_kernel(const __half* __restrict__ hseq, int R, int RS, int Tp,
+                                                      const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O,
+                                                      float* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    constexpr int HP = H + 8;                                   // padded row (bf16 elements) -> conflict-free row stride
+    __half* hs = reinterpret_cast<__half*>(fsm);  // [FC_ROWS][HP]
+    float* wt = reinterpret_cast<float*>(fsm + FC_ROWS * HP * 2);  // [H][O] transposed weights
+    const int t = blockIdx.y;
+    const int row0 = blockIdx.x * FC_ROWS;
+    for (int i = threadIdx.x; i < H * O; i += blockDim.x) {
+        int k = i / O, o = i - k * O;
+        wt[i] = fc_w[(size_t)o * H + k];
+    }
+    // coalesced 16-byte loads of the [FC_ROWS][H] tile
+    for (int i = threadIdx.x; i < FC_ROWS * (H / 8); i += blockDim.x) {
+        int r = i / (H / 8), c = i - r * (H / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row0 + r < R) v = __ldg(reinterpret_cast<const uint4*>(hseq + ((size_t)t * RS + row0 + r) * H) + c);
+        *reinterpret_cast<uint4*>(hs + r * HP + c * 8) = v;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < FC_ROWS * O; p += blockDim.x) {
+        int r = p / O, o = p - r * O;
+        if (row0 + r >= R) continue;
+        const __half2* hr = reinterpret_cast<const __half2*>(hs + r * HP);
+        float acc = fc_b[o];
+#pragma unroll 8
+        for (int k2 = 0; k2 < H / 2; ++k2) {
+            float2 hv = __half22float2(hr[k2]);
+            acc = fmaf(hv.x, wt[(2 * k2) * O + o], acc);
+            acc = fmaf(hv.y, wt[(2 * k2 + 1) * O + o], acc);
+        }
+        y[((size_t)(row0 + r) * O + o) * Tp + t] = acc;
+    }
+}
+
+template <int CL>
+int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const void* zx, int RS, int Tp,
+                  cudaStream_t s) {
+    auto kern = lstm_rec_kernel<CL>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
-    int tiles = nppc::cdiv(R, ROWS);
+    int tiles = RS / ROWS;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nppc::cdiv(tiles, CL) * CL));  // padded CTAs own no valid rows but keep the cluster protocol
+    cfg.gridDim = dim3((unsigned)(nppc::cdiv(tiles, CL) * CL));  // padded CTAs keep the cluster protocol, store nothing
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = RecSmem::TOTAL;
     cfg.stream = s;
@@ -358,8 +390,7 @@ int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static int dbg = getenv("NPPC_REC_DBG") ? atoi(getenv("NPPC_REC_DBG")) : 0;
-    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, dbg));
+    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, (const uint4*)zx, RS, Tp));
     NPPC_COUNT_LAUNCH(1);
     return NPPC_OK;
 }
@@ -368,19 +399,18 @@ int rec_cluster_size() {
     static int cl = -1;
     if (cl < 0) {
         const char* e = getenv("NPPC_LSTM_CLUSTER");
-        cl = e ? atoi(e) : 4;
-        if (cl != 1 && cl != 2 && cl != 4) cl = 4;
+        cl = e ? atoi(e) : 2;
+        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
     }
     return cl;
 }
 
-template <int OP>
-int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const __nv_bfloat16* zx, __nv_bfloat16* hseq, int R, int Tp,
-               const float* fc_w, const float* fc_b, int O, float* y, cudaStream_t s) {
+int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const void* zx, int RS, int Tp,
+               cudaStream_t s) {
     switch (rec_cluster_size()) {
-        case 1: return launch_rec_cl<OP, 1>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
-        case 2: return launch_rec_cl<OP, 2>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
-        default: return launch_rec_cl<OP, 4>(tw, th, zx, hseq, R, Tp, fc_w, fc_b, O, y, s);
+        case 1: return launch_rec_cl<1>(tw, th, thst, zx, RS, Tp, s);
+        case 2: return launch_rec_cl<2>(tw, th, thst, zx, RS, Tp, s);
+        default: return launch_rec_cl<4>(tw, th, thst, zx, RS, Tp, s);
     }
 }
 
@@ -390,8 +420,8 @@ namespace nppc {
 
 size_t lstm_workspace_tc(const nppc_lstm_plan* p, int R, int Tp) {
     (void)p;
-    size_t rows = (size_t)Tp * R + ROWS;  // + one tile of slack for the row tail of the last step
-    return rows * H4 * 2 + rows * H * 2 + 512;
+    size_t rows = (size_t)Tp * (size_t)(cdiv(R, ROWS) * ROWS);
+    return rows * H4 * 2 + rows * H * 2 + 1024;
 }
 
 int lstm_plan_pack_tc(nppc_lstm_plan* p, const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
@@ -405,8 +435,8 @@ int lstm_plan_pack_tc(nppc_lstm_plan* p, const float* w_ih0, const float* w_hh0,
         NPPC_CUDA_OK(cudaMalloc(&p->wp_ih[l], sizeof(__nv_bfloat16) * (size_t)H4 * KP));
         NPPC_CUDA_OK(cudaMalloc(&p->wp_hh[l], sizeof(__nv_bfloat16) * (size_t)H4 * H));
         NPPC_CUDA_OK(cudaMalloc(&p->bias_p[l], sizeof(float) * H4));
-        pack_w_kernel<<<256, 256, 0, s>>>(wih[l], Kin, KP, p->wp_ih[l]);
-        pack_w_kernel<<<256, 256, 0, s>>>(whh[l], H, H, p->wp_hh[l]);
+        pack_w_kernel<<<256, 256, 0, s>>>(wih[l], Kin, KP, (__half*)p->wp_ih[l]);
+        pack_w_kernel<<<256, 256, 0, s>>>(whh[l], H, H, (__half*)p->wp_hh[l]);
         pack_b_kernel<<<cdiv(H4, 256), 256, 0, s>>>(p->bias[l], p->bias_p[l]);
     }
     NPPC_LAUNCH_OK();
@@ -419,42 +449,52 @@ void lstm_plan_free_tc(nppc_lstm_plan* p) {
     }
 }
 
-int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int Tp, int KP, void* ws, size_t ws_bytes, float* y,
-                    cudaStream_t s) {
+int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int Tp, int KP, void* ws, size_t ws_bytes,
+                    float* y, cudaStream_t s) {
     NPPC_CHECK_ARG(p->H == H && p->wp_hh[0], "nppc_lstm_forward(impl 1): the tcgen05 path is built for H=384 (got %d)", p->H);
     NPPC_CHECK_ARG(KP == p->KP0, "nppc_lstm_forward(impl 1): KP must be %d (got %d)", p->KP0, KP);
     NPPC_CHECK_ARG(p->O <= OPMAX, "nppc_lstm_forward(impl 1): output size %d > %d", p->O, OPMAX);
+    NPPC_CHECK_ARG(RS == cdiv(R, ROWS) * ROWS, "nppc_lstm_forward(impl 1): R_stride must be R rounded up to %d (got %d for R=%d)",
+                   ROWS, RS, R);
     NPPC_CHECK_ARG(ws_bytes >= lstm_workspace_tc(p, R, Tp), "nppc_lstm_forward: workspace too small");
-    NPPC_CHECK_ARG((long long)Tp * R + ROWS < (1LL << 31), "nppc_lstm_forward(impl 1): T'*R too large");
-    const size_t rows = (size_t)Tp * R + ROWS;
+    NPPC_CHECK_ARG((long long)Tp * RS < (1LL << 31), "nppc_lstm_forward(impl 1): T'*R too large");
+    const size_t rows = (size_t)Tp * RS;
     uintptr_t base = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
     __nv_bfloat16* zx = (__nv_bfloat16*)base;
     __nv_bfloat16* hseq = zx + rows * H4;
-    const long long M = (long long)Tp * R;
-    CUtensorMap tw[2], th;
+    const long long M = (long long)rows;
+    CUtensorMap tw[2], th, thst;
     for (int l = 0; l < 2; ++l) {
         int rc = tc::make_tmap_bf16_2d(&tw[l], p->wp_hh[l], H4, H, H * 2, 128, 64);
         if (rc) return rc;
     }
     int rc = tc::make_tmap_bf16_2d(&th, hseq, (uint64_t)M, H, H * 2, ROWS, 64);
     if (rc) return rc;
-    // layer 0
-    rc = gemm_bf16_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, s);
+    rc = tc::make_tmap_bf16_2d(&thst, hseq, (uint64_t)M, H, H * 2, ROWS, CH, 0);
     if (rc) return rc;
-    rc = launch_rec<0>(tw[0], th, zx, hseq, R, Tp, nullptr, nullptr, 0, nullptr, s);
+    // layer 0
+    rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 1, s);
+    if (rc) return rc;
+    rc = launch_rec(tw[0], th, thst, zx, RS, Tp, s);
     if (rc) return rc;
     // layer 1 (+ fc)
-    rc = gemm_bf16_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, s);
+    rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 1, s);
     if (rc) return rc;
-    if (p->O <= 8) return launch_rec<8>(tw[1], th, zx, hseq, R, Tp, p->fc_w, p->fc_b, p->O, y, s);
-    if (p->O <= 16) return launch_rec<16>(tw[1], th, zx, hseq, R, Tp, p->fc_w, p->fc_b, p->O, y, s);
-    return launch_rec<24>(tw[1], th, zx, hseq, R, Tp, p->fc_w, p->fc_b, p->O, y, s);
+    rc = launch_rec(tw[1], th, thst, zx, RS, Tp, s);
+    if (rc) return rc;
+    size_t fsm = (size_t)FC_ROWS * (H + 8) * 2 + (size_t)H * p->O * 4;
+    NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    lstm_fc_kernel<<<dim3(cdiv(R, FC_ROWS), Tp), 256, fsm, s>>>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
 }
 
 }  // namespace nppc
 
+
 #ifdef NPPC_REC_TRACE
-extern "C" int nppc_debug_rec_trace(unsigned long long* host_out) {
+extern "C" int nppc_debug_rec_trace(long long* host_out) {
     return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(g_trace)) == cudaSuccess ? 0 : -2;
 }
 #endif

@@ -108,6 +108,10 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with IEEE fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -174,7 +178,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- host: TMA descriptor for a row-major bf16 matrix [rows][cols], box [box_rows][64 cols] with 128B swizzle ---
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                      uint32_t box_rows, uint32_t box_cols);
+                      uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 }  // namespace tc
 }  // namespace nppc

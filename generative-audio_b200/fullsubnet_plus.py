@@ -2,7 +2,7 @@
 
 Data flow per forward (all device-resident, fp32 unless noted):
   pad+offline-norm (1 fused kernel per plane) -> TSSE -> TCN (torch library ops, "next" row N2)
-  -> fused sub-band pack (unfold ++ cat ++ norm ++ drop_band, written time-major [T',R,64]; bf16 for the
+  -> fused sub-band pack (unfold ++ cat ++ norm ++ drop_band, written time-major [T',R,64]; fp16 for the
      tensor-core LSTM) -> 2-layer LSTM + fc kernels -> mask assembly kernel.
 The [B,F,34,T'] sub-band tensor of the reference is never materialised."""
 from typing import Optional
@@ -72,11 +72,11 @@ class FullSubNet_Plus(nn.Module):
         """-> (y [R,O,T'], F') from the four [B,F,T'] planes."""
         B, F, Tp = fb.shape
         impl = _IMPL[self.lstm_impl]
-        dt = torch.bfloat16 if impl == 1 else torch.float32
+        dt = torch.float16 if impl == 1 else torch.float32
         G = self.num_groups_in_drop_band
         if self.norm_type == "offline_laplace_norm":
-            xs = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt)
-            Fp = xs.shape[1] // B
+            xs, R = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt)
+            Fp = R // B
         else:
             # explicit route through the standalone kernels (cumulative norm is not fused into the packer)
             n = self.sb_num_neighbors
@@ -87,9 +87,10 @@ class FullSubNet_Plus(nn.Module):
                 sb = ops.drop_band(sb.permute(0, 2, 1, 3).contiguous(), G).permute(0, 2, 1, 3)
             Fp = sb.shape[1]
             S = sb.shape[2]
-            xs = torch.zeros(Tp, B * Fp, KP, device=fb.device, dtype=dt)
-            xs[:, :, :S] = sb.reshape(B * Fp, S, Tp).permute(2, 0, 1).to(dt)
-        return self.sb_model.lstm_forward(xs, impl), Fp
+            R = B * Fp
+            xs = torch.zeros(Tp, ops.padded_rows(R, dt), KP, device=fb.device, dtype=dt)
+            xs[:, :R, :S] = sb.reshape(R, S, Tp).permute(2, 0, 1).to(dt)
+        return self.sb_model.lstm_forward(xs, impl, R), Fp
 
     @torch.no_grad()
     def forward(self, noisy_mag, noisy_real, noisy_imag):

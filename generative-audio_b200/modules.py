@@ -113,8 +113,8 @@ class SequenceModel(nn.Module):
             self._plan_key = key
         return self._plan
 
-    def lstm_forward(self, xs, impl: int):
-        """xs [T', R, KP] -> [R, O, T'] (the layout SequenceModel.forward returns, sequence_model.py:122)."""
+    def lstm_forward(self, xs, impl: int, R: int = None):
+        """xs [T', R_stride, KP] -> [R, O, T'] (the layout SequenceModel.forward returns, sequence_model.py:122)."""
         if self.output_activate_function:
             raise NotImplementedError("sb_output_activate_function is False in every reference config")
-        return self._lstm_plan().forward(xs, impl)
+        return self._lstm_plan().forward(xs, impl, R)

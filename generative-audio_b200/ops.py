@@ -5,6 +5,7 @@ import torch
 from . import _lib
 
 _BF16 = torch.bfloat16
+_F16 = torch.float16  # operand dtype of the tensor-core LSTM path
 
 
 def _chk(*ts):
@@ -226,20 +227,29 @@ def projection_loss(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
                 second_moment_mse=sm)
 
 
+TC_ROW_TILE = 128  # the tensor-core LSTM owns 128 sequences per CTA; its time-major buffers pad rows to this
+
+
+def padded_rows(R: int, dtype) -> int:
+    return -(-R // TC_ROW_TILE) * TC_ROW_TILE if dtype == _F16 else R
+
+
 def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int = 64, dtype=torch.float32):
-    """Fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> time-major LSTM input [T', R, KP]."""
+    """Fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> time-major LSTM input [T', R_stride, KP]
+    (R = B*F' real rows; rows R..R_stride-1 are zero padding for the tensor-core path). Returns (xs, R)."""
     nbr_src, fb, fbr, fbi = (_f32(v) for v in (nbr_src, fb, fbr, fbi))
     _chk(nbr_src, fb, fbr, fbi)
     B, F, Tp = nbr_src.shape
     G = groups if (groups > 1 and B > 1) else 1
     R = B * (F // G)
-    xs = torch.empty(Tp, R, KP, device=fb.device, dtype=dtype)
+    RS = padded_rows(R, dtype)
+    xs = torch.empty(Tp, RS, KP, device=fb.device, dtype=dtype)
     sums = torch.empty(B, device=fb.device, dtype=torch.float64)
     _lib.check(_lib.load().nppc_subband_pack(nbr_src.data_ptr(), fb.data_ptr(), fbr.data_ptr(), fbi.data_ptr(), B, F, Tp,
-                                             num_neighbor, groups, KP, sums.data_ptr(),
+                                             num_neighbor, groups, KP, RS, sums.data_ptr(),
                                              xs.data_ptr() if dtype == torch.float32 else 0,
-                                             xs.data_ptr() if dtype == _BF16 else 0, _stream()), "nppc_subband_pack")
-    return xs
+                                             xs.data_ptr() if dtype == _F16 else 0, _stream()), "nppc_subband_pack")
+    return xs, R
 
 
 class LstmPlan:
@@ -266,17 +276,18 @@ class LstmPlan:
         except Exception:
             pass
 
-    def forward(self, xs: torch.Tensor, impl: int):
-        """xs [T', R, KP] (fp32 for impl 0, bf16 for impl 1) -> y [R, O, T'] fp32."""
+    def forward(self, xs: torch.Tensor, impl: int, R: int = None):
+        """xs [T', R_stride, KP] (fp32 for impl 0; fp16 with R_stride = R rounded up to 128 for impl 1) -> y [R, O, T']."""
         _chk(xs)
-        Tp, R, KP = xs.shape
-        if impl == 0 and xs.dtype != torch.float32 or impl == 1 and xs.dtype != _BF16:
+        Tp, RS, KP = xs.shape
+        R = RS if R is None else R
+        if impl == 0 and xs.dtype != torch.float32 or impl == 1 and xs.dtype != _F16:
             raise RuntimeError("LstmPlan.forward: xs dtype does not match impl")
         lib = _lib.load()
         nbytes = lib.nppc_lstm_workspace_bytes(self._h, R, Tp, impl)
         ws = torch.empty(max(nbytes, 16), device=xs.device, dtype=torch.uint8)
         y = torch.empty(R, self.O, Tp, device=xs.device, dtype=torch.float32)
-        _lib.check(lib.nppc_lstm_forward(self._h, xs.data_ptr(), R, Tp, KP, impl, ws.data_ptr(), nbytes, y.data_ptr(),
+        _lib.check(lib.nppc_lstm_forward(self._h, xs.data_ptr(), R, RS, Tp, KP, impl, ws.data_ptr(), nbytes, y.data_ptr(),
                                          _stream()), "nppc_lstm_forward")
         return y
 

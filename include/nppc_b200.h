@@ -103,12 +103,13 @@ int nppc_projection_loss(const float* w_mat, const float* gt, const float* pred,
 /* ---- a5+a2 fused for the sub-band LSTM: feature packing ------------------------------------------
  * Builds the sub-band model input of fullsubnet_plus.py:203-223 / networks.py:133-151 without materialising
  * the [B,F,34,T'] tensor: unfold(nbr_src, N) ++ fb ++ fbr ++ fbi, offline_laplace_norm over (F,S,T') per
- * sample, drop_band(groups) row selection, written TIME-MAJOR as xs [T', R, KP] (KP >= S, zero padded),
+ * sample, drop_band(groups) row selection, written TIME-MAJOR as xs [T', R_stride, KP] (KP >= S, zero padded;
+ * rows R..R_stride-1 of every step are zero: the tensor-core LSTM wants R_stride % 128 == 0),
  * R = B*F' rows ordered like the reference's reshape(B*F', S, T').  nbr_src/fb/fbr/fbi are [B,F,T'].
- * xs_f32 (fp32) and/or xs_bf16 may be NULL.  `sums` [B] fp64 scratch. */
+ * xs_f32 (fp32) and/or xs_f16 (IEEE fp16, saturating) may be NULL.  `sums` [B] fp64 scratch. */
 int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B, int F,
-                      int Tp, int num_neighbor, int groups, int KP, double* sums, float* xs_f32,
-                      void* xs_bf16, void* stream);
+                      int Tp, int num_neighbor, int groups, int KP, int R_stride, double* sums, float* xs_f32,
+                      void* xs_f16, void* stream);
 
 /* ---- a7: sub-band LSTM (2 layers) + fc -----------------------------------------------------------
  * Replaces nn.LSTM(I->H, 2 layers, batch_first) + nn.Linear(H->O) of SequenceModel
@@ -123,11 +124,12 @@ int nppc_lstm_plan_create(nppc_lstm_plan** plan, int I, int H, int O, const floa
                           void* stream);
 void nppc_lstm_plan_destroy(nppc_lstm_plan* plan);
 /* Workspace bytes needed by nppc_lstm_forward for R rows x Tp steps with the given implementation
- * (impl: 0 = fp32 SIMT reference-precision path, 1 = bf16 tcgen05 tensor-core path). */
+ * (impl: 0 = fp32 SIMT reference-precision path, 1 = fp16-operand / fp32-accumulate tcgen05 tensor-core path). */
 size_t nppc_lstm_workspace_bytes(const nppc_lstm_plan* plan, int R, int Tp, int impl);
-/* xs: time-major input [Tp, R, KP] (fp32 for impl 0, bf16 for impl 1; KP as given to nppc_subband_pack).
+/* xs: time-major input [Tp, R_stride, KP] (fp32 for impl 0, fp16 for impl 1; KP / R_stride as given to
+ * nppc_subband_pack; impl 1 needs R_stride % 128 == 0).
  * y: [R, O, Tp] fp32 — the layout SequenceModel.forward returns (sequence_model.py:122). */
-int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int Tp, int KP, int impl,
+int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int R_stride, int Tp, int KP, int impl,
                       void* workspace, size_t workspace_bytes, float* y, void* stream);
 
 /* ---- a8/a11 output assembly -----------------------------------------------------------------------

@@ -179,12 +179,16 @@ def test_subband_pack(ops, B, G):
     if B > 1:
         sb = O.drop_band(sb.permute(0, 2, 1, 3), G).permute(0, 2, 1, 3)
     ref = sb.reshape(-1, 34, Tp).permute(2, 0, 1)  # [T', R, 34]
-    xs = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.float32).cpu()
-    assert xs.shape == (Tp, ref.shape[1], 64)
+    xs, R = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.float32)
+    xs = xs.cpu()
+    assert R == ref.shape[1] and xs.shape == (Tp, R, 64)
     assert rel_err(xs[:, :, :34], ref) < TOL
     assert torch.count_nonzero(xs[:, :, 34:]) == 0
-    xb = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.bfloat16).cpu().float()
-    assert rel_err(xb[:, :, :34], ref) < 1e-2
+    xb, R2 = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.float16)
+    xb = xb.cpu().float()
+    assert R2 == R and xb.shape[1] % 128 == 0 and xb.shape[1] >= R
+    assert rel_err(xb[:, :R, :34], ref) < 1e-2
+    assert torch.count_nonzero(xb[:, R:, :]) == 0
 
 
 def test_lstm_f32(ops):

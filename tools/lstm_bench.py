@@ -21,16 +21,19 @@ plan = g.ops.LstmPlan(*[p[lp + f"{k}_l{l}"].cuda() for l in (0, 1) for k in ("we
                       p["sb_model.fc_output_layer.weight"].cuda(), p["sb_model.fc_output_layer.bias"].cuda())
 R, Tp = B * 257, 253
 torch.manual_seed(0)
-xs = torch.randn(Tp, R, 64, device="cuda").to(torch.bfloat16 if impl == 1 else torch.float32)
+dt = torch.float16 if impl == 1 else torch.float32
+RS = g.ops.padded_rows(R, dt)
+xs = torch.randn(Tp, RS, 64, device="cuda").to(dt)
 xs[:, :, 34:] = 0
+xs[:, R:] = 0
 for _ in range(2):
-    y = plan.forward(xs, impl)
+    y = plan.forward(xs, impl, R)
 torch.cuda.synchronize()
 ts = []
 for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    y = plan.forward(xs, impl)
+    y = plan.forward(xs, impl, R)
     e1.record()
     e1.synchronize()
     ts.append(e0.elapsed_time(e1))

@@ -1,7 +1,6 @@
-"""Debug: per-chunk timeline of the recurrent LSTM kernel (needs a library built with -DNPPC_REC_TRACE)."""
+"""Debug: per-chunk timeline of the recurrent LSTM kernel (library built with NPPC_REC_TRACE=1)."""
 import ctypes as C
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,19 +18,19 @@ lp = "sb_model.sequence_model."
 plan = g.ops.LstmPlan(*[p[lp + f"{k}_l{l}"].cuda() for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")],
                       p["sb_model.fc_output_layer.weight"].cuda(), p["sb_model.fc_output_layer.bias"].cuda())
 R, Tp = B * 257, 40
+RS = g.ops.padded_rows(R, torch.bfloat16)
 torch.manual_seed(0)
-xs = torch.randn(Tp, R, 64, device="cuda").to(torch.bfloat16)
-y = plan.forward(xs, 1)
+xs = torch.randn(Tp, RS, 64, device="cuda").to(torch.bfloat16)
+y = plan.forward(xs, 1, R)
 torch.cuda.synchronize()
 lib = g._lib.load()
-buf = (C.c_ulonglong * (8 * 12 * 16))()
+buf = (C.c_longlong * (4 * 12 * 16))()
 lib.nppc_debug_rec_trace.argtypes = [C.c_void_p]
 assert lib.nppc_debug_rec_trace(buf) == 0
-a = np.array(buf, dtype=np.int64).reshape(8, 12, 16)
+a = np.array(buf, dtype=np.int64).reshape(4, 12, 16)
 t0 = a[0, 0, 0]
-np.set_printoptions(linewidth=250)
-print("slots: 0 acc_empty ok | 1-6 w_full[k] ok | 7 commit issued | 8 a_full[0] ok | 9 epi acc_full seen | 10 epi arrive acc_empty | 11 epi math done | 12 h_ready arrive | 13 A-producer woke")
+print("MMA: 0 acc_empty ok | 1 w_full[0] ok | 2 w_full[3] ok | 3 w_full[5] ok | 4 commit issued || epi warp4: 5 acc_full seen | 6 arrived acc_empty | 7 math+STTM done | 8 h staged+TMA issued || epi warp11: 10..13 same")
 for t in range(3):
     for j in range(12):
         r = a[t, j] - t0
-        print(f"t={t+2} j={j:2d} " + " ".join(f"{int(v):7d}" if v > -10**9 and a[t, j, i] != 0 else "      -" for i, v in enumerate(r[:14])))
+        print(f"t={t+5} j={j:2d} " + " ".join(f"{int(v):7d}" if a[t, j, i] != 0 else "      -" for i, v in enumerate(r[:14])))
