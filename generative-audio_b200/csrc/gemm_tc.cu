@@ -29,7 +29,7 @@ struct GemmSmem {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int BN, bool F16>
+template <int BN, bool F16, bool ZX>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, long long M, int N, int K) {
@@ -136,13 +136,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         packed[i] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 }
-                // staging layout = TMA SWIZZLE_128B box [128 rows][64 cols]: 16-byte chunk q of row r lives at q ^ (r & 7)
-                unsigned char* box = cs + (c >> 1) * (BM * 128) + rloc * 128;
+                if (ZX) {
+                    // LSTM pre-activation layout (see lstm_tc.cu): [m_blk][chunk][warp-quad][half][piece q][lane][8 x fp16],
+                    // staged in exactly that order (conflict-free 16-byte stores) so that each 128-column chunk of the tile
+                    // is one contiguous 32 KB block in global memory; the recurrent kernel's epilogue thread (same
+                    // row <-> lane mapping) reads its 64 values back with fully coalesced 16-byte loads.
+                    const int col = c * 32;
+                    const int chunk_l = col >> 7, half = (col >> 6) & 1, q0 = (col >> 3) & 7;
+                    uint4* dst = reinterpret_cast<uint4*>(cs) + ((((chunk_l * 4 + ew) * 2 + half) * 8 + q0) * 32 + lane);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int chunk = ((c & 1) * 4 + q) ^ (rloc & 7);
-                    *reinterpret_cast<uint4*>(box + chunk * 16) =
-                        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q)
+                        dst[q * 32] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                } else {
+                    // staging layout = TMA SWIZZLE_128B box [128 rows][64 cols]: 16-byte chunk q of row r lives at q ^ (r & 7)
+                    unsigned char* box = cs + (c >> 1) * (BM * 128) + rloc * 128;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int chunk = ((c & 1) * 4 + q) ^ (rloc & 7);
+                        *reinterpret_cast<uint4*>(box + chunk * 16) =
+                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    }
                 }
             }
             // accumulator stage is free as soon as it is in shared memory
@@ -151,11 +164,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 128) {
+                if (ZX) {
+                    // tmap_c views the interleaved buffer as [blocks*256 rows][64 x 16 bit]: one 32 KB block = 256 rows
 #pragma unroll
-                for (int cb = 0; cb < BN / 64; ++cb)
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_c),
-                                 "r"(smem_u32(cs + cb * (BM * 128))), "r"(n_blk * BN + cb * 64), "r"(m_blk * BM)
-                                 : "memory");
+                    for (int cl = 0; cl < BN / 128; ++cl)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_c),
+                                     "r"(smem_u32(cs + cl * 32768)), "r"(0),
+                                     "r"((m_blk * (N >> 7) + n_blk * (BN / 128) + cl) * 256)
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int cb = 0; cb < BN / 64; ++cb)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_c),
+                                     "r"(smem_u32(cs + cb * (BM * 128))), "r"(n_blk * BN + cb * 64), "r"(m_blk * BM)
+                                     : "memory");
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
@@ -170,7 +193,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
-template <int BN, bool F16>
+template <int BN, bool F16, bool ZX>
 int launch_gemm(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, BM, BK);
@@ -178,13 +201,14 @@ int launch_gemm(const void* A, const void* W, const float* bias, void* C, long l
     rc = make_tmap_bf16_2d(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, BK);
     if (rc) return rc;
     CUtensorMap tcm;
-    rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, BM, 64);
+    if (ZX) rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)(M / 128) * (N / 128) * 256, 64, 128, 256, 64, 0);
+    else rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, BM, 64);
     if (rc) return rc;
     using S = GemmSmem<BN>;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, F16, ZX>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     long long tiles = ((M + BM - 1) / BM) * (N / BN);
     int grid = (int)(tiles < nppc::sm_count() ? tiles : nppc::sm_count());
-    gemm_bf16_tn_kernel<BN, F16><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
+    gemm_bf16_tn_kernel<BN, F16, ZX><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -201,8 +225,13 @@ int gemm_16bit_tn(const void* A, const void* W, const float* bias, void* C, long
                    "nppc_gemm_bf16_tn: need K %% 64 == 0 and N %% 128 == 0 (M=%lld N=%d K=%d)", M, N, K);
     NPPC_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)C % 16 == 0),
                    "nppc_gemm_bf16_tn: pointers must be 16-byte aligned");
-    if (f16) return N % 256 == 0 ? launch_gemm<256, true>(A, W, bias, C, M, N, K, s) : launch_gemm<128, true>(A, W, bias, C, M, N, K, s);
-    return N % 256 == 0 ? launch_gemm<256, false>(A, W, bias, C, M, N, K, s) : launch_gemm<128, false>(A, W, bias, C, M, N, K, s);
+    if (f16 == 2) {  // fp16 operands, output in the LSTM pre-activation layout
+        NPPC_CHECK_ARG(M % 128 == 0 && N % 256 == 0 && (M / 128) * (N / 128) * 256 < (1LL << 31),
+                       "gemm (LSTM layout): need M %% 128 == 0, N %% 256 == 0");
+        return launch_gemm<256, true, true>(A, W, bias, C, M, N, K, s);
+    }
+    if (f16) return N % 256 == 0 ? launch_gemm<256, true, false>(A, W, bias, C, M, N, K, s) : launch_gemm<128, true, false>(A, W, bias, C, M, N, K, s);
+    return N % 256 == 0 ? launch_gemm<256, false, false>(A, W, bias, C, M, N, K, s) : launch_gemm<128, false, false>(A, W, bias, C, M, N, K, s);
 }
 }  // namespace nppc
 

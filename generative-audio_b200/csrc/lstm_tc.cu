@@ -210,17 +210,17 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             tmem_wait_st();
         }
         uint32_t it = 0;
-        // software-pipelined Zx stream: this thread's 64 pre-activations (i,f,g,o x 16 units) of chunk j are the 128
-        // contiguous bytes at zx[(t*RS + row)*4H + j*128 + half*64] (row-major fp16, gate-permuted columns).  The loads
-        // for chunk it+1 are issued while chunk it is computed.
+        // software-pipelined Zx stream: piece q of this thread's 64 pre-activations (i,f,g,o x 16 units, fp16) for chunk
+        // (t, j) is the uint4 at ((((t*tiles + tile)*12 + j)*4 + ew)*2 + half)*256 + q*32 + lane  (layout written by the
+        // GEMM epilogue) -> each warp-wide load reads 512 contiguous bytes.  Chunk it+1 is requested while it is computed.
         auto zx_ptr = [&](int t, int j) -> const uint4* {
-            return zx + ((((size_t)t * RS + row0 + rloc) * H4 + j * 128 + half * 64) >> 3);
+            return zx + (((((size_t)t * tiles + tile_c) * NCHUNK + j) * 4 + ew) * 2 + half) * 256 + lane;
         };
         uint4 zraw[8];
         {
             const uint4* zp = zx_ptr(0, 0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q);
+            for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
         }
         for (int t = 0; t < Tp; ++t) {
 #pragma unroll 1
@@ -249,7 +249,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     if (tn < Tp) {
                         const uint4* zp = zx_ptr(tn, jn);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q);
+                        for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
                     }
                 }
                 const __half2* zh = reinterpret_cast<const __half2*>(zcur);  // zh[gate*8 + u/2] = fp16 pair (u, u+1)
@@ -473,12 +473,12 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     rc = tc::make_tmap_bf16_2d(&thst, hseq, (uint64_t)M, H, H * 2, ROWS, CH, 0);
     if (rc) return rc;
     // layer 0
-    rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 1, s);
+    rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
     if (rc) return rc;
     rc = launch_rec(tw[0], th, thst, zx, RS, Tp, s);
     if (rc) return rc;
     // layer 1 (+ fc)
-    rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 1, s);
+    rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
     if (rc) return rc;
     rc = launch_rec(tw[1], th, thst, zx, RS, Tp, s);
     if (rc) return rc;
