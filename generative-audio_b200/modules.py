@@ -32,11 +32,11 @@ class ChannelTimeSenseSELayer(nn.Module):
         self.fc1 = nn.Linear(num_channels, num_channels // reduction_ratio, bias=True)
         self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
 
-    def forward(self, x):  # [B,C,T]
-        feats = [torch.relu(m[0](x).mean(dim=-1)) for m in (self.smallConv1d, self.middleConv1d, self.largeConv1d)]
-        s = self.feature_concate_fc(torch.stack(feats, dim=-1))[..., 0]
-        g = torch.sigmoid(self.fc2(torch.relu(self.fc1(s))))
-        return x * g[:, :, None]
+    def forward(self, x):  # [B,C,T] -> three fused kernels (squeeze via windowed sums, excitation MLP, scale)
+        convs = (self.smallConv1d[0], self.middleConv1d[0], self.largeConv1d[0])
+        return ops.tsse(x.contiguous(), [c.kernel_size[0] for c in convs], [c.weight for c in convs],
+                        [c.bias for c in convs], self.feature_concate_fc.weight, self.feature_concate_fc.bias,
+                        self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
 
 
 class TCNBlock(nn.Module):
@@ -54,10 +54,35 @@ class TCNBlock(nn.Module):
         self.norm2 = nn.GroupNorm(1, hidden_channel, eps=1e-8)
         self.sconv = nn.Conv1d(hidden_channel, out_channels, 1)
 
+        self.dilation = dilation
+        self._fold = None
+        self._fold_key = None
+
+    def _folded(self):
+        """GroupNorm2's affine folded into the second 1x1 conv: W2' = W2 diag(gamma2), u = W2 gamma2, vb = W2 beta2 + b2.
+        Derived cache, rebuilt when the parameters change; never serialised."""
+        ps = (self.sconv.weight, self.sconv.bias, self.norm2.weight, self.norm2.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._fold is None or key != self._fold_key:
+            with torch.no_grad():
+                W2 = self.sconv.weight[:, :, 0].double()
+                w2f = (W2 * self.norm2.weight.double()[None, :]).float()[:, :, None].contiguous()
+                u = (W2 @ self.norm2.weight.double()).float().contiguous()
+                vb = (W2 @ self.norm2.bias.double() + self.sconv.bias.double()).float().contiguous()
+            self._fold, self._fold_key = (w2f, u, vb), key
+        return self._fold
+
     def forward(self, x):
-        y = self.norm1(self.prelu1(self.conv1x1(x)))
-        y = self.norm2(self.prelu2(self.depthwise_conv(y)))
-        return x + self.sconv(y)
+        """x [B,C,T'] -> x + sconv(norm2(prelu2(dwconv(norm1(prelu1(conv1x1(x)))))))  (causal_conv.py:96-108).
+        1x1 convolutions: library GEMM; everything between them: 3 fused kernels (prelu_stats, tcn_mid, tcn_out)."""
+        x = x.contiguous()
+        y1 = F.conv1d(x, self.conv1x1.weight, self.conv1x1.bias)
+        stats1 = ops.prelu_stats(y1, self.prelu1.weight)
+        z, stats2 = ops.tcn_mid(y1, self.prelu1.weight, stats1, self.norm1.weight, self.norm1.bias,
+                                self.depthwise_conv.weight, self.depthwise_conv.bias, self.dilation, self.prelu2.weight)
+        w2f, u, vb = self._folded()
+        o = F.conv1d(z, w2f)
+        return ops.tcn_out(o, x, z.shape[1], stats2, u, vb)
 
 
 class SequenceModel(nn.Module):

@@ -292,6 +292,55 @@ class LstmPlan:
         return y
 
 
+def tsse(x: torch.Tensor, kersize, conv_w, conv_b, fcat_w, fcat_b, fc1_w, fc1_b, fc2_w, fc2_b):
+    """ChannelTimeSenseSELayer.forward (attention_model.py:78-98): x [B,C,T] -> x * gate."""
+    import ctypes as C
+    x = _f32(x)
+    ts = [_f32(t.detach()) for t in (*conv_w, *conv_b, fcat_w, fcat_b, fc1_w, fc1_b, fc2_w, fc2_b)]
+    _chk(x, *ts)
+    B, Cc, T = x.shape
+    y = torch.empty_like(x)
+    scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
+    ks = (C.c_int * 3)(*[int(k) for k in kersize])
+    cw = (C.c_void_p * 3)(*[t.data_ptr() for t in ts[0:3]])
+    cb = (C.c_void_p * 3)(*[t.data_ptr() for t in ts[3:6]])
+    _lib.check(_lib.load().nppc_tsse(x.data_ptr(), B, Cc, T, ks, cw, cb, *[t.data_ptr() for t in ts[6:12]],
+                                     ts[8].shape[0], scratch.data_ptr(), y.data_ptr(), _stream()), "nppc_tsse")
+    return y
+
+
+def prelu_stats(y: torch.Tensor, prelu_a: torch.Tensor):
+    """[B,2] fp64 (sum, sum of squares) of PReLU(y) per sample."""
+    _chk(y, prelu_a)
+    B = y.shape[0]
+    stats = torch.empty(B, 2, device=y.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_prelu_stats(y.data_ptr(), B, y.numel() // B, prelu_a.data_ptr(), stats.data_ptr(), _stream()),
+               "nppc_prelu_stats")
+    return stats
+
+
+def tcn_mid(y1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation: int, prelu2_a):
+    """z = PReLU2(depthwise(GroupNorm1(PReLU1(y1)))) and the per-sample moments of z (causal_conv.py:100-104)."""
+    _chk(y1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, prelu2_a)
+    B, Cc, T = y1.shape
+    z = torch.empty_like(y1)
+    stats2 = torch.empty(B, 2, device=y1.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_tcn_mid(y1.data_ptr(), B, Cc, T, prelu1_a.data_ptr(), stats1.data_ptr(), gamma1.data_ptr(),
+                                        beta1.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), dilation, prelu2_a.data_ptr(),
+                                        z.data_ptr(), stats2.data_ptr(), _stream()), "nppc_tcn_mid")
+    return z, stats2
+
+
+def tcn_out(o, x, c_hidden: int, stats2, u, vb):
+    """x + sconv(GroupNorm2(z)) with the norm folded: x + o*rstd + vb - mean*rstd*u (causal_conv.py:105-108)."""
+    _chk(o, x, stats2, u, vb)
+    B, Cc, T = x.shape
+    xn = torch.empty_like(x)
+    _lib.check(_lib.load().nppc_tcn_out(o.data_ptr(), x.data_ptr(), B, Cc, T, c_hidden, stats2.data_ptr(), u.data_ptr(),
+                                        vb.data_ptr(), xn.data_ptr(), _stream()), "nppc_tcn_out")
+    return xn
+
+
 def assemble_mask(y: torch.Tensor, B: int, Fp: int, look_ahead: int):
     """y [B*F', O, T'] -> [B, O, F', T'-la] (fullsubnet_plus.py:227-229)."""
     _chk(y)

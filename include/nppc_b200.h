@@ -111,6 +111,28 @@ int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, c
                       int Tp, int num_neighbor, int groups, int KP, int R_stride, double* sums, float* xs_f32,
                       void* xs_f16, void* stream);
 
+/* ---- a3: TSSE channel attention ----------------------------------------------------------------------
+ * ChannelTimeSenseSELayer.forward (audio_zen/model/module/attention_model.py:78-98): x [B,C,T] -> y = x * gate[b,c].
+ * kersize, conv_w, conv_b are HOST arrays of 3 entries (conv_w[i]: device [C,1,k_i] depthwise weights, conv_b[i]: [C]);
+ * fcat_* = feature_concate_fc (3->1), fc1 [Cr,C], fc2 [C,Cr].  scratch: 2*B*C floats (device). */
+int nppc_tsse(const float* x, int B, int C, int T, const int* kersize, const float* const* conv_w,
+              const float* const* conv_b, const float* fcat_w, const float* fcat_b, const float* fc1_w,
+              const float* fc1_b, const float* fc2_w, const float* fc2_b, int C_reduced, float* scratch, float* y,
+              void* stream);
+
+/* ---- a4: TCN block, normalisation / depthwise half (causal_conv.py:96-108) ------------------------------
+ * stats buffers are [B,2] fp64 (sum, sum of squares) on the device; prelu_* point to the 1-element PReLU weight.
+ * nppc_prelu_stats: stats = moments of PReLU(y) per sample, y [B,n].
+ * nppc_tcn_mid:     z = PReLU2(depthwise_dilated(GroupNorm1(PReLU1(y1)))) [B,C,T] and stats2 = moments of z.
+ * nppc_tcn_out:     xnew = x + o*rstd2[b] + vb[c] - mean2[b]*rstd2[b]*u[c], where o = conv1x1(z; W2*diag(gamma2)),
+ *                   u = W2 gamma2, vb = W2 beta2 + b2  (GroupNorm2 folded into the second 1x1 convolution). */
+int nppc_prelu_stats(const float* y, int B, long long n, const float* prelu_a, double* stats, void* stream);
+int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* prelu1_a, const double* stats1, const float* gamma1,
+                 const float* beta1, const float* dw_w, const float* dw_b, int dilation, const float* prelu2_a, float* z,
+                 double* stats2, void* stream);
+int nppc_tcn_out(const float* o, const float* x, int B, int C, int T, int C_hidden, const double* stats2, const float* u,
+                 const float* vb, float* xnew, void* stream);
+
 /* ---- a7: sub-band LSTM (2 layers) + fc -----------------------------------------------------------
  * Replaces nn.LSTM(I->H, 2 layers, batch_first) + nn.Linear(H->O) of SequenceModel
  * (audio_zen/model/module/sequence_model.py:31-38,79,113-123).  Gate order i,f,g,o; z = W_ih x + b_ih + W_hh h + b_hh.

@@ -212,3 +212,40 @@ def test_assemble_mask(ops):
     y = torch.randn(3 * 7, 4, 11)
     ref = y.reshape(3, 7, 4, 11).permute(0, 2, 1, 3)[..., 2:]
     assert torch.equal(ops.assemble_mask(cu(y), 3, 7, 2).cpu(), ref)
+
+
+def test_tsse_vs_oracle(ops):
+    import weights
+    import generative_audio_b200 as g
+    p = weights.synth_state_dict(5, 0, "pretrained_restoration_model.")
+    gen = torch.Generator().manual_seed(12)
+    for B, T in ((3, 253), (2, 19), (1, 10)):
+        x = torch.randn(B, 257, T, generator=gen)
+        ref = O.tsse(x, p, "channel_attention_real")
+        m = g.modules.ChannelTimeSenseSELayer(257)
+        m.load_state_dict({k[len("channel_attention_real."):]: v for k, v in p.items() if k.startswith("channel_attention_real.")})
+        m.cuda()
+        assert rel_err(m(cu(x)).cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("C,d", [(257, 1), (514, 9), (257, 5)])
+def test_tcn_block_vs_oracle(ops, C, d):
+    import weights
+    import generative_audio_b200 as g
+    pre = "pretrained_restoration_model." if C == 257 else "audio_pc_wrapper.net."
+    p = weights.synth_state_dict(5, 0, pre)
+    idx = {1: 0, 2: 1, 5: 2, 9: 3}[d]
+    blk = f"fb_model_imag.sequence_model.{idx}"
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(3, C, 253, generator=gen)
+    ref = O.tcn_block(x, p, blk, d)
+    m = g.modules.TCNBlock(C, 512, C, dilation=d)
+    m.load_state_dict({k[len(blk) + 1:]: v for k, v in p.items() if k.startswith(blk + ".")})
+    m.cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = m(cu(x))
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    assert rel_err(out.cpu(), ref) < TOL
