@@ -224,62 +224,58 @@ __global__ void __launch_bounds__(TPB) subband_sum_kernel(const float* __restric
 }
 
 // xs[t][row][k], row = ob*Fg + j  (drop_band order), k < S real features, zero padded to KP.
-// One CTA per (row-tile of 8 rows, time-tile of 32 frames): reads are T'-contiguous, writes are KP-contiguous;
-// transposed through shared memory.
-constexpr int PK_ROWS = 4;
+// One CTA per (8 rows, 32 frames): thread (r, tt) gathers its S features (reads coalesced along T'), the tile is
+// transposed through shared memory and written as KP-contiguous rows (8 consecutive rows per frame = 8*KP contiguous).
+constexpr int PK_ROWS = 8;
 constexpr int PK_T = 32;
 __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
                                                           const float* __restrict__ fbr, const float* __restrict__ fbi,
                                                           int B, int F, int Tp, int nn, int G, int KP, int RS,
                                                           const double* __restrict__ sums, float* __restrict__ xs_f32,
                                                           __half* __restrict__ xs_f16) {
-    extern __shared__ float tile[];  // [PK_ROWS][KP][PK_T+1]
+    extern __shared__ float tile[];  // [PK_T][PK_ROWS][KP + 1]
     const int S = 2 * nn + 1 + 3;
     const int Fg = F / G;
     const long long R = (long long)B * Fg;
-    const long long row0 = (long long)blockIdx.x * PK_ROWS;
-    const int t0 = blockIdx.y * PK_T;
-    const double count = (double)F * S * Tp;
-    for (int idx = threadIdx.x; idx < PK_ROWS * KP * PK_T; idx += blockDim.x) {
-        int tt = idx % PK_T;
-        int k = (idx / PK_T) % KP;
-        int r = idx / (PK_T * KP);
-        long long row = row0 + r;
-        int t = t0 + tt;
-        float v = 0.f;
-        if (row < R && t < Tp && k < S) {
-            int ob = (int)(row / Fg), j = (int)(row % Fg);
-            int g = 0, start = 0, sb = ob, f = j;
-            if (G > 1) {
-                for (; g < G; ++g) {
-                    int cnt = (B - g + G - 1) / G;
-                    if (ob < start + cnt) break;
-                    start += cnt;
-                }
-                sb = g + G * (ob - start);
-                f = g + G * j;
+    const int r = threadIdx.x >> 5, tt = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * PK_ROWS + r;
+    const int t = blockIdx.y * PK_T + tt;
+    const int KS = KP + 1;
+    float* mine = tile + ((size_t)tt * PK_ROWS + r) * KS;
+    if (row < R && t < Tp) {
+        int ob = (int)(row / Fg), j = (int)(row % Fg);
+        int sb = ob, f = j;
+        if (G > 1) {  // drop_band: group g owns a run of output batches; sample = g + G*(ob - start), freq = g + G*j
+            int g = 0, start = 0;
+            for (; g < G; ++g) {
+                int cnt = (B - g + G - 1) / G;
+                if (ob < start + cnt) break;
+                start += cnt;
             }
-            const size_t off = (size_t)sb * F * Tp;
-            float raw;
-            if (k < 2 * nn + 1) raw = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp + t];
-            else if (k == 2 * nn + 1) raw = fb[off + (size_t)f * Tp + t];
-            else if (k == 2 * nn + 2) raw = fbr[off + (size_t)f * Tp + t];
-            else raw = fbi[off + (size_t)f * Tp + t];
-            float den = (float)(sums[sb] / count) + 1e-5f;
-            v = raw / den;
+            sb = g + G * (ob - start);
+            f = g + G * j;
         }
-        tile[(r * KP + k) * (PK_T + 1) + tt] = v;
+        const float den = (float)(sums[sb] / ((double)F * S * Tp)) + 1e-5f;
+        const size_t off = (size_t)sb * F * Tp + t;
+        for (int k = 0; k < 2 * nn + 1; ++k) mine[k] = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp] / den;
+        mine[2 * nn + 1] = fb[off + (size_t)f * Tp] / den;
+        mine[2 * nn + 2] = fbr[off + (size_t)f * Tp] / den;
+        mine[2 * nn + 3] = fbi[off + (size_t)f * Tp] / den;
+        for (int k = S; k < KP; ++k) mine[k] = 0.f;
+    } else {
+        for (int k = 0; k < KP; ++k) mine[k] = 0.f;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < PK_ROWS * KP * PK_T; idx += blockDim.x) {
-        int k = idx % KP;
-        int r = (idx / KP) % PK_ROWS;
-        int tt = idx / (KP * PK_ROWS);
-        long long row = row0 + r;
-        int t = t0 + tt;
-        if (row < RS && t < Tp) {
-            float v = tile[(r * KP + k) * (PK_T + 1) + tt];
-            size_t o = ((size_t)t * RS + row) * KP + k;
+    // write: for each frame, PK_ROWS*KP consecutive elements
+    const int per_frame = PK_ROWS * KP;
+    for (int idx = threadIdx.x; idx < PK_T * per_frame; idx += blockDim.x) {
+        int ft = idx / per_frame, rem = idx - ft * per_frame;
+        int rr = rem / KP, k = rem - rr * KP;
+        long long orow = (long long)blockIdx.x * PK_ROWS + rr;
+        int ot = blockIdx.y * PK_T + ft;
+        if (orow < RS && ot < Tp) {
+            float v = tile[((size_t)ft * PK_ROWS + rr) * KS + k];
+            size_t o = ((size_t)ot * RS + orow) * KP + k;
             if (xs_f32) xs_f32[o] = v;
             if (xs_f16) xs_f16[o] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));  // saturating
         }
@@ -420,7 +416,7 @@ extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const fl
     subband_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(nbr_src, fb, fbr, fbi, F, Tp, num_neighbor, sums);
     long long R = (long long)B * (F / G);
     NPPC_CHECK_ARG(R_stride >= R, "nppc_subband_pack: R_stride (%d) < rows (%lld)", R_stride, R);
-    size_t smem = sizeof(float) * PK_ROWS * KP * (PK_T + 1);
+    size_t smem = sizeof(float) * PK_T * PK_ROWS * (KP + 1);
     if (smem > 48 * 1024)
         NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)nppc::cdiv(R_stride, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));

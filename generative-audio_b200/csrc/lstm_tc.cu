@@ -34,7 +34,7 @@ constexpr int NCHUNK = H / CH;      // 12
 constexpr int NSLAB = H / 64;       // 6 K-slabs of 64
 constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have the same shape: 128 x 64 bf16)
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
-constexpr int OPMAX = 64;
+constexpr int OPMAX = 24;
 
 constexpr int HST_BYTES = ROWS * CH * 2;   // one chunk of h_t for the CTA's rows: [128][32] bf16 = 8 KB
 
@@ -334,42 +334,97 @@ __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ o
 }
 
 // fc_output_layer over the h sequence of the last layer: y[row][o][t] = b[o] + sum_k W[o][k] * h[t][row][k]
-// (sequence_model.py:79,119). HBM-bound: one read of hseq (bf16), O*4 bytes written per (row, t).
+// (sequence_model.py:79,119).  One CTA = 64 (t,row) rows staged in shared memory by coalesced 16-byte loads; warp w
+// covers K-quarter (w & 3) of rows 32*(w >> 2) + lane, so weight reads are warp-broadcast float4; the four partial
+// sums per row meet in shared memory.  One pass over hseq.
 constexpr int FC_ROWS = 64;
+constexpr int FC_TG = 8;     // frames per CTA: each (row, o) pair writes 8 consecutive floats
+template <int OQ>   // OQ = ceil(O / 4)
 __global__ void __launch_bounds__(256) lstm_fc_kernel(const __half* __restrict__ hseq, int R, int RS, int Tp,
                                                       const float* __restrict__ fc_w, const float* __restrict__ fc_b, int O,
                                                       float* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    constexpr int HP = H + 8;                                   // padded row (bf16 elements) -> conflict-free row stride
-    __half* hs = reinterpret_cast<__half*>(fsm);  // [FC_ROWS][HP]
-    float* wt = reinterpret_cast<float*>(fsm + FC_ROWS * HP * 2);  // [H][O] transposed weights
-    const int t = blockIdx.y;
+    constexpr int HP = H + 8;                         // padded row (fp16 elements): conflict-free row stride
+    constexpr int KQ = H / 4;                         // 96 k per warp
+    __half* hs = reinterpret_cast<__half*>(fsm);      // [FC_ROWS][HP]
+    float4* wt = reinterpret_cast<float4*>(fsm + FC_ROWS * HP * 2);                  // [H][OQ] transposed, zero-padded
+    float* part = reinterpret_cast<float*>(fsm + FC_ROWS * HP * 2 + H * OQ * 16);    // [4][FC_ROWS][OQ*4]
+    const int t0 = blockIdx.y * FC_TG;
     const int row0 = blockIdx.x * FC_ROWS;
-    for (int i = threadIdx.x; i < H * O; i += blockDim.x) {
-        int k = i / O, o = i - k * O;
-        wt[i] = fc_w[(size_t)o * H + k];
+    for (int i = threadIdx.x; i < H * OQ * 4; i += blockDim.x) {
+        int k = i / (OQ * 4), o = i - k * (OQ * 4);
+        reinterpret_cast<float*>(wt)[i] = o < O ? fc_w[(size_t)o * H + k] : 0.f;
     }
-    // coalesced 16-byte loads of the [FC_ROWS][H] tile
-    for (int i = threadIdx.x; i < FC_ROWS * (H / 8); i += blockDim.x) {
-        int r = i / (H / 8), c = i - r * (H / 8);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row0 + r < R) v = __ldg(reinterpret_cast<const uint4*>(hseq + ((size_t)t * RS + row0 + r) * H) + c);
-        *reinterpret_cast<uint4*>(hs + r * HP + c * 8) = v;
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < FC_ROWS * O; p += blockDim.x) {
-        int r = p / O, o = p - r * O;
-        if (row0 + r >= R) continue;
-        const __half2* hr = reinterpret_cast<const __half2*>(hs + r * HP);
-        float acc = fc_b[o];
-#pragma unroll 8
-        for (int k2 = 0; k2 < H / 2; ++k2) {
-            float2 hv = __half22float2(hr[k2]);
-            acc = fmaf(hv.x, wt[(2 * k2) * O + o], acc);
-            acc = fmaf(hv.y, wt[(2 * k2 + 1) * O + o], acc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kq = warp & 3, r = (warp >> 2) * 32 + lane;
+    const __half2* hr = reinterpret_cast<const __half2*>(hs + r * HP + kq * KQ);
+    const float4* wq = wt + (size_t)kq * KQ * OQ;
+    constexpr int NP = (FC_ROWS * OQ * 4 + 255) / 256;   // (row, o) pairs finished by each thread
+    float res[NP][FC_TG];
+    for (int tt = 0; tt < FC_TG; ++tt) {
+        const int t = t0 + tt;
+        if (t >= Tp) break;
+        __syncthreads();   // previous tile fully consumed
+        for (int i = threadIdx.x; i < FC_ROWS * (H / 8); i += blockDim.x) {
+            int rr = i / (H / 8), c = i - rr * (H / 8);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row0 + rr < R) v = __ldg(reinterpret_cast<const uint4*>(hseq + ((size_t)t * RS + row0 + rr) * H) + c);
+            *reinterpret_cast<uint4*>(hs + rr * HP + c * 8) = v;
         }
-        y[((size_t)(row0 + r) * O + o) * Tp + t] = acc;
+        __syncthreads();
+        float acc[OQ * 4];
+#pragma unroll
+        for (int o = 0; o < OQ * 4; ++o) acc[o] = 0.f;
+#pragma unroll 4
+        for (int k2 = 0; k2 < KQ / 2; ++k2) {
+            float2 hv = __half22float2(hr[k2]);
+#pragma unroll
+            for (int q = 0; q < OQ; ++q) {
+                float4 w0 = wq[(2 * k2) * OQ + q], w1 = wq[(2 * k2 + 1) * OQ + q];
+                acc[4 * q + 0] = fmaf(hv.x, w0.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(hv.x, w0.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(hv.x, w0.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(hv.x, w0.w, acc[4 * q + 3]);
+                acc[4 * q + 0] = fmaf(hv.y, w1.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(hv.y, w1.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(hv.y, w1.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(hv.y, w1.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < OQ * 4; ++o) part[((size_t)kq * FC_ROWS + r) * (OQ * 4) + o] = acc[o];
+        __syncthreads();
+#pragma unroll
+        for (int pi = 0; pi < NP; ++pi) {
+            int i = threadIdx.x + pi * 256;
+            float v = 0.f;
+            if (i < FC_ROWS * OQ * 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v += part[(size_t)q * FC_ROWS * (OQ * 4) + i];
+            }
+#pragma unroll
+            for (int u = 0; u < FC_TG; ++u) if (u == tt) res[pi][u] = v;
+        }
     }
+    // each (row, o) pair now owns FC_TG consecutive frames: contiguous 32-byte runs in y [R][O][Tp]
+#pragma unroll
+    for (int pi = 0; pi < NP; ++pi) {
+        int i = threadIdx.x + pi * 256;
+        if (i >= FC_ROWS * OQ * 4) continue;
+        int rr = i / (OQ * 4), o = i - rr * (OQ * 4);
+        if (o >= O || row0 + rr >= R) continue;
+        float* dst = y + ((size_t)(row0 + rr) * O + o) * Tp + t0;
+        const float bias = fc_b[o];
+#pragma unroll
+        for (int u = 0; u < FC_TG; ++u)
+            if (t0 + u < Tp) dst[u] = res[pi][u] + bias;
+    }
+}
+
+template <int OQ>
+int launch_fc(const __half* hseq, int R, int RS, int Tp, const float* w, const float* b, int O, float* y, cudaStream_t s) {
+    size_t fsm = (size_t)FC_ROWS * (H + 8) * 2 + (size_t)H * OQ * 16 + (size_t)4 * FC_ROWS * OQ * 16;
+    NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_fc_kernel<OQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    lstm_fc_kernel<OQ><<<dim3(nppc::cdiv(R, FC_ROWS), nppc::cdiv(Tp, FC_TG)), 256, fsm, s>>>(hseq, R, RS, Tp, w, b, O, y);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
 }
 
 template <int CL>
@@ -482,12 +537,17 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     if (rc) return rc;
     rc = launch_rec(tw[1], th, thst, zx, RS, Tp, s);
     if (rc) return rc;
-    size_t fsm = (size_t)FC_ROWS * (H + 8) * 2 + (size_t)H * p->O * 4;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(lstm_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-    lstm_fc_kernel<<<dim3(cdiv(R, FC_ROWS), Tp), 256, fsm, s>>>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y);
-    NPPC_COUNT_LAUNCH(1);
-    NPPC_LAUNCH_OK();
-    return NPPC_OK;
+    switch ((p->O + 3) / 4) {
+        case 1: return launch_fc<1>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        case 2: return launch_fc<2>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        case 3: return launch_fc<3>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        case 4: return launch_fc<4>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        case 5: return launch_fc<5>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        case 6: return launch_fc<6>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
+        default: break;
+    }
+    set_error("nppc_lstm_forward(impl 1): output size %d > 24 not built", p->O);
+    return NPPC_ERR_UNSUPPORTED;
 }
 
 }  // namespace nppc

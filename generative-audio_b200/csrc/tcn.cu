@@ -46,38 +46,47 @@ __global__ void __launch_bounds__(TPB) prelu_stats_kernel(const float* __restric
     }
 }
 
-// grid (ceil(T/128), C, B): block handles 128 consecutive frames of one channel row (coalesced), 3 taps from L1/L2.
-__global__ void __launch_bounds__(128) tcn_mid_kernel(const float* __restrict__ y1, int C, int T, const float* __restrict__ a1_ptr,
-                                                      const double* __restrict__ stats1, const float* __restrict__ g1,
-                                                      const float* __restrict__ b1, const float* __restrict__ dw_w,
-                                                      const float* __restrict__ dw_b, int dil, const float* __restrict__ a2_ptr,
-                                                      float* __restrict__ z, double* __restrict__ stats2) {
+// grid (blocks per sample, B), 8 warps per block: each warp owns whole channel rows (coalesced along T', the 3 taps hit
+// L1), moments are accumulated per thread in fp32 over one row, per block in fp64, ONE atomic pair per block.
+__global__ void __launch_bounds__(TPB) tcn_mid_kernel(const float* __restrict__ y1, int C, int T, const float* __restrict__ a1_ptr,
+                                                     const double* __restrict__ stats1, const float* __restrict__ g1,
+                                                     const float* __restrict__ b1, const float* __restrict__ dw_w,
+                                                     const float* __restrict__ dw_b, int dil, const float* __restrict__ a2_ptr,
+                                                     float* __restrict__ z, double* __restrict__ stats2) {
     __shared__ double red[32];
-    const int b = blockIdx.z, c = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const double n = (double)C * T;
     const double mu_d = stats1[2 * b] / n;
     const double var_d = stats1[2 * b + 1] / n - mu_d * mu_d;
     const float mu = (float)mu_d, rstd = (float)(1.0 / sqrt(fmax(var_d, 0.0) + 1e-8));
     const float a1 = *a1_ptr, a2 = *a2_ptr;
-    const float sc = rstd * g1[c], sh = b1[c] - mu * rstd * g1[c];   // norm1(v) = v * sc + sh
-    const float k0 = dw_w[c * 3], k1 = dw_w[c * 3 + 1], k2 = dw_w[c * 3 + 2], kb = dw_b[c];
-    const float* row = y1 + ((size_t)b * C + c) * T;
-    float out = 0.f;
-    if (t < T) {
-        float acc = kb;
-        int tm = t - dil, tp = t + dil;
-        if (tm >= 0) acc += k0 * (prelu(row[tm], a1) * sc + sh);   // zero padding applies to the NORMALISED signal
-        acc += k1 * (prelu(row[t], a1) * sc + sh);
-        if (tp < T) acc += k2 * (prelu(row[tp], a1) * sc + sh);
-        out = prelu(acc, a2);
-        z[((size_t)b * C + c) * T + t] = out;
+    double ds = 0.0, dss = 0.0;
+    for (int c = blockIdx.x * nw + warp; c < C; c += gridDim.x * nw) {
+        const float sc = rstd * g1[c], sh = b1[c] - mu * rstd * g1[c];   // norm1(v) = v * sc + sh
+        const float k0 = dw_w[c * 3], k1 = dw_w[c * 3 + 1], k2 = dw_w[c * 3 + 2], kb = dw_b[c];
+        const float* row = y1 + ((size_t)b * C + c) * T;
+        float* zrow = z + ((size_t)b * C + c) * T;
+        float s = 0.f, ss = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            float acc = kb;
+            int tm = t - dil, tp = t + dil;
+            if (tm >= 0) acc += k0 * (prelu(row[tm], a1) * sc + sh);   // zero padding applies to the NORMALISED signal
+            acc += k1 * (prelu(row[t], a1) * sc + sh);
+            if (tp < T) acc += k2 * (prelu(row[tp], a1) * sc + sh);
+            float out = prelu(acc, a2);
+            zrow[t] = out;
+            s += out;
+            ss += out * out;
+        }
+        ds += (double)s;
+        dss += (double)ss;
     }
-    double s = nppc::block_sum((double)out, red);
-    double ss = nppc::block_sum((double)out * (double)out, red);
+    ds = nppc::block_sum(ds, red);
+    dss = nppc::block_sum(dss, red);
     if (threadIdx.x == 0) {
-        atomicAdd(&stats2[2 * b], s);
-        atomicAdd(&stats2[2 * b + 1], ss);
+        atomicAdd(&stats2[2 * b], ds);
+        atomicAdd(&stats2[2 * b + 1], dss);
     }
 }
 
@@ -203,8 +212,13 @@ extern "C" int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* p
     NPPC_CHECK_ARG(B > 0 && C > 0 && T > 0 && dilation > 0 && C <= 65535 && B <= 65535, "nppc_tcn_mid: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     NPPC_CUDA_OK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * B, s));
-    tcn_mid_kernel<<<dim3(nppc::cdiv(T, 128), C, B), 128, 0, s>>>(y1, C, T, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation,
-                                                                prelu2_a, z, stats2);
+    {
+        int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
+        int gx = nppc::cdiv(C, TPB / 32);
+        if (gx > per) gx = per < 1 ? 1 : per;
+        tcn_mid_kernel<<<dim3(gx, B), TPB, 0, s>>>(y1, C, T, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation,
+                                                   prelu2_a, z, stats2);
+    }
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
