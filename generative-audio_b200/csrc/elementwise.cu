@@ -72,8 +72,13 @@ __global__ void __launch_bounds__(TPB) sample_sum_kernel(const float* __restrict
     const int b = blockIdx.y;
     const float* xb = x + (size_t)b * n;
     double acc = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        acc += (double)xb[i];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {   // 4 independent loads in flight per thread
+        float v0 = xb[i], v1 = xb[i + stride], v2 = xb[i + 2 * stride], v3 = xb[i + 3 * stride];
+        acc += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; i < n; i += stride) acc += (double)xb[i];
     acc = nppc::block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(&sums[b], acc);
 }
@@ -86,8 +91,13 @@ __global__ void __launch_bounds__(TPB) offline_norm_kernel(const float* __restri
     const float den = mu + 1e-5f;
     const float* xb = x + (size_t)b * n;
     float* yb = y + (size_t)b * n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        yb[i] = xb[i] / den;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {   // 4 independent loads in flight per thread
+        float v0 = xb[i], v1 = xb[i + stride], v2 = xb[i + 2 * stride], v3 = xb[i + 3 * stride];
+        yb[i] = v0 / den; yb[i + stride] = v1 / den; yb[i + 2 * stride] = v2 / den; yb[i + 3 * stride] = v3 / den;
+    }
+    for (; i < n; i += stride) yb[i] = xb[i] / den;
 }
 
 // x [B,F,T] -> y [B,F,T+la] = pad + norm (mean counts the zero look-ahead frames, fullsubnet_plus.py:158-165)
@@ -155,7 +165,8 @@ __device__ __forceinline__ int reflect_idx(int p, int F) {
     return p;
 }
 
-// out [B,F,C,K,T]; one CTA per (b, f, c) writes K rows of T; source rows are contiguous T-rows -> coalesced both ways.
+// out [B,F,C,K,T]; one CTA per (b, f, c): thread = frame t, loop over the K neighbour rows (source and destination rows
+// are both T-contiguous -> coalesced, no index division in the loop).
 __global__ void __launch_bounds__(TPB) unfold_kernel(const float* __restrict__ x, int C, int F, int T, int nn,
                                                     float* __restrict__ out) {
     const int K = 2 * nn + 1;
@@ -166,10 +177,9 @@ __global__ void __launch_bounds__(TPB) unfold_kernel(const float* __restrict__ x
     int b = (int)(bf / F);
     const float* src = x + ((size_t)b * C + c) * F * T;
     float* dst = out + (size_t)row * K * T;
-    const int n = K * T;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int k = i / T, t = i - k * T;
-        dst[i] = src[(size_t)reflect_idx(f + k - nn, F) * T + t];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) dst[(size_t)k * T + t] = src[(size_t)reflect_idx(f + k - nn, F) * T + t];
     }
 }
 
@@ -223,25 +233,28 @@ __global__ void __launch_bounds__(TPB) subband_sum_kernel(const float* __restric
     if (threadIdx.x == 0) atomicAdd(&sums[b], acc);
 }
 
-// xs[t][row][k], row = ob*Fg + j  (drop_band order), k < S real features, zero padded to KP.
+// xs[t][row][k], row = ob*Fg + j  (drop_band order), k < S real features, zero padded to KP = 64.
 // One CTA per (8 rows, 32 frames): thread (r, tt) gathers its S features (reads coalesced along T'), the tile is
-// transposed through shared memory and written as KP-contiguous rows (8 consecutive rows per frame = 8*KP contiguous).
+// transposed through shared memory and written as 16-byte pieces of KP-contiguous rows (8 consecutive rows of one
+// frame = 8*KP contiguous elements).  All index arithmetic in the write phase is compile-time shifts.
 constexpr int PK_ROWS = 8;
 constexpr int PK_T = 32;
+constexpr int PK_KP = 64;
+template <bool F16OUT>
 __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
                                                           const float* __restrict__ fbr, const float* __restrict__ fbi,
-                                                          int B, int F, int Tp, int nn, int G, int KP, int RS,
-                                                          const double* __restrict__ sums, float* __restrict__ xs_f32,
-                                                          __half* __restrict__ xs_f16) {
-    extern __shared__ float tile[];  // [PK_T][PK_ROWS][KP + 1]
+                                                          int B, int F, int Tp, int nn, int G, int RS,
+                                                          const double* __restrict__ sums, void* __restrict__ xs_out) {
+    extern __shared__ float tile[];  // [PK_ROWS][PK_KP][PK_T + 1] (+1 word skew per row): both phases (nearly) conflict-free
+    constexpr int TS = PK_T + 1;
+    constexpr int RSK = PK_KP * TS + 1;
     const int S = 2 * nn + 1 + 3;
     const int Fg = F / G;
     const long long R = (long long)B * Fg;
     const int r = threadIdx.x >> 5, tt = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * PK_ROWS + r;
     const int t = blockIdx.y * PK_T + tt;
-    const int KS = KP + 1;
-    float* mine = tile + ((size_t)tt * PK_ROWS + r) * KS;
+    float* mine = tile + (size_t)r * RSK + tt;   // element k at mine[k * TS]
     if (row < R && t < Tp) {
         int ob = (int)(row / Fg), j = (int)(row % Fg);
         int sb = ob, f = j;
@@ -257,27 +270,40 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
         }
         const float den = (float)(sums[sb] / ((double)F * S * Tp)) + 1e-5f;
         const size_t off = (size_t)sb * F * Tp + t;
-        for (int k = 0; k < 2 * nn + 1; ++k) mine[k] = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp] / den;
-        mine[2 * nn + 1] = fb[off + (size_t)f * Tp] / den;
-        mine[2 * nn + 2] = fbr[off + (size_t)f * Tp] / den;
-        mine[2 * nn + 3] = fbi[off + (size_t)f * Tp] / den;
-        for (int k = S; k < KP; ++k) mine[k] = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 2 * nn + 1; ++k) mine[k * TS] = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp] / den;
+        mine[(2 * nn + 1) * TS] = fb[off + (size_t)f * Tp] / den;
+        mine[(2 * nn + 2) * TS] = fbr[off + (size_t)f * Tp] / den;
+        mine[(2 * nn + 3) * TS] = fbi[off + (size_t)f * Tp] / den;
+        for (int k = S; k < PK_KP; ++k) mine[k * TS] = 0.f;
     } else {
-        for (int k = 0; k < KP; ++k) mine[k] = 0.f;
+        for (int k = 0; k < PK_KP; ++k) mine[k * TS] = 0.f;
     }
     __syncthreads();
-    // write: for each frame, PK_ROWS*KP consecutive elements
-    const int per_frame = PK_ROWS * KP;
-    for (int idx = threadIdx.x; idx < PK_T * per_frame; idx += blockDim.x) {
-        int ft = idx / per_frame, rem = idx - ft * per_frame;
-        int rr = rem / KP, k = rem - rr * KP;
-        long long orow = (long long)blockIdx.x * PK_ROWS + rr;
-        int ot = blockIdx.y * PK_T + ft;
-        if (orow < RS && ot < Tp) {
-            float v = tile[((size_t)ft * PK_ROWS + rr) * KS + k];
-            size_t o = ((size_t)ot * RS + orow) * KP + k;
-            if (xs_f32) xs_f32[o] = v;
-            if (xs_f16) xs_f16[o] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));  // saturating
+    // write phase: piece = 8 consecutive k of one (frame, row); PK_T*PK_ROWS*8 pieces per CTA
+    constexpr int PIECES = PK_T * PK_ROWS * (PK_KP / 8);
+    for (int idx = threadIdx.x; idx < PIECES; idx += TPB) {
+        const int kq = idx & 7, rr = (idx >> 3) & (PK_ROWS - 1), ft = idx >> 6;
+        const long long orow = (long long)blockIdx.x * PK_ROWS + rr;
+        const int ot = blockIdx.y * PK_T + ft;
+        if (orow >= RS || ot >= Tp) continue;
+        const float* src = tile + (size_t)rr * RSK + (size_t)(kq * 8) * TS + ft;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = src[e * TS];
+        const size_t o = ((size_t)ot * RS + orow) * PK_KP + kq * 8;
+        if (F16OUT) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * e], -65504.f), 65504.f), fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f));
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(xs_out) + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(xs_out) + o);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
 }
@@ -416,13 +442,21 @@ extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const fl
     subband_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(nbr_src, fb, fbr, fbi, F, Tp, num_neighbor, sums);
     long long R = (long long)B * (F / G);
     NPPC_CHECK_ARG(R_stride >= R, "nppc_subband_pack: R_stride (%d) < rows (%lld)", R_stride, R);
-    size_t smem = sizeof(float) * PK_T * PK_ROWS * (KP + 1);
-    if (smem > 48 * 1024)
-        NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CHECK_ARG(KP == PK_KP, "nppc_subband_pack: KP must be %d (got %d)", PK_KP, KP);
     dim3 grid((unsigned)nppc::cdiv(R_stride, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));
-    subband_pack_kernel<<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, KP, R_stride, sums, xs_f32,
-                                                (__half*)xs_f16);
-    NPPC_COUNT_LAUNCH(2);
+    int nlaunch = 1;
+    const size_t smem = sizeof(float) * PK_ROWS * (PK_KP * (PK_T + 1) + 1);
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (xs_f32) {
+        subband_pack_kernel<false><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f32);
+        ++nlaunch;
+    }
+    if (xs_f16) {
+        subband_pack_kernel<true><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f16);
+        ++nlaunch;
+    }
+    NPPC_COUNT_LAUNCH(nlaunch);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
 }

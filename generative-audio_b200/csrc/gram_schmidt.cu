@@ -42,58 +42,56 @@ __global__ void __launch_bounds__(TPB) gram_kernel(const float* __restrict__ x, 
                                                   SampleScratch* __restrict__ scr) {
     constexpr int NPAIR = (J1 - J0) * NV - (J1 * (J1 - 1) / 2 - J0 * (J0 - 1) / 2);
     constexpr int NACC = NPAIR * (COMPLEX ? 2 : 1);
-    __shared__ double red[32];
     const int b = blockIdx.y;
-    double dacc[NACC];
+    // one CTA = one run of TPB*RUN elements: fp32 per-thread partials over RUN (=16) products only, fp64 from there on
+    const long long base = (long long)blockIdx.x * TPB * RUN;
+    float acc[NACC];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) dacc[i] = 0.0;
-    const long long chunk = (long long)TPB * RUN;
-    for (long long base = (long long)blockIdx.x * chunk; base < P; base += (long long)gridDim.x * chunk) {
-        float acc[NACC];
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < RUN; ++r) {
+        long long p = base + (long long)r * TPB + threadIdx.x;
+        if (p < P) {
+            float vr[NV], vi[NV];
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-#pragma unroll 2
-        for (int r = 0; r < RUN; ++r) {
-            long long p = base + (long long)r * TPB + threadIdx.x;
-            if (p < P) {
-                float vr[NV], vi[NV];
+            for (int v = 0; v < NV; ++v) load_vec<COMPLEX>(x, gt, pred, b, n, v, P, p, vr[v], vi[v]);
+            int a = 0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) load_vec<COMPLEX>(x, gt, pred, b, n, v, P, p, vr[v], vi[v]);
-                int a = 0;
+            for (int j = J0; j < J1; ++j) {
 #pragma unroll
-                for (int j = J0; j < J1; ++j) {
-#pragma unroll
-                    for (int k = j; k < NV; ++k) {
-                        if (COMPLEX) {
-                            acc[a] += vr[j] * vr[k] + vi[j] * vi[k];      // Re conj(x_j) x_k
-                            acc[a + 1] += vr[j] * vi[k] - vi[j] * vr[k];  // Im conj(x_j) x_k
-                            a += 2;
-                        } else {
-                            acc[a] += vr[j] * vr[k];
-                            a += 1;
-                        }
+                for (int k = j; k < NV; ++k) {
+                    if (COMPLEX) {
+                        acc[a] += vr[j] * vr[k] + vi[j] * vi[k];      // Re conj(x_j) x_k
+                        acc[a + 1] += vr[j] * vi[k] - vi[j] * vr[k];  // Im conj(x_j) x_k
+                        a += 2;
+                    } else {
+                        acc[a] += vr[j] * vr[k];
+                        a += 1;
                     }
                 }
             }
         }
-#pragma unroll
-        for (int i = 0; i < NACC; ++i) dacc[i] += (double)acc[i];
     }
-    // block reduce each accumulator, one atomic per CTA per entry
-    int a = 0;
+    // block reduction: fp32 shuffles inside a warp (32 partials of <=16 products each), fp64 across the 8 warps,
+    // one fp64 atomic per Gram entry per CTA
+    __shared__ float wsum[TPB / 32][NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int j = J0; j < J1; ++j) {
+    for (int i = 0; i < NACC; ++i) {
+        float v = nppc::warp_sum(acc[i]);
+        if (lane == 0) wsum[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double d = 0.0;
 #pragma unroll
-        for (int k = j; k < NV; ++k) {
-            double re = nppc::block_sum(dacc[a], red);
-            double im = 0.0;
-            if (COMPLEX) im = nppc::block_sum(dacc[a + 1], red);
-            a += COMPLEX ? 2 : 1;
-            if (threadIdx.x == 0) {
-                atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2], re);
-                if (COMPLEX) atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2 + 1], im);
-            }
-        }
+        for (int w = 0; w < TPB / 32; ++w) d += (double)wsum[w][threadIdx.x];
+        // accumulator index -> (j, k, re/im)
+        int a = threadIdx.x, comp = COMPLEX ? (a & 1) : 0, pair = COMPLEX ? (a >> 1) : a;
+        int j = J0, rowlen = NV - J0;
+        while (pair >= rowlen) { pair -= rowlen; ++j; --rowlen; }
+        int k = j + pair;
+        atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2 + comp], d);
     }
 }
 
@@ -107,13 +105,18 @@ __global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n, i
                                 float* __restrict__ err_norm, float* __restrict__ err_proj,
                                 float* __restrict__ w_norms, float* __restrict__ reconst_err,
                                 float* __restrict__ second_moment) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    int b = blockIdx.x;
+    if (b >= B || threadIdx.x != 0) return;
     SampleScratch& s = scr[b];
-    auto G = [&](int j, int k) -> cd {  // full Hermitian access from the stored upper triangle
-        if (j <= k) return cd{s.G[(j * NV_MAX + k) * 2], s.G[(j * NV_MAX + k) * 2 + 1]};
-        return cd{s.G[(k * NV_MAX + j) * 2], -s.G[(k * NV_MAX + j) * 2 + 1]};
-    };
+    const int nv = n + (has_err ? 1 : 0);
+    cd Gl[NV_MAX][NV_MAX];   // full Hermitian matrix from the stored upper triangle (local copy: no global loads in the solve)
+    for (int j = 0; j < nv; ++j)
+        for (int k = j; k < nv; ++k) {
+            cd g{s.G[(j * NV_MAX + k) * 2], s.G[(j * NV_MAX + k) * 2 + 1]};
+            Gl[j][k] = g;
+            Gl[k][j] = cd{g.x, -g.y};
+        }
+    auto G = [&](int j, int k) -> cd { return Gl[j][k]; };
     cd ahat[12][12];  // normalised coefficient vectors of the previous directions
     cd v[12][12];     // v_j = G * ahat_j
     double nu[12];
@@ -216,10 +219,9 @@ __global__ void __launch_bounds__(TPB) apply_kernel(const float* __restrict__ x,
 }
 
 int chunks_for(long long P, int B) {
+    (void)B;
     long long per = ((long long)TPB * RUN);
-    long long c = (P + per - 1) / per;
-    long long want = (2LL * nppc::sm_count() + B - 1) / B;  // ~2 CTAs per SM overall
-    if (c > want) c = want;
+    long long c = (P + per - 1) / per;   // one CTA per run of TPB*RUN elements
     return (int)(c < 1 ? 1 : c);
 }
 
@@ -256,7 +258,7 @@ int dispatch_gram(int NV, const float* x, const float* gt, const float* pred, in
 template <bool COMPLEX>
 int dispatch_apply(int n, const float* x, int B, long long P, const SampleScratch* scr, float* out, cudaStream_t s) {
     long long c = (P + TPB - 1) / TPB;
-    long long want = (4LL * nppc::sm_count() + B - 1) / B;
+    long long want = (16LL * nppc::sm_count() + B - 1) / B;
     if (c > want) c = want;
     dim3 grid((unsigned)(c < 1 ? 1 : c), B);
     switch (n) {
@@ -281,7 +283,7 @@ int run(const float* x, const float* gt, const float* pred, int B, int n, long l
     NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
     int rc = dispatch_gram<COMPLEX>(n + has_err, x, gt, pred, B, n, P, scr, s);
     if (rc) return rc;
-    gs_solve_kernel<COMPLEX><<<nppc::cdiv(B, 32), 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms,
+    gs_solve_kernel<COMPLEX><<<B, 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms,
                                                            reconst_err, second_moment);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();

@@ -1,7 +1,7 @@
 // a1 STFT front end and a15 iSTFT back end (n_fft = win = 512, hop = 256).
 //
-// HBM-bound kernels: one CTA transforms 32 consecutive frames of one utterance so that the [B,F,T]
-// (T contiguous) planes are read/written in 128-byte rows; the 512-point real FFT of each frame is done by one
+// HBM-bound kernels: one CTA transforms 16 consecutive frames of one utterance so that the [B,F,T]
+// (T contiguous) planes are read/written in 64-byte runs; the 512-point real FFT of each frame is done by one
 // warp as a 256-point complex radix-2 FFT in shared memory (even/odd packing), twiddles and the periodic hann
 // window staged in shared memory once per CTA.
 #include "common.cuh"
@@ -12,7 +12,7 @@ constexpr int NFFT = 512;
 constexpr int HOP = 256;
 constexpr int NBIN = 257;
 constexpr int M = 256;        // complex FFT size
-constexpr int FRAMES = 32;    // frames per CTA
+constexpr int FRAMES = 16;    // frames per CTA (64-byte output runs; 4 CTAs / SM)
 constexpr int WARPS = 8;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -44,18 +44,33 @@ __device__ __forceinline__ void warp_fft256(float2* buf, const float2* tw, int l
 
 __device__ __forceinline__ int bitrev8(int m) { return (int)(__brev((unsigned)m) >> 24); }
 
-struct SmemTables {
+struct __align__(16) SmemTables {
     float2 tw[M];     // exp(-2 pi i k / 512)
     float win[NFFT];  // periodic hann
 };
 
-__device__ __forceinline__ void fill_tables(SmemTables* tb) {
+__device__ SmemTables g_tables;   // filled once per process by init_tables_kernel
+__global__ void init_tables_kernel() {
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
         float s, c;
         sincospif(-(float)k / 256.0f, &s, &c);
-        tb->tw[k] = make_float2(c, s);
+        g_tables.tw[k] = make_float2(c, s);
     }
-    for (int n = threadIdx.x; n < NFFT; n += blockDim.x) tb->win[n] = 0.5f - 0.5f * cospif((float)n / 256.0f);
+    for (int n = threadIdx.x; n < NFFT; n += blockDim.x) g_tables.win[n] = 0.5f - 0.5f * cospif((float)n / 256.0f);
+}
+__device__ __forceinline__ void fill_tables(SmemTables* tb) {
+    const float4* src = reinterpret_cast<const float4*>(&g_tables);
+    float4* dst = reinterpret_cast<float4*>(tb);
+    for (int i = threadIdx.x; i < (int)(sizeof(SmemTables) / 16); i += blockDim.x) dst[i] = src[i];
+}
+int ensure_tables(cudaStream_t s) {
+    static bool done = false;
+    if (!done) {
+        init_tables_kernel<<<1, 256, 0, s>>>();
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        done = true;
+    }
+    return 0;
 }
 
 // grid: (ceil(T/32), B), block 256. dynamic smem: tables + per-warp FFT buffers + output tile.
@@ -109,7 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const float* __restric
     __syncthreads();
     const size_t plane = (size_t)b * NBIN * T;
     for (int idx = threadIdx.x; idx < NBIN * FRAMES; idx += blockDim.x) {
-        int k = idx >> 5, fi = idx & 31;
+        int k = idx / FRAMES, fi = idx % FRAMES;
         int t = t0 + fi;
         if (t < T) {
             float2 v = tile[k * (FRAMES + 1) + fi];
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const float* __restri
     __syncthreads();
     float* out = wave + (size_t)b * length;
     for (int idx = threadIdx.x; idx < FRAMES * HOP; idx += blockDim.x) {
-        int hbi = idx >> 8, o = idx & 255;
+        int hbi = idx / HOP, o = idx % HOP;
         int hb = hb0 + hbi;
         long long n = (long long)hb * HOP + o - NFFT / 2;
         if (n >= length) continue;
@@ -204,6 +219,7 @@ extern "C" int nppc_stft_mri(const float* wave, int B, int L, int n_fft, int hop
     NPPC_CHECK_ARG(B > 0 && L > NFFT / 2, "nppc_stft_mri: need B>0 and L>%d for reflect padding (B=%d L=%d)", NFFT / 2, B, L);
     NPPC_CHECK_ARG(wave && mag && real && imag, "nppc_stft_mri: null pointer");
     int T = 1 + L / HOP;
+    NPPC_CHECK_ARG(ensure_tables((cudaStream_t)stream) == 0, "nppc_stft_mri: table init failed");
     size_t smem = sizeof(SmemTables) + sizeof(float2) * WARPS * M + sizeof(float2) * NBIN * (FRAMES + 1);
     NPPC_CUDA_OK(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nppc::cdiv(T, FRAMES), B);
@@ -218,6 +234,7 @@ extern "C" int nppc_istft(const float* real, const float* imag, int B, int T, in
     NPPC_CHECK_ARG(n_fft == NFFT && hop == HOP, "nppc_istft: only n_fft=512/hop=256 is built (got %d/%d)", n_fft, hop);
     NPPC_CHECK_ARG(B > 0 && T > 0 && length > 0, "nppc_istft: bad sizes B=%d T=%d length=%d", B, T, length);
     NPPC_CHECK_ARG(real && imag && wave, "nppc_istft: null pointer");
+    NPPC_CHECK_ARG(ensure_tables((cudaStream_t)stream) == 0, "nppc_istft: table init failed");
     size_t smem = sizeof(SmemTables) + sizeof(float2) * WARPS * M + sizeof(float) * (FRAMES + 1) * NFFT +
                   sizeof(float2) * NBIN * (FRAMES + 2);
     NPPC_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
