@@ -206,10 +206,10 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e_step = (t / args.steps).tolist()
+    # whole-job aggregation: all ranks' audio-seconds / the slowest rank's device time (max over ranks)
+    from generative_audio_b200.sharding import aggregate_throughput
+    _, ms_step = aggregate_throughput(B * L / SR, ms_total / args.steps)
+    _, ms_e2e_step = aggregate_throughput(B * L / SR, ms_e2e / args.steps)
     audio_s = B * world * L / SR
     lstm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in lstm_events) / max(len(lstm_events), 1)
     R, Tp = (lstm_events[0][2], lstm_events[0][3]) if lstm_events else (B * F, TP)

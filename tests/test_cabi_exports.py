@@ -1,0 +1,74 @@
+"""CPU checks of the drop-in boundary: libnppc_b200.so builds/loads without a GPU, exports every symbol that
+include/nppc_b200.h declares (and the ctypes table lists each of them), and the host-side mirror keeps the reference's
+state_dict contract (680 tensors, same keys and shapes as nppc_audio.NPPCModel)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "nppc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nppc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    import generative_audio_b200 as g
+    lib = g._lib.load()
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nppc_b200.h but not exported"
+        assert n in g._lib.PROTOTYPES, f"{n} missing from the ctypes prototype table"
+    assert set(g._lib.PROTOTYPES) <= set(names), set(g._lib.PROTOTYPES) - set(names)
+    assert b"sm_100a" in lib.nppc_version()
+
+
+def test_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call: usable on the CPU box."""
+    import generative_audio_b200 as g
+    lib = g._lib.load()
+    assert lib.nppc_stft_mri(None, 1, 4096, 512, 256, None, None, None, None) == -1
+    assert b"null pointer" in lib.nppc_last_error()
+    assert lib.nppc_drop_band(1, 2, 3, 257, 7, 2, 1, None) == -1   # B must be > groups (feature.py:263)
+    assert b"The batch size should larger than the num_groups" in lib.nppc_last_error()
+    assert lib.nppc_gs_scratch_bytes(4, 5) > 0
+
+
+def test_state_dict_contract():
+    import json
+
+    import generative_audio_b200 as g
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")))["entries"]
+    bb = g.FullSubNet_Plus()
+    head = g.MultiDirectionFullSubNet_Plus(g.MultiDirectionConfig(n_directions=5))
+    sd = {"pretrained_restoration_model." + k: tuple(v.shape) for k, v in bb.state_dict().items()}
+    sd.update({"audio_pc_wrapper.net." + k: tuple(v.shape) for k, v in head.state_dict().items()})
+    ref = {k: tuple(10 if s == "2*n_dirs" else s for s in shp) for k, shp in man}
+    assert sd == ref and len(sd) == 680
+
+
+def test_cpu_tensors_and_cpu_device_are_refused():
+    import torch
+
+    import generative_audio_b200 as g
+    with pytest.raises(RuntimeError):
+        g.ops.stft_mri(torch.zeros(1, 4096))
+    cfg = g.NPPCModelConfig(pretrained_restoration_model_configuration=g.FullSubNetPlusConfig(),
+                            pretrained_restoration_model_path="/nonexistent.tar",
+                            audio_pc_wrapper_configuration=g.AudioPCWrapperConfig(
+                                multi_direction_configuration=g.MultiDirectionConfig(n_directions=5)),
+                            stft_configuration=g.StftConfig(), device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g.NPPCModel(cfg)
+
+
+def test_loss_lambda_schedule():
+    import nppc_oracle as O
+    import generative_audio_b200 as g
+    for step in (0, 100, 250, 251, 400, 500, 600):
+        assert g.second_moment_lambda(step, 500, 1.0) == O.second_moment_lambda(step, 500, 1.0)
+    assert g.second_moment_lambda(0, 500, 1.0) == 1e-6 and g.second_moment_lambda(600, 500, 0.5) == 0.5

@@ -1,0 +1,51 @@
+"""N>1 host logic on CPU (gloo, world_size 2): utterance sharding of the inference sweep (BASELINE config 5) and the
+max-over-ranks timing / whole-job aggregation bench.py uses.  The data path has NO collective (independent utterances);
+the only communication is the timing all-reduce."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from generative_audio_b200.sharding import shard_utterances, aggregate_throughput
+    n_utt, micro = 1000, 64
+    mine = shard_utterances(n_utt, rank, world)
+    # every utterance is owned by exactly one rank, round-robin
+    owned = torch.zeros(n_utt, dtype=torch.int64)
+    owned[mine] = 1
+    dist.all_reduce(owned)
+    assert bool((owned == 1).all())
+    assert abs(len(mine) - n_utt / world) <= 1
+    batches = [mine[i:i + micro] for i in range(0, len(mine), micro)]
+    assert sum(len(b) for b in batches) == len(mine) and all(len(b) <= micro for b in batches)
+    # timing aggregation: value = all units / max-over-ranks time
+    my_ms = 100.0 + 50.0 * rank
+    value, ms = aggregate_throughput(len(mine) * 4.0, my_ms, backend_device="cpu")
+    if rank == 0:
+        ret["value"], ret["ms"] = value, ms
+    dist.destroy_process_group()
+
+
+def test_sharding_and_aggregation_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, 29631, ret), nprocs=2, join=True)
+    assert abs(ret["ms"] - 150.0) < 1e-9                     # max over ranks
+    assert abs(ret["value"] - 1000 * 4.0 / 0.150) < 1e-6     # whole-job audio-seconds / slowest rank's time
+
+
+def test_shard_edge_cases():
+    from generative_audio_b200.sharding import shard_utterances
+    assert shard_utterances(0, 0, 4) == []
+    assert shard_utterances(3, 3, 4) == []            # more ranks than utterances: empty shard
+    assert shard_utterances(5, 1, 2) == [1, 3]
+    all_idx = sorted(i for r in range(8) for i in shard_utterances(1000, r, 8))
+    assert all_idx == list(range(1000))
