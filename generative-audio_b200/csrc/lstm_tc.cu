@@ -42,8 +42,9 @@ struct RecSmem {
     static constexpr int NST = 6;                                        // W ring stages
     static constexpr int A_OFF = 0;                                      // h_{t-1}: 6 slabs [128][64] bf16, SW128
     static constexpr int W_OFF = NSLAB * SLAB_BYTES;                     // W_hh ring
-    static constexpr int HST_OFF = W_OFF + NST * SLAB_BYTES;             // 2 x [128][32] bf16 staging for the TMA store of h_t
-    static constexpr int BAR_OFF = HST_OFF + 2 * HST_BYTES;
+    static constexpr int HST_OFF = W_OFF + NST * SLAB_BYTES;             // 2 x [128][32] fp16 staging for the TMA store of h_t
+    static constexpr int X_OFF = HST_OFF + 2 * HST_BYTES;                // layer 0 (fused input projection): x_t [128][64] fp16
+    static constexpr int BAR_OFF = X_OFF + SLAB_BYTES;
 #ifdef NPPC_REC_TRACE
     static constexpr int TRACE_OFF = BAR_OFF + 256;
     static constexpr int TOTAL = TRACE_OFF + 4 * 12 * 16 * 8 + 1024;
@@ -71,11 +72,16 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 // multicast into every CTA's ring.
 // Buffers are time-major with RS (multiple of 128) rows per step:  zx in the interleaved layout written by the GEMM
 // ([m_blk][chunk][warp-quad][half][piece][lane][8 bf16], m_blk = t*tiles + tile), hseq row-major [T'*RS][H].
-template <int CL>
+// FUSE_X (layer 0): the K=64 input projection is fused — x_t is a 7th A slab (TMA from the packed time-major input),
+// W_ih a 7th weight slab per chunk, and the epilogue adds the bias instead of streaming pre-activations from HBM.
+template <int CL, bool FUSE_X>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                const __grid_constant__ CUtensorMap tmap_hst, const uint4* __restrict__ zx, int RS, int Tp) {
+                const __grid_constant__ CUtensorMap tmap_hst, const __grid_constant__ CUtensorMap tmap_x,
+                const __grid_constant__ CUtensorMap tmap_wx, const uint4* __restrict__ zx,
+                const float* __restrict__ bias, int RS, int Tp) {
     constexpr int NST = RecSmem::NST;
+    constexpr int NK = NSLAB + (FUSE_X ? 1 : 0);   // weight slabs per chunk
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RecSmem::BAR_OFF);
@@ -84,7 +90,9 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint64_t* acc_full = a_full + NSLAB;
     uint64_t* acc_empty = acc_full + 1;
     uint64_t* h_ready = acc_empty + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(h_ready + 1);
+    uint64_t* x_full = h_ready + 1;
+    uint64_t* x_free = x_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_free + 1);
 #ifdef NPPC_REC_TRACE
     long long* trace_s = reinterpret_cast<long long*>(smem + RecSmem::TRACE_OFF);
     for (int i = threadIdx.x; i < 4 * 12 * 16; i += NTHREADS) trace_s[i] = 0;
@@ -105,6 +113,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_h);
         tma_prefetch_desc(&tmap_hst);
+        if (FUSE_X) { tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_wx); }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
@@ -112,6 +121,8 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 256);
         mbar_init(h_ready, 1);
+        mbar_init(x_full, 1);
+        mbar_init(x_free, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_ptr);
@@ -131,12 +142,14 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             uint32_t s = 0;
             for (int t = 0; t < Tp; ++t)
                 for (int j = 0; j < NCHUNK; ++j)
-                    for (int k = 0; k < NSLAB; ++k, ++s) {
+                    for (int k = 0; k < NK; ++k, ++s) {
                         mbar_wait(&w_empty[stage], phase ^ 1);   // every CTA of the cluster has released this slot
                         mbar_arrive_expect_tx(&w_full[stage], SLAB_BYTES);
                         unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
-                        if (CL == 1) tma_load_2d(dst, &tmap_w, &w_full[stage], k * 64, j * 128);
-                        else if (s % CL == crank) tma_load_2d_mcast(dst, &tmap_w, &w_full[stage], k * 64, j * 128, CMASK);
+                        const CUtensorMap* tm = (FUSE_X && k == NSLAB) ? &tmap_wx : &tmap_w;
+                        const int kc = (FUSE_X && k == NSLAB) ? 0 : k * 64;
+                        if (CL == 1) tma_load_2d(dst, tm, &w_full[stage], kc, j * 128);
+                        else if (s % CL == crank) tma_load_2d_mcast(dst, tm, &w_full[stage], kc, j * 128, CMASK);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
         }
@@ -145,7 +158,16 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             for (int k = 0; k < NSLAB; ++k) mbar_arrive(&a_full[k]);  // step 0: zeros already in place
+            if (FUSE_X) {
+                mbar_arrive_expect_tx(x_full, SLAB_BYTES);
+                tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, row0);
+            }
             for (int t = 1; t < Tp; ++t) {
+                if (FUSE_X) {   // x_t: needs only the previous step's x MMAs to be done (independent of h)
+                    mbar_wait(x_free, (t - 1) & 1);
+                    mbar_arrive_expect_tx(x_full, SLAB_BYTES);
+                    tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, t * RS + row0);
+                }
                 mbar_wait(h_ready, (t - 1) & 1);
                 for (int k = 0; k < NSLAB; ++k) {
                     mbar_arrive_expect_tx(&a_full[k], SLAB_BYTES);
@@ -165,26 +187,32 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             uint32_t it = 0;  // chunk counter for the acc_empty parity
             const uint32_t a_base = smem_u32(smem + RecSmem::A_OFF);
             const uint32_t w_base = smem_u32(smem + RecSmem::W_OFF);
+            const uint32_t x_base = smem_u32(smem + RecSmem::X_OFF);
             for (int t = 0; t < Tp; ++t) {
                 for (int j = 0; j < NCHUNK; ++j, ++it) {
                     mbar_wait(acc_empty, (it & 1) ^ 1);
                     TRACE(0);
                     tcgen05_fence_after();
-                    for (int k = 0; k < NSLAB; ++k) {
-                        if (j == 0) mbar_wait(&a_full[k], t & 1);
+                    for (int k = 0; k < NK; ++k) {
+                        const bool is_x = FUSE_X && k == NSLAB;
+                        if (j == 0) {
+                            if (is_x) mbar_wait(x_full, t & 1);
+                            else mbar_wait(&a_full[k], t & 1);
+                        }
                         mbar_wait(&w_full[stage], phase);
                         if (k == 0) TRACE(1);
                         if (k == 3) TRACE(2);
                         if (k == 5) TRACE(3);
                         tcgen05_fence_after();
-                        const uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
+                        const uint64_t da = umma_desc_k128(is_x ? x_base : a_base + k * SLAB_BYTES);
                         const uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
                         if (elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
                             if (CL == 1) umma_commit(&w_empty[stage]);
                             else umma_commit_mcast(&w_empty[stage], CMASK);
-                            if (k == NSLAB - 1) umma_commit(acc_full);
+                            if (k == NK - 1) umma_commit(acc_full);
+                            if (is_x && j == NCHUNK - 1) umma_commit(x_free);   // x_t consumed by every chunk of this step
                         }
                         __syncwarp();
                         if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -217,7 +245,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             return zx + (((((size_t)t * tiles + tile_c) * NCHUNK + j) * 4 + ew) * 2 + half) * 256 + lane;
         };
         uint4 zraw[8];
-        {
+        if (!FUSE_X) {
             const uint4* zp = zx_ptr(0, 0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
@@ -241,9 +269,9 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 if (threadIdx.x == 128) TRACE(6);
                 if (threadIdx.x == 352) TRACE(11);
                 uint4 zcur[8];
+                if (!FUSE_X) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) zcur[q] = zraw[q];
-                {
+                    for (int q = 0; q < 8; ++q) zcur[q] = zraw[q];
                     int jn = j + 1, tn = t;
                     if (jn == NCHUNK) { jn = 0; tn = t + 1; }
                     if (tn < Tp) {
@@ -253,15 +281,23 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     }
                 }
                 const __half2* zh = reinterpret_cast<const __half2*>(zcur);  // zh[gate*8 + u/2] = fp16 pair (u, u+1)
+                const float* bj = bias + j * 128 + half * 64;                // fused: warp-uniform (broadcast) bias loads
                 float hv[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                    const float2 pi = __half22float2(zh[u >> 1]), pf = __half22float2(zh[8 + (u >> 1)]);
-                    const float2 pg = __half22float2(zh[16 + (u >> 1)]), po = __half22float2(zh[24 + (u >> 1)]);
-                    float zi = __uint_as_float(gi[u]) + ((u & 1) ? pi.y : pi.x);
-                    float zf = __uint_as_float(gf[u]) + ((u & 1) ? pf.y : pf.x);
-                    float zg = __uint_as_float(gg[u]) + ((u & 1) ? pg.y : pg.x);
-                    float zo = __uint_as_float(go[u]) + ((u & 1) ? po.y : po.x);
+                    float ai, af, ag, ao;
+                    if (FUSE_X) {
+                        ai = __ldg(bj + u); af = __ldg(bj + 16 + u); ag = __ldg(bj + 32 + u); ao = __ldg(bj + 48 + u);
+                    } else {
+                        const float2 pi = __half22float2(zh[u >> 1]), pf = __half22float2(zh[8 + (u >> 1)]);
+                        const float2 pg = __half22float2(zh[16 + (u >> 1)]), po = __half22float2(zh[24 + (u >> 1)]);
+                        ai = (u & 1) ? pi.y : pi.x; af = (u & 1) ? pf.y : pf.x;
+                        ag = (u & 1) ? pg.y : pg.x; ao = (u & 1) ? po.y : po.x;
+                    }
+                    float zi = __uint_as_float(gi[u]) + ai;
+                    float zf = __uint_as_float(gf[u]) + af;
+                    float zg = __uint_as_float(gg[u]) + ag;
+                    float zo = __uint_as_float(go[u]) + ao;
                     float c = sigmoid_fast(zf) * __uint_as_float(cc[u]) + sigmoid_fast(zi) * tanh_fast(zg);
                     cc[u] = __float_as_uint(c);
                     hv[u] = sigmoid_fast(zo) * tanh_fast(c);
@@ -427,10 +463,10 @@ int launch_fc(const __half* hseq, int R, int RS, int Tp, const float* w, const f
     return NPPC_OK;
 }
 
-template <int CL>
-int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const void* zx, int RS, int Tp,
-                  cudaStream_t s) {
-    auto kern = lstm_rec_kernel<CL>;
+template <int CL, bool FUSE_X>
+int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
+                  const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, cudaStream_t s) {
+    auto kern = lstm_rec_kernel<CL, FUSE_X>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
     int tiles = RS / ROWS;
     cudaLaunchConfig_t cfg = {};
@@ -445,7 +481,7 @@ int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, (const uint4*)zx, RS, Tp));
+    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, tx, twx, (const uint4*)zx, bias, RS, Tp));
     NPPC_COUNT_LAUNCH(1);
     return NPPC_OK;
 }
@@ -460,12 +496,13 @@ int rec_cluster_size() {
     return cl;
 }
 
-int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const void* zx, int RS, int Tp,
-               cudaStream_t s) {
+template <bool FUSE_X>
+int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
+               const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, cudaStream_t s) {
     switch (rec_cluster_size()) {
-        case 1: return launch_rec_cl<1>(tw, th, thst, zx, RS, Tp, s);
-        case 2: return launch_rec_cl<2>(tw, th, thst, zx, RS, Tp, s);
-        default: return launch_rec_cl<4>(tw, th, thst, zx, RS, Tp, s);
+        case 1: return launch_rec_cl<1, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
+        case 2: return launch_rec_cl<2, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
+        default: return launch_rec_cl<4, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
     }
 }
 
@@ -527,15 +564,25 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     if (rc) return rc;
     rc = tc::make_tmap_bf16_2d(&thst, hseq, (uint64_t)M, H, H * 2, ROWS, CH, 0);
     if (rc) return rc;
-    // layer 0
-    rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
+    // layer 0: input projection (K = 64) fused into the recurrent kernel unless NPPC_LSTM_FUSE_X=0
+    static const bool fuse_x = !(getenv("NPPC_LSTM_FUSE_X") && atoi(getenv("NPPC_LSTM_FUSE_X")) == 0);
+    CUtensorMap tx, twx;
+    rc = tc::make_tmap_bf16_2d(&tx, xs, (uint64_t)M, (uint64_t)KP, (uint64_t)KP * 2, ROWS, 64);
     if (rc) return rc;
-    rc = launch_rec(tw[0], th, thst, zx, RS, Tp, s);
+    rc = tc::make_tmap_bf16_2d(&twx, p->wp_ih[0], H4, (uint64_t)KP, (uint64_t)KP * 2, 128, 64);
+    if (rc) return rc;
+    if (fuse_x && KP == 64) {
+        rc = launch_rec<true>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, s);
+    } else {
+        rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
+        if (rc) return rc;
+        rc = launch_rec<false>(tw[0], th, thst, tx, twx, zx, nullptr, RS, Tp, s);
+    }
     if (rc) return rc;
     // layer 1 (+ fc)
     rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
     if (rc) return rc;
-    rc = launch_rec(tw[1], th, thst, zx, RS, Tp, s);
+    rc = launch_rec<false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, s);
     if (rc) return rc;
     switch ((p->O + 3) / 4) {
         case 1: return launch_fc<1>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
