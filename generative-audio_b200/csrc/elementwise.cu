@@ -88,16 +88,16 @@ __global__ void __launch_bounds__(TPB) offline_norm_kernel(const float* __restri
                                                           float* __restrict__ y) {
     const int b = blockIdx.y;
     const float mu = (float)(sums[b] / count);
-    const float den = mu + 1e-5f;
+    const float inv = 1.0f / (mu + 1e-5f);   // x * (1/den): within 1 ulp of the reference's x / den
     const float* xb = x + (size_t)b * n;
     float* yb = y + (size_t)b * n;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {   // 4 independent loads in flight per thread
         float v0 = xb[i], v1 = xb[i + stride], v2 = xb[i + 2 * stride], v3 = xb[i + 3 * stride];
-        yb[i] = v0 / den; yb[i + stride] = v1 / den; yb[i + 2 * stride] = v2 / den; yb[i + 3 * stride] = v3 / den;
+        yb[i] = v0 * inv; yb[i + stride] = v1 * inv; yb[i + 2 * stride] = v2 * inv; yb[i + 3 * stride] = v3 * inv;
     }
-    for (; i < n; i += stride) yb[i] = xb[i] / den;
+    for (; i < n; i += stride) yb[i] = xb[i] * inv;
 }
 
 // x [B,F,T] -> y [B,F,T+la] = pad + norm (mean counts the zero look-ahead frames, fullsubnet_plus.py:158-165)
@@ -106,13 +106,13 @@ __global__ void __launch_bounds__(TPB) pad_norm_kernel(const float* __restrict__
     const int b = blockIdx.y;
     const int Tp = T + la;
     const float mu = (float)(sums[b] / ((double)F * Tp));
-    const float den = mu + 1e-5f;
+    const float inv = 1.0f / (mu + 1e-5f);
     const float* xb = x + (size_t)b * F * T;
     float* yb = y + (size_t)b * F * Tp;
     const int n = F * Tp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int f = i / Tp, t = i - f * Tp;
-        yb[i] = (t < T) ? xb[f * T + t] / den : 0.0f / den;
+        yb[i] = (t < T) ? xb[f * T + t] * inv : 0.0f;
     }
 }
 
@@ -269,12 +269,14 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
             f = g + G * j;
         }
         const float den = (float)(sums[sb] / ((double)F * S * Tp)) + 1e-5f;
+        const float inv = 1.0f / den;   // x * (1/den): within 1 ulp of the reference's x / den, well inside the 1e-4 budget
+        const float* base = nbr + (size_t)sb * F * Tp + t;
         const size_t off = (size_t)sb * F * Tp + t;
 #pragma unroll 8
-        for (int k = 0; k < 2 * nn + 1; ++k) mine[k * TS] = nbr[off + (size_t)reflect_idx(f + k - nn, F) * Tp] / den;
-        mine[(2 * nn + 1) * TS] = fb[off + (size_t)f * Tp] / den;
-        mine[(2 * nn + 2) * TS] = fbr[off + (size_t)f * Tp] / den;
-        mine[(2 * nn + 3) * TS] = fbi[off + (size_t)f * Tp] / den;
+        for (int k = 0; k < 2 * nn + 1; ++k) mine[k * TS] = base[reflect_idx(f + k - nn, F) * Tp] * inv;
+        mine[(2 * nn + 1) * TS] = fb[off + (size_t)f * Tp] * inv;
+        mine[(2 * nn + 2) * TS] = fbr[off + (size_t)f * Tp] * inv;
+        mine[(2 * nn + 3) * TS] = fbi[off + (size_t)f * Tp] * inv;
         for (int k = S; k < PK_KP; ++k) mine[k * TS] = 0.f;
     } else {
         for (int k = 0; k < PK_KP; ++k) mine[k * TS] = 0.f;

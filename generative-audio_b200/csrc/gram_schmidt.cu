@@ -100,16 +100,18 @@ __device__ __forceinline__ cd cmul(cd a, cd b) { return {a.x * b.x - a.y * b.y, 
 __device__ __forceinline__ cd cconj(cd a) { return {a.x, -a.y}; }
 
 // One thread per sample. mode: do_gs (orthogonalise; else A = identity), has_err (loss statistics).
-template <bool COMPLEX>
-__global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n, int do_gs, int has_err,
+template <bool COMPLEX, int N_T>   // N_T = compile-time n (fully unrolled, everything in registers); 0 = generic
+__global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n_rt, int do_gs, int has_err,
                                 float* __restrict__ err_norm, float* __restrict__ err_proj,
                                 float* __restrict__ w_norms, float* __restrict__ reconst_err,
                                 float* __restrict__ second_moment) {
     int b = blockIdx.x;
     if (b >= B || threadIdx.x != 0) return;
     SampleScratch& s = scr[b];
+    const int n = N_T > 0 ? N_T : n_rt;
     const int nv = n + (has_err ? 1 : 0);
-    cd Gl[NV_MAX][NV_MAX];   // full Hermitian matrix from the stored upper triangle (local copy: no global loads in the solve)
+    constexpr int GD = N_T > 0 ? N_T + 1 : NV_MAX;
+    cd Gl[GD][GD];   // full Hermitian matrix from the stored upper triangle (local copy: no global loads in the solve)
     for (int j = 0; j < nv; ++j)
         for (int k = j; k < nv; ++k) {
             cd g{s.G[(j * NV_MAX + k) * 2], s.G[(j * NV_MAX + k) * 2 + 1]};
@@ -117,11 +119,12 @@ __global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n, i
             Gl[k][j] = cd{g.x, -g.y};
         }
     auto G = [&](int j, int k) -> cd { return Gl[j][k]; };
-    cd ahat[12][12];  // normalised coefficient vectors of the previous directions
-    cd v[12][12];     // v_j = G * ahat_j
-    double nu[12];
+    constexpr int ND = N_T > 0 ? N_T : 12;
+    cd ahat[ND][ND];  // normalised coefficient vectors of the previous directions
+    cd v[ND][ND];     // v_j = G * ahat_j
+    double nu[ND];
     for (int i = 0; i < n; ++i) {
-        cd a[12];
+        cd a[ND];
         for (int k = 0; k < n; ++k) a[k] = cd{k == i ? 1.0 : 0.0, 0.0};
         if (do_gs) {
             for (int j = 0; j < i; ++j) {
@@ -283,8 +286,14 @@ int run(const float* x, const float* gt, const float* pred, int B, int n, long l
     NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
     int rc = dispatch_gram<COMPLEX>(n + has_err, x, gt, pred, B, n, P, scr, s);
     if (rc) return rc;
-    gs_solve_kernel<COMPLEX><<<B, 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms,
-                                                           reconst_err, second_moment);
+#define SOLVE(NT) gs_solve_kernel<COMPLEX, NT><<<B, 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms, reconst_err, second_moment)
+    switch (n) {
+        case 4: SOLVE(4); break;
+        case 5: SOLVE(5); break;
+        case 10: SOLVE(10); break;
+        default: SOLVE(0); break;
+    }
+#undef SOLVE
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     if (out) return dispatch_apply<COMPLEX>(n, x, B, P, scr, out, s);
