@@ -1,13 +1,13 @@
-"""NPPC-audio training-step statistics (a14): forward of NPPCAudioTrainer.base_step (nppc_audio/trainer.py:234-317),
-_get_true_and_pred_crm (:344-371) and _calculate_final_objective (:337-342) on the B200 kernels.
+"""NPPC-audio training step (a14): NPPCAudioTrainer.base_step (nppc_audio/trainer.py:234-317), _get_true_and_pred_crm
+(:344-371) and _calculate_final_objective (:337-342).
 
-Compared with the reference step the frozen backbone and the noisy STFT run ONCE (the reference runs the backbone
-twice and the noisy STFT three times) and Gram-Schmidt + loss are two HBM passes in total.
-Round-1 scope: forward statistics (reconst_err, objective, log dict); the hand-written backward of the PC head is
-not built yet, so `objective` carries no autograd graph."""
+`base_step(batch)` (no grad): everything on the B200 kernels; the frozen backbone and the noisy STFT run ONCE (the reference
+runs the backbone twice and the noisy STFT three times); Gram-Schmidt + loss are two HBM passes in total.
+`base_step(batch, requires_grad=True)` / `train_step`: same statistics with an autograd graph through the PC head — the
+frozen half still runs on the hand-written kernels, the head's forward/backward on torch autograd (see training.py)."""
 import torch
 
-from . import ops
+from . import ops, training
 from .nppc_model import NPPCModel
 
 
@@ -24,9 +24,53 @@ class NPPCAudioStep:
         self.second_moment_loss_grace = second_moment_loss_grace
         self.second_moment_loss_lambda = second_moment_loss_lambda
 
-    @torch.no_grad()
-    def base_step(self, batch):
+    def base_step(self, batch, requires_grad: bool = False):
         """batch = (noisy [B,L], clean [B,L]) -> (reconst_err [B], objective [], log dict with the reference's keys)."""
+        if requires_grad:
+            return self._base_step_autograd(batch)
+        with torch.no_grad():
+            return self._base_step_kernels(batch)
+
+    def _frozen_half(self, noisy, clean):
+        """Kernels only: STFTs, frozen backbone, enhanced spectrum (conj quirk), gt / pred cIRM after drop_band."""
+        model = self.nppc_model
+        G = model.audio_pc_wrapper.net.num_groups_in_drop_band
+        c = model.config.stft_configuration
+        with torch.no_grad():
+            mag, real, imag = ops.stft_mri(noisy.to(model.device), c.nfft, c.hop_length, c.win_length)
+            pred_crm = model.pretrained_restoration_model(mag, real, imag)
+            emag, ereal, eimag = ops.crm_decompress_apply(pred_crm, real, imag, conj=True)
+            _, cr, ci = ops.stft_mri(clean.to(model.device), c.nfft, c.hop_length, c.win_length)
+            gt = ops.drop_band(ops.build_cirm(real[:, 0], imag[:, 0], cr[:, 0], ci[:, 0]), G)
+            pred = ops.drop_band(pred_crm, G)
+        return (mag, real, imag, emag[:, None], ereal[:, None], eimag[:, None]), gt, pred
+
+    def _base_step_autograd(self, batch):
+        model = self.nppc_model
+        noisy, clean = batch
+        feats, gt, pred = self._frozen_half(noisy, clean)
+        head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats)
+        w_mat = training.gram_schmidt_autograd(head)
+        lam = second_moment_lambda(self.step, self.second_moment_loss_grace, self.second_moment_loss_lambda)
+        st = training.nppc_loss_autograd(w_mat, gt, pred, lam)
+        log = {"noisy_complex": noisy, "clean_complex": clean, "pred_crm": pred, "w_mat": w_mat.detach(),
+               "err_norm": st["err_norm"].detach(), "err_proj": st["err_proj"].detach(),
+               "err_proj_mag": st["err_proj_mag"].detach(), "w_norms": st["w_norms"].detach(),
+               "reconst_err": st["reconst_err"].detach(), "second_moment_mse": st["second_moment_mse"].detach(),
+               "objective": st["objective"].detach()}
+        return st["reconst_err"], st["objective"], log
+
+    def train_step(self, batch, optimizer):
+        """zero_grad / backward / DP gradient all-reduce / optimizer.step (trainer.py:100-106) -> (objective, log)."""
+        optimizer.zero_grad(set_to_none=True)
+        _, objective, log = self.base_step(batch, requires_grad=True)
+        objective.backward()
+        training.allreduce_gradients(self.nppc_model.audio_pc_wrapper.parameters())
+        optimizer.step()
+        self.step += 1
+        return objective.detach(), log
+
+    def _base_step_kernels(self, batch):
         model = self.nppc_model
         noisy, clean = batch
         G = model.audio_pc_wrapper.net.num_groups_in_drop_band

@@ -73,3 +73,44 @@ def test_batch_of_one_skips_drop_band_assert():
     assert rel_err(m(x.cuda()).cpu(), ref) < 2e-3
     with pytest.raises(AssertionError):
         m(wave(2, 4096, 23).cuda())  # B=2 is not > groups=2 (feature.py:263)
+
+
+def test_training_step_autograd_matches_reference_gradients():
+    """base_step(requires_grad=True): frozen half on the kernels, PC head on autograd; objective and gradients vs the
+    unmodified reference's CPU autograd (tests/golden/model_step_g2_b4_grads.npz)."""
+    import generative_audio_b200 as G
+    g = load_golden("model_step_g2_b4")
+    gg = load_golden("model_step_g2_b4_grads")
+    m, sd = build_model(5, 2, "f32")
+    st = G.NPPCAudioStep(m, 500, 1.0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for step in (0, 600):
+            st.step = step
+            m.zero_grad(set_to_none=True)
+            reconst, obj, log = st.base_step((g["noisy"].cuda(), g["clean"].cuda()), requires_grad=True)
+            assert abs(obj.item() - gg[f"s{step}_objective"].item()) < 2e-3
+            obj.backward()
+            net = m.audio_pc_wrapper.net
+            assert all(p.grad is None for p in m.pretrained_restoration_model.parameters())  # frozen backbone
+            picks = {"sb_fc_w": net.sb_model.fc_output_layer.weight, "sb_fc_b": net.sb_model.fc_output_layer.bias,
+                     "lstm_b_hh_l1": net.sb_model.sequence_model.bias_hh_l1, "lstm_w_ih_l0": net.sb_model.sequence_model.weight_ih_l0}
+            for k, p in picks.items():
+                assert rel_err(p.grad.cpu(), gg[f"s{step}_{k}"]) < 2e-2, k
+            gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in net.parameters() if p.grad is not None)).item()
+            assert abs(gn - gg[f"s{step}_head_grad_norm"].item()) < 2e-2 * gg[f"s{step}_head_grad_norm"].item()
+        # the no-grad kernel path gives the same statistics
+        st.step = 600
+        r2, o2, _ = st.base_step((g["noisy"].cuda(), g["clean"].cuda()))
+        assert abs(o2.item() - obj.item()) < 2e-3
+        # one optimizer step runs end to end and changes the head only
+        opt = torch.optim.Adam(m.audio_pc_wrapper.parameters(), lr=1e-4)
+        before = net.sb_model.fc_output_layer.weight.detach().clone()
+        bb_before = m.pretrained_restoration_model.sb_model.fc_output_layer.weight.detach().clone()
+        st.train_step((g["noisy"].cuda(), g["clean"].cuda()), opt)
+        assert not torch.equal(before, net.sb_model.fc_output_layer.weight)
+        assert torch.equal(bb_before, m.pretrained_restoration_model.sb_model.fc_output_layer.weight)
+        assert st.step == 601
+    finally:
+        torch.backends.cudnn.allow_tf32 = True

@@ -49,3 +49,28 @@ def test_shard_edge_cases():
     assert shard_utterances(5, 1, 2) == [1, 3]
     all_idx = sorted(i for r in range(8) for i in shard_utterances(1000, r, 8))
     assert all_idx == list(range(1000))
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from generative_audio_b200.training import allreduce_gradients
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 1000, 3, 70000)]
+    params.append(torch.nn.Parameter(torch.zeros(4)))  # no grad: must be skipped
+    for i, p in enumerate(params[:4]):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    calls = allreduce_gradients(params, bucket_bytes=2048)
+    expect = [(1 + 2) / 2 * (i + 1) for i in range(4)]   # mean over 2 ranks
+    ok = all(torch.allclose(p.grad, torch.full_like(p, e)) for p, e in zip(params[:4], expect)) and params[4].grad is None
+    if rank == 0:
+        ret["ok"], ret["calls"] = ok, calls
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_allreduce_world2():
+    """DP training exchange: flat-bucket mean all-reduce of the PC-head gradients."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, 29641, ret), nprocs=2, join=True)
+    assert ret["ok"] and ret["calls"] >= 2
