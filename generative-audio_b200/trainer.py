@@ -49,10 +49,11 @@ class NPPCAudioStep:
         model = self.nppc_model
         noisy, clean = batch
         feats, gt, pred = self._frozen_half(noisy, clean)
-        head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats)
-        w_mat = training.gram_schmidt_autograd(head)
         lam = second_moment_lambda(self.step, self.second_moment_loss_grace, self.second_moment_loss_lambda)
-        st = training.nppc_loss_autograd(w_mat, gt, pred, lam)
+        with torch.enable_grad():
+            head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats)
+            w_mat = training.gram_schmidt_autograd(head)
+            st = training.nppc_loss_autograd(w_mat, gt, pred, lam)
         log = {"noisy_complex": noisy, "clean_complex": clean, "pred_crm": pred, "w_mat": w_mat.detach(),
                "err_norm": st["err_norm"].detach(), "err_proj": st["err_proj"].detach(),
                "err_proj_mag": st["err_proj_mag"].detach(), "w_norms": st["w_norms"].detach(),

@@ -79,7 +79,13 @@ def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag):
         sb = _drop_band(sb.permute(0, 2, 1, 3), net.num_groups_in_drop_band).permute(0, 2, 1, 3)
     Fp, S = sb.shape[1], sb.shape[2]
     seq = sb.reshape(B * Fp, S, Tp).permute(0, 2, 1).contiguous()
-    o, _ = net.sb_model.sequence_model(seq)
+    lstm = net.sb_model.sequence_model
+    was_training = lstm.training
+    lstm.train(True)   # cuDNN's RNN backward needs the training-mode forward (no dropout here: identical numerics)
+    try:
+        o, _ = lstm(seq)
+    finally:
+        lstm.train(was_training)
     y = net.sb_model.fc_output_layer(o).permute(0, 2, 1)  # [B*F', 2n, T']
     n = net.n_directions
     return y.reshape(B, Fp, n, 2, Tp).permute(0, 2, 3, 1, 4)[..., la:]

@@ -91,7 +91,8 @@ def test_training_step_autograd_matches_reference_gradients():
             m.zero_grad(set_to_none=True)
             reconst, obj, log = st.base_step((g["noisy"].cuda(), g["clean"].cuda()), requires_grad=True)
             assert abs(obj.item() - gg[f"s{step}_objective"].item()) < 2e-3
-            obj.backward()
+            with torch.enable_grad():
+                obj.backward()
             net = m.audio_pc_wrapper.net
             assert all(p.grad is None for p in m.pretrained_restoration_model.parameters())  # frozen backbone
             picks = {"sb_fc_w": net.sb_model.fc_output_layer.weight, "sb_fc_b": net.sb_model.fc_output_layer.bias,
