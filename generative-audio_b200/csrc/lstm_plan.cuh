@@ -16,6 +16,7 @@ struct nppc_lstm_plan {
     __nv_bfloat16* wp_ih[2];   // [4H][KP] permuted rows
     __nv_bfloat16* wp_hh[2];   // [4H][H]  permuted rows
     float* bias_p[2];          // [4H] permuted
+    __nv_bfloat16* wp_fc;      // [16][H] fp16 fc weights, rows >= O zero (fused fc of the last layer, O <= 16)
 };
 
 namespace nppc {

@@ -74,14 +74,19 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 // ([m_blk][chunk][warp-quad][half][piece][lane][8 bf16], m_blk = t*tiles + tile), hseq row-major [T'*RS][H].
 // FUSE_X (layer 0): the K=64 input projection is fused — x_t is a 7th A slab (TMA from the packed time-major input),
 // W_ih a 7th weight slab per chunk, and the epilogue adds the bias instead of streaming pre-activations from HBM.
-template <int CL, bool FUSE_X>
+// FUSE_FC (last layer): y_{t-1} = W_fc h_{t-1} + b is a 13th, 16-column mini-chunk issued at the start of step t (h_{t-1} is the
+// A operand that was just reloaded), plus one pseudo-step after the last; its 128 x 16 fp32 result is read from TMEM cols 0..15.
+template <int CL, bool FUSE_X, bool FUSE_FC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const __grid_constant__ CUtensorMap tmap_hst, const __grid_constant__ CUtensorMap tmap_x,
-                const __grid_constant__ CUtensorMap tmap_wx, const uint4* __restrict__ zx,
-                const float* __restrict__ bias, int RS, int Tp) {
+                const __grid_constant__ CUtensorMap tmap_wx, const __grid_constant__ CUtensorMap tmap_fc,
+                const uint4* __restrict__ zx, const float* __restrict__ bias, int RS, int Tp,
+                const float* __restrict__ fc_b, int O, int R, float* __restrict__ y) {
     constexpr int NST = RecSmem::NST;
     constexpr int NK = NSLAB + (FUSE_X ? 1 : 0);   // weight slabs per chunk
+    constexpr int FC_SLAB_BYTES = 16 * 64 * 2;     // [16 outputs][64 k] fp16
+    const int Tx = Tp + (FUSE_FC ? 1 : 0);         // steps incl. the fc-only pseudo-step
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RecSmem::BAR_OFF);
@@ -114,6 +119,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         tma_prefetch_desc(&tmap_h);
         tma_prefetch_desc(&tmap_hst);
         if (FUSE_X) { tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_wx); }
+        if (FUSE_FC) tma_prefetch_desc(&tmap_fc);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
@@ -140,7 +146,17 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             uint32_t s = 0;
-            for (int t = 0; t < Tp; ++t)
+            for (int t = 0; t < Tx; ++t) {
+                if (FUSE_FC && t >= 1)
+                    for (int k = 0; k < NSLAB; ++k, ++s) {   // fc weights for y_{t-1}
+                        mbar_wait(&w_empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&w_full[stage], FC_SLAB_BYTES);
+                        unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
+                        if (CL == 1) tma_load_2d(dst, &tmap_fc, &w_full[stage], k * 64, 0);
+                        else if (s % CL == crank) tma_load_2d_mcast(dst, &tmap_fc, &w_full[stage], k * 64, 0, CMASK);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                if (t >= Tp) break;
                 for (int j = 0; j < NCHUNK; ++j)
                     for (int k = 0; k < NK; ++k, ++s) {
                         mbar_wait(&w_empty[stage], phase ^ 1);   // every CTA of the cluster has released this slot
@@ -152,6 +168,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         else if (s % CL == crank) tma_load_2d_mcast(dst, tm, &w_full[stage], kc, j * 128, CMASK);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
+            }
         }
     } else if (warp == 3) {
         // ---- A producer: reload h_t (TMA-stored by the epilogue) as the A operand of step t+1 ----
@@ -162,8 +179,8 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 mbar_arrive_expect_tx(x_full, SLAB_BYTES);
                 tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, row0);
             }
-            for (int t = 1; t < Tp; ++t) {
-                if (FUSE_X) {   // x_t: needs only the previous step's x MMAs to be done (independent of h)
+            for (int t = 1; t < Tx; ++t) {
+                if (FUSE_X && t < Tp) {   // x_t: needs only the previous step's x MMAs to be done (independent of h)
                     mbar_wait(x_free, (t - 1) & 1);
                     mbar_arrive_expect_tx(x_full, SLAB_BYTES);
                     tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, t * RS + row0);
@@ -188,7 +205,30 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             const uint32_t a_base = smem_u32(smem + RecSmem::A_OFF);
             const uint32_t w_base = smem_u32(smem + RecSmem::W_OFF);
             const uint32_t x_base = smem_u32(smem + RecSmem::X_OFF);
-            for (int t = 0; t < Tp; ++t) {
+            for (int t = 0; t < Tx; ++t) {
+                if (FUSE_FC && t >= 1) {   // y_{t-1}: [128 x 16] = h_{t-1} * W_fc^T into TMEM cols 0..15
+                    constexpr uint32_t idesc_fc = umma_idesc_f16(ROWS, 16);
+                    mbar_wait(acc_empty, (it & 1) ^ 1);
+                    tcgen05_fence_after();
+                    for (int k = 0; k < NSLAB; ++k) {
+                        mbar_wait(&a_full[k], t & 1);
+                        mbar_wait(&w_full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
+                        const uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc_fc, (k | kk) != 0);
+                            if (CL == 1) umma_commit(&w_empty[stage]);
+                            else umma_commit_mcast(&w_empty[stage], CMASK);
+                            if (k == NSLAB - 1) umma_commit(acc_full);
+                        }
+                        __syncwarp();
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                    ++it;
+                }
+                if (t >= Tp) break;
                 for (int j = 0; j < NCHUNK; ++j, ++it) {
                     mbar_wait(acc_empty, (it & 1) ^ 1);
                     TRACE(0);
@@ -250,7 +290,27 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 #pragma unroll
             for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
         }
-        for (int t = 0; t < Tp; ++t) {
+        const bool valid = live && (row0 + rloc) < R;
+        for (int t = 0; t < Tx; ++t) {
+            if (FUSE_FC && t >= 1) {   // fc mini-chunk: y[row][o][t-1] from TMEM cols 0..15 (half 0 threads own the rows)
+                mbar_wait(acc_full, it & 1);
+                tcgen05_fence_after();
+                uint32_t yv[16];
+                if (half == 0) {
+                    tmem_ld16(t_lane, yv);
+                    tmem_wait_ld();
+                }
+                tcgen05_fence_before();
+                mbar_arrive(acc_empty);
+                if (half == 0 && valid) {
+                    float* dst = y + (size_t)(row0 + rloc) * O * Tp + (t - 1);
+#pragma unroll
+                    for (int o = 0; o < 16; ++o)
+                        if (o < O) dst[(size_t)o * Tp] = __uint_as_float(yv[o]) + __ldg(fc_b + o);
+                }
+                ++it;
+            }
+            if (t >= Tp) break;
 #pragma unroll 1
             for (int j = 0; j < NCHUNK; ++j, ++it) {
                 mbar_wait(acc_full, it & 1);
@@ -361,6 +421,10 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int K, int KP, __half
         out[i] = __float2half_rn(k < K ? fminf(fmaxf(w[(size_t)src * K + k], -65504.f), 65504.f) : 0.f);
     }
 }
+__global__ void pack_fc_kernel(const float* __restrict__ w, int O, __half* __restrict__ out) {  // [O][H] f32 -> [16][H] fp16
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 16 * H) out[i] = __float2half_rn(i / H < O ? fminf(fmaxf(w[i], -65504.f), 65504.f) : 0.f);
+}
 __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < H4) {
@@ -463,10 +527,18 @@ int launch_fc(const __half* hseq, int R, int RS, int Tp, const float* w, const f
     return NPPC_OK;
 }
 
-template <int CL, bool FUSE_X>
+struct FcArgs {
+    const CUtensorMap* tfc;
+    const float* fc_b;
+    int O, R;
+    float* y;
+};
+
+template <int CL, bool FUSE_X, bool FUSE_FC>
 int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
-                  const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, cudaStream_t s) {
-    auto kern = lstm_rec_kernel<CL, FUSE_X>;
+                  const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc,
+                  cudaStream_t s) {
+    auto kern = lstm_rec_kernel<CL, FUSE_X, FUSE_FC>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
     int tiles = RS / ROWS;
     cudaLaunchConfig_t cfg = {};
@@ -481,7 +553,8 @@ int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, tx, twx, (const uint4*)zx, bias, RS, Tp));
+    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, tx, twx, *fc.tfc, (const uint4*)zx, bias, RS, Tp, fc.fc_b, fc.O,
+                                    fc.R, fc.y));
     NPPC_COUNT_LAUNCH(1);
     return NPPC_OK;
 }
@@ -496,13 +569,13 @@ int rec_cluster_size() {
     return cl;
 }
 
-template <bool FUSE_X>
+template <bool FUSE_X, bool FUSE_FC>
 int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
-               const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, cudaStream_t s) {
+               const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc, cudaStream_t s) {
     switch (rec_cluster_size()) {
-        case 1: return launch_rec_cl<1, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
-        case 2: return launch_rec_cl<2, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
-        default: return launch_rec_cl<4, FUSE_X>(tw, th, thst, tx, twx, zx, bias, RS, Tp, s);
+        case 1: return launch_rec_cl<1, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
+        case 2: return launch_rec_cl<2, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
+        default: return launch_rec_cl<4, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
     }
 }
 
@@ -531,11 +604,14 @@ int lstm_plan_pack_tc(nppc_lstm_plan* p, const float* w_ih0, const float* w_hh0,
         pack_w_kernel<<<256, 256, 0, s>>>(whh[l], H, H, (__half*)p->wp_hh[l]);
         pack_b_kernel<<<cdiv(H4, 256), 256, 0, s>>>(p->bias[l], p->bias_p[l]);
     }
+    NPPC_CUDA_OK(cudaMalloc(&p->wp_fc, sizeof(__half) * 16 * H));
+    pack_fc_kernel<<<cdiv(16 * H, 256), 256, 0, s>>>(p->fc_w, p->O, (__half*)p->wp_fc);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
 }
 
 void lstm_plan_free_tc(nppc_lstm_plan* p) {
+    cudaFree(p->wp_fc);
     for (int l = 0; l < 2; ++l) {
         cudaFree(p->wp_ih[l]); cudaFree(p->wp_hh[l]); cudaFree(p->bias_p[l]);
     }
@@ -571,18 +647,27 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     if (rc) return rc;
     rc = tc::make_tmap_bf16_2d(&twx, p->wp_ih[0], H4, (uint64_t)KP, (uint64_t)KP * 2, 128, 64);
     if (rc) return rc;
+    static const bool fuse_fc = !(getenv("NPPC_LSTM_FUSE_FC") && atoi(getenv("NPPC_LSTM_FUSE_FC")) == 0);
+    CUtensorMap tfc;
+    rc = tc::make_tmap_bf16_2d(&tfc, p->wp_fc, 16, H, H * 2, 16, 64);
+    if (rc) return rc;
+    const FcArgs no_fc{&tfc, nullptr, 0, R, nullptr};
     if (fuse_x && KP == 64) {
-        rc = launch_rec<true>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, s);
+        rc = launch_rec<true, false>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, no_fc, s);
     } else {
         rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
         if (rc) return rc;
-        rc = launch_rec<false>(tw[0], th, thst, tx, twx, zx, nullptr, RS, Tp, s);
+        rc = launch_rec<false, false>(tw[0], th, thst, tx, twx, zx, nullptr, RS, Tp, no_fc, s);
     }
     if (rc) return rc;
     // layer 1 (+ fc)
     rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
     if (rc) return rc;
-    rc = launch_rec<false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, s);
+    if (fuse_fc && p->O <= 16) {   // fc fused into the last layer's recurrent kernel (13th mini-chunk per step)
+        const FcArgs fc{&tfc, p->fc_b, p->O, R, y};
+        return launch_rec<false, true>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
+    }
+    rc = launch_rec<false, false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, no_fc, s);
     if (rc) return rc;
     switch ((p->O + 3) / 4) {
         case 1: return launch_fc<1>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);
