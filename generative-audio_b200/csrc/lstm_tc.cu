@@ -1,17 +1,9 @@
-// a7, implementation 1: bf16 tcgen05 tensor-core LSTM (2 layers + fc), H = 384.
+// a7, implementation 1: fp16 tcgen05 tensor-core LSTM (2 layers + fc), H = 384.
 //
-// Per layer:  (1) input projection for ALL steps as one big GEMM (gemm_tc.cu):  Zx[T'*R, 4H] = X * W_ih^T + (b_ih+b_hh)
-//             (2) persistent recurrent kernel: one CTA owns 128 sequences for all T' steps.
-//
-// Recurrent kernel, per step t and per gate chunk j (32 hidden units = 128 gate columns, 12 chunks):
-//   tensor core : acc[128 x 128] (TMEM cols 0..127) = h_{t-1}[128 x 384] (smem, bf16, K-major SW128) * W_hh[chunk j]^T
-//                 W_hh streams from L2 through a 6-stage TMA ring (it is shared by every CTA and stays L2-resident)
-//   epilogue    : 8 warps; thread = (row, 16-hidden-unit half): acc + Zx -> sigmoid/tanh -> c (fp32, resident in TMEM
-//                 cols 128..511) -> h ; h_t is written (bf16) to the time-major h sequence in global memory, which is
-//                 both the next layer's GEMM operand and this CTA's own A operand for step t+1 (re-loaded by TMA, so
-//                 L2 acts as the double buffer that shared memory has no room for); last layer: fc partial sums.
-// Gate columns are permuted at pack time so that a thread's 4 gates x 16 units are contiguous in Zx and in TMEM:
-//   packed column = chunk*128 + half*64 + gate*16 + u   <->   nn.LSTM row gate*H + chunk*32 + half*16 + u.
+// Layer 0:  ONE persistent recurrent kernel; the K = 64 input projection is fused (x_t is a 7th A slab).
+// Layer 1:  input projection for ALL steps as one big GEMM (gemm_tc.cu): Zx[T'*R, 4H] = H0 * W_ih^T + (b_ih+b_hh), fp16,
+//           then the persistent recurrent kernel, which also computes the fc output layer (16-column mini-chunk per step).
+// The recurrent kernel (CTA pair, cta_group::2) is described at lstm_rec_kernel below.
 #include <stdlib.h>
 #include <string.h>
 #include <cuda_fp16.h>
@@ -36,23 +28,7 @@ constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have th
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
 constexpr int OPMAX = 24;
 
-constexpr int HST_BYTES = ROWS * CH * 2;   // one chunk of h_t for the CTA's rows: [128][32] bf16 = 8 KB
-
-struct RecSmem {
-    static constexpr int NST = 6;                                        // W ring stages
-    static constexpr int A_OFF = 0;                                      // h_{t-1}: 6 slabs [128][64] bf16, SW128
-    static constexpr int W_OFF = NSLAB * SLAB_BYTES;                     // W_hh ring
-    static constexpr int HST_OFF = W_OFF + NST * SLAB_BYTES;             // 2 x [128][32] fp16 staging for the TMA store of h_t
-    static constexpr int X_OFF = HST_OFF + 2 * HST_BYTES;                // layer 0 (fused input projection): x_t [128][64] fp16
-    static constexpr int BAR_OFF = X_OFF + SLAB_BYTES;
-#ifdef NPPC_REC_TRACE
-    static constexpr int TRACE_OFF = BAR_OFF + 256;
-    static constexpr int TOTAL = TRACE_OFF + 4 * 12 * 16 * 8 + 1024;
-#else
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-#endif
-    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
-};
+constexpr int HST_BYTES = ROWS * CH * 2;   // one chunk of h_t for the CTA's rows: [128][32] fp16 = 8 KB
 
 #ifdef NPPC_REC_TRACE
 __device__ long long g_trace[4 * 12 * 16];
@@ -68,51 +44,117 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-// CL = cluster size: the CL CTAs of a cluster share ONE W_hh stream — slab s is fetched from L2 by CTA (s % CL) and
-// multicast into every CTA's ring.
-// Buffers are time-major with RS (multiple of 128) rows per step:  zx in the interleaved layout written by the GEMM
-// ([m_blk][chunk][warp-quad][half][piece][lane][8 bf16], m_blk = t*tiles + tile), hseq row-major [T'*RS][H].
-// FUSE_X (layer 0): the K=64 input projection is fused — x_t is a 7th A slab (TMA from the packed time-major input),
-// W_ih a 7th weight slab per chunk, and the epilogue adds the bias instead of streaming pre-activations from HBM.
-// FUSE_FC (last layer): y_{t-1} = W_fc h_{t-1} + b is a 13th, 16-column mini-chunk issued at the start of step t (h_{t-1} is the
-// A operand that was just reloaded), plus one pseudo-step after the last; its 128 x 16 fp32 result is read from TMEM cols 0..15.
-template <int CL, bool FUSE_X, bool FUSE_FC>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
+// =====================================================================================================================
+// CTA-pair persistent recurrent kernel.  Two CTAs (cluster of 2, ranks 0/1) own 2 x 128 sequences for all T' steps and
+// run ONE tcgen05.mma.cta_group::2 of M = 256 per K-step: each CTA supplies its own 128 rows of h_{t-1} (A, shared
+// memory, K-major SW128) and only HALF of the weight tile (64 of the chunk's 128 gate columns), so per SM the weight
+// stream through shared memory (TMA write + operand read) is halved.
+//   per step t, per chunk (32 hidden units = 128 gate columns, 12 chunks, walked in a per-pair rotated order):
+//     tensor core : acc[stage][256 x 128] = h_{t-1} * W_hh[chunk]^T  (+ x_t * W_ih[chunk]^T when the K=64 layer-0 input
+//                   projection is fused, + a 16-column fc mini-chunk per step for the last layer)
+//     epilogue    : 8 warps, thread = (row, 16-unit half).  The half's 64 accumulator columns are ordered
+//                   [4-unit block][gate][unit] so that one 16-column tcgen05.ld brings i,f,g,o of 4 units: the load of
+//                   block b+1 is in flight while block b goes through the MUFU (tanh) pipe — TMEM reads (64 B/clk/SM)
+//                   and the 5 tanh per unit are the two floors of this kernel and now overlap.
+//                   c lives in TMEM as packed fp16 pairs (192 columns; measured cost at the LSTM output 6.3e-4 ->
+//                   7.1e-4 max-rel vs fp32), which leaves room for the second accumulator stage.
+//   TMEM columns: [0,128) acc stage 0 | [128,256) acc stage 1 | [256,448) c (fp16x2) | [448,464) fc accumulator.
+//   mbarriers   : w_full / a_full / x_full / acc_empty / fc_empty live in the LEADER (both CTAs' producers and epilogues
+//                 arrive remotely, CTA-scope semantics: a cluster-scope release costs ~700 cycles per arrive);
+//                 w_empty / acc_full / fc_full / x_free are signalled in both CTAs by multicast tcgen05.commit.
+// Packed gate column (weights, bias, Zx):  chunk*128 + half*64 + blk*16 + gate*4 + uu  <->  nn.LSTM row
+//                 gate*H + chunk*32 + half*16 + blk*4 + uu.
+// Zx (layer >= 1 pre-activations, fp16) is read in the layout the GEMM epilogue writes:
+//   uint4 index ((((t*tiles + tile)*12 + chunk)*4 + warp-quad)*2 + half)*256 + piece*32 + lane, piece q = columns 8q..8q+7
+//   of the half -> block b = pieces 2b (i,f) and 2b+1 (g,o); every warp-wide load reads 512 contiguous bytes.
+template <bool FUSE_X>
+struct RecSmem {
+    static constexpr int WST_BYTES = 2 * 64 * 64 * 2;                    // ring stage: this CTA's half of TWO K slabs (16 KB)
+#ifdef NPPC_REC_TRACE
+    static constexpr int NST = FUSE_X ? 5 : 6;
+#else
+    static constexpr int NST = FUSE_X ? 6 : 7;
+#endif
+    static constexpr int A_OFF = 0;                                      // h_{t-1}: 6 slabs [128][64] fp16, SW128
+    static constexpr int W_OFF = NSLAB * SLAB_BYTES;
+    static constexpr int HST_OFF = W_OFF + NST * WST_BYTES;              // 2 x [128 rows][32 units] fp16 staging for the TMA store of h_t
+    static constexpr int X_OFF = HST_OFF + 2 * HST_BYTES;                // layer 0: x_t [128][64] fp16
+    static constexpr int BAR_OFF = X_OFF + (FUSE_X ? SLAB_BYTES : 0);
+#ifdef NPPC_REC_TRACE
+    static constexpr int TRACE_OFF = BAR_OFF + 512;
+    static constexpr int TOTAL = TRACE_OFF + 4 * 12 * 16 * 8 + 1024;
+#else
+    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+#endif
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    static constexpr int C_COL = 256, FC_COL = 448;
+};
+
+template <bool FUSE_X, bool FUSE_FC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const __grid_constant__ CUtensorMap tmap_hst, const __grid_constant__ CUtensorMap tmap_x,
                 const __grid_constant__ CUtensorMap tmap_wx, const __grid_constant__ CUtensorMap tmap_fc,
                 const uint4* __restrict__ zx, const float* __restrict__ bias, int RS, int Tp,
-                const float* __restrict__ fc_b, int O, int R, float* __restrict__ y) {
-    constexpr int NST = RecSmem::NST;
-    constexpr int NK = NSLAB + (FUSE_X ? 1 : 0);   // weight slabs per chunk
-    constexpr int FC_SLAB_BYTES = 16 * 64 * 2;     // [16 outputs][64 k] fp16
-    const int Tx = Tp + (FUSE_FC ? 1 : 0);         // steps incl. the fc-only pseudo-step
+                const float* __restrict__ fc_b, int O, int R, float* __restrict__ y, int dbg) {
+    using S = RecSmem<FUSE_X>;
+    constexpr int NST = S::NST;
+    constexpr int NP = NSLAB / 2;                  // slab pairs per chunk (one ring stage each)
+    constexpr int NK = NP + (FUSE_X ? 1 : 0);      // ring stages per chunk; with FUSE_X the x slab comes FIRST (k = 0)
+    constexpr int HALF_SLAB = 64 * 64 * 2;         // this CTA's [64 cols][64 k] half of one weight slab
+    constexpr int FC_HALF = 8 * 64 * 2;            // this CTA's 8 of the 16 fc rows, one K slab
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RecSmem::BAR_OFF);
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* w_empty = w_full + NST;
     uint64_t* a_full = w_empty + NST;      // [NSLAB]
-    uint64_t* acc_full = a_full + NSLAB;
-    uint64_t* acc_empty = acc_full + 1;
-    uint64_t* h_ready = acc_empty + 1;
-    uint64_t* x_full = h_ready + 1;
+    uint64_t* acc_full = a_full + NSLAB;   // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint64_t* fc_full = acc_empty + 2;
+    uint64_t* fc_empty = fc_full + 1;
+    uint64_t* h_stored = fc_empty + 1;     // [NSLAB] CTA-local: h_t slab is in global memory (both chunks, all 8 warps)
+    uint64_t* a_free = h_stored + NSLAB;   // every MMA of the step has completed: the A operand may be overwritten
+    uint64_t* staged = a_free + 1;         // [2] CTA-local: all 8 epilogue warps have written their h tile into staging buffer b
+    uint64_t* stage_free = staged + 2;     // [2] CTA-local: the TMA store has read staging buffer b
+    uint64_t* late_written = stage_free + 2;   // CTA-local: the late slab of the A operand has been written by all 8 warps
+    uint64_t* x_full = late_written + 1;
     uint64_t* x_free = x_full + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_free + 1);
 #ifdef NPPC_REC_TRACE
-    long long* trace_s = reinterpret_cast<long long*>(smem + RecSmem::TRACE_OFF);
+    long long* trace_s = reinterpret_cast<long long*>(smem + S::TRACE_OFF);
     for (int i = threadIdx.x; i < 4 * 12 * 16; i += NTHREADS) trace_s[i] = 0;
 #endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = RS / ROWS;
-    const int tile = blockIdx.x;          // CTAs beyond `tiles` (cluster padding) redo the last tile's loads, store nothing
+    const int tile = blockIdx.x;          // the odd CTA of the last pair may be padding: it redoes the last tile, stores nothing
     const bool live = tile < tiles;
     const int tile_c = live ? tile : tiles - 1;
     const int row0 = tile_c * ROWS;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    // Every pair walks the 12 chunks in its own rotated order (so the pairs, which run in lock-step, do not all fetch the
+    // same weight lines at the same moment) and consumes the K slabs in the order the previous step PRODUCED them: the slab
+    // finished last (positions 10, 11) is needed last, so the reload of h_t overlaps the tail of step t.
+    const int krot = (blockIdx.x >> 1) % NP;
+    const int rot = 4 * krot;
+    auto chunk_of = [&](int j) { int c = j + rot; return c >= NCHUNK ? c - NCHUNK : c; };
+    auto pair_of = [&](int k) { int c = k + krot; return c >= NP ? c - NP : c; };
+    // The slab produced LAST in a step (positions 10, 11) skips the global round trip: the epilogue writes it straight into
+    // the A operand (its region is free once the accumulator of position 11 has been seen) and arrives on a_full itself.
+    const int late_slab = chunk_of(NCHUNK - 1) >> 1;
 
-    // zero the A operand (h_{-1} = 0)
-    for (int i = threadIdx.x; i < NSLAB * SLAB_BYTES / 16; i += NTHREADS)
-        reinterpret_cast<uint4*>(smem + RecSmem::A_OFF)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NSLAB * SLAB_BYTES / 16; i += NTHREADS)   // h_{-1} = 0
+        reinterpret_cast<uint4*>(smem + S::A_OFF)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_w);
@@ -122,137 +164,205 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         if (FUSE_FC) tma_prefetch_desc(&tmap_fc);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
-        for (int i = 0; i < NSLAB; ++i) mbar_init(&a_full[i], 1);
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 256);
-        mbar_init(h_ready, 1);
-        mbar_init(x_full, 1);
+        for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 2); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < NSLAB; ++i) mbar_init(&a_full[i], 2);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+        mbar_init(fc_full, 1);
+        mbar_init(fc_empty, 8);
+        for (int i = 0; i < NSLAB; ++i) mbar_init(&h_stored[i], 2);
+        for (int i = 0; i < 2; ++i) { mbar_init(&staged[i], 8); mbar_init(&stage_free[i], 1); }
+        mbar_init(late_written, 8);
+        mbar_init(a_free, 1);
+        mbar_init(x_full, 2);
         mbar_init(x_free, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_ptr);
+    if (warp == 2) tmem_alloc_pair<512>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
+    cluster_sync_all();   // the peer's barriers are initialised and its TMEM allocated before any remote arrive / pair MMA
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
-    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
-        // ---- W_hh producer: 72 slabs per step, independent of t (runs ahead across step boundaries) ----
+        // ---- weight producer (both CTAs): this CTA's 64-column half of two K slabs per TMA, counted on the leader's barrier ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            uint32_t s = 0;
-            for (int t = 0; t < Tx; ++t) {
+            const uint32_t wf0 = mapa_u32(smem_u32(w_full), 0);
+            for (int t = 0; t < Tp + (FUSE_FC ? 1 : 0); ++t) {
                 if (FUSE_FC && t >= 1)
-                    for (int k = 0; k < NSLAB; ++k, ++s) {   // fc weights for y_{t-1}
+                    for (int k = 0; k < NP; ++k) {
                         mbar_wait(&w_empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&w_full[stage], FC_SLAB_BYTES);
-                        unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
-                        if (CL == 1) tma_load_2d(dst, &tmap_fc, &w_full[stage], k * 64, 0);
-                        else if (s % CL == crank) tma_load_2d_mcast(dst, &tmap_fc, &w_full[stage], k * 64, 0, CMASK);
+                        mbar_arrive_expect_tx_cluster(wf0 + stage * 8, 2 * FC_HALF);
+                        tma_load_3d_pair(smem + S::W_OFF + stage * S::WST_BYTES, &tmap_fc, wf0 + stage * 8, 0, (int)crank * 8,
+                                         pair_of(k) * 2);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 if (t >= Tp) break;
                 for (int j = 0; j < NCHUNK; ++j)
-                    for (int k = 0; k < NK; ++k, ++s) {
-                        mbar_wait(&w_empty[stage], phase ^ 1);   // every CTA of the cluster has released this slot
-                        mbar_arrive_expect_tx(&w_full[stage], SLAB_BYTES);
-                        unsigned char* dst = smem + RecSmem::W_OFF + stage * SLAB_BYTES;
-                        const CUtensorMap* tm = (FUSE_X && k == NSLAB) ? &tmap_wx : &tmap_w;
-                        const int kc = (FUSE_X && k == NSLAB) ? 0 : k * 64;
-                        if (CL == 1) tma_load_2d(dst, tm, &w_full[stage], kc, j * 128);
-                        else if (s % CL == crank) tma_load_2d_mcast(dst, tm, &w_full[stage], kc, j * 128, CMASK);
+                    for (int k = 0; k < NK; ++k) {
+                        mbar_wait(&w_empty[stage], phase ^ 1);
+                        if (k == 0) TRACE(9);
+                        if (k == NK - 1) TRACE(14);
+                        unsigned char* dst = smem + S::W_OFF + stage * S::WST_BYTES;
+                        const int wrow = chunk_of(j) * 128 + (int)crank * 64;
+                        if (dbg & 2) {
+                            mbar_arrive_cluster(wf0 + stage * 8);
+                        } else if (FUSE_X && k == 0) {
+                            mbar_arrive_expect_tx_cluster(wf0 + stage * 8, HALF_SLAB);
+                            tma_load_2d_pair(dst, &tmap_wx, wf0 + stage * 8, 0, wrow);
+                        } else {
+                            mbar_arrive_expect_tx_cluster(wf0 + stage * 8, 2 * HALF_SLAB);
+                            tma_load_3d_pair(dst, &tmap_w, wf0 + stage * 8, 0, wrow, pair_of(FUSE_X ? k - 1 : k) * 2);
+                        }
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
             }
         }
     } else if (warp == 3) {
-        // ---- A producer: reload h_t (TMA-stored by the epilogue) as the A operand of step t+1 ----
+        // ---- A producer (both CTAs): reload this CTA's h_t rows as the A operand of step t+1 ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (lane == 0) {
-            for (int k = 0; k < NSLAB; ++k) mbar_arrive(&a_full[k]);  // step 0: zeros already in place
+            const uint32_t af0 = mapa_u32(smem_u32(a_full), 0);
+            const uint32_t xf0 = mapa_u32(smem_u32(x_full), 0);
+            for (int k = 0; k < NSLAB; ++k) mbar_arrive_cluster(af0 + k * 8);  // step 0: zeros already in place
             if (FUSE_X) {
-                mbar_arrive_expect_tx(x_full, SLAB_BYTES);
-                tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, row0);
+                mbar_arrive_expect_tx_cluster(xf0, SLAB_BYTES);
+                tma_load_2d_pair(smem + S::X_OFF, &tmap_x, xf0, 0, row0);
             }
-            for (int t = 1; t < Tx; ++t) {
+            for (int t = 1; t < Tp + (FUSE_FC ? 1 : 0); ++t) {
                 if (FUSE_X && t < Tp) {   // x_t: needs only the previous step's x MMAs to be done (independent of h)
                     mbar_wait(x_free, (t - 1) & 1);
-                    mbar_arrive_expect_tx(x_full, SLAB_BYTES);
-                    tma_load_2d(smem + RecSmem::X_OFF, &tmap_x, x_full, 0, t * RS + row0);
+                    mbar_arrive_expect_tx_cluster(xf0, SLAB_BYTES);
+                    tma_load_2d_pair(smem + S::X_OFF, &tmap_x, xf0, 0, t * RS + row0);
                 }
-                mbar_wait(h_ready, (t - 1) & 1);
-                for (int k = 0; k < NSLAB; ++k) {
-                    mbar_arrive_expect_tx(&a_full[k], SLAB_BYTES);
-                    tma_load_2d(smem + RecSmem::A_OFF + k * SLAB_BYTES, &tmap_h, &a_full[k], k * 64, (t - 1) * RS + row0);
+                mbar_wait(a_free, (t - 1) & 1);
+                for (int kk = 0; kk < NSLAB; ++kk) {   // in the order the slabs were produced = the order they are consumed
+                    const int k = pair_of(kk >> 1) * 2 + (kk & 1);
+                    if (k == late_slab) continue;
+                    mbar_wait(&h_stored[k], (t - 1) & 1);
+                    if (dbg & 8) { mbar_arrive_cluster(af0 + k * 8); continue; }
+                    mbar_arrive_expect_tx_cluster(af0 + k * 8, SLAB_BYTES);
+                    tma_load_2d_pair(smem + S::A_OFF + k * SLAB_BYTES, &tmap_h, af0 + k * 8, k * 64, (t - 1) * RS + row0);
                 }
             }
         }
     } else if (warp == 2) {
+        // ---- store warp (both CTAs): everything slow about getting h_t out of the SM lives here, off the epilogue warps'
+        //      critical path: the generic->async proxy fence (a MEMBAR that in an epilogue warp would also wait for its
+        //      in-flight Zx loads), the TMA store of the staged [128 x 32] tile, its read / write completion, and the
+        //      hand-over of the late slab to the MMA issuer.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        if (lane == 0) {
+            const uint32_t al0 = mapa_u32(smem_u32(&a_full[late_slab]), 0);
+            unsigned char* hst = smem + S::HST_OFF;
+            for (int t = 0; t < Tp; ++t)
+                for (int j = 0; j < NCHUNK; ++j) {
+                    const uint32_t b = j & 1, use = (uint32_t)t * (NCHUNK / 2) + (j >> 1);
+                    if (j == NCHUNK - 1) {   // positions 10, 11 are in the A operand: publish them to the tensor core first
+                        mbar_wait(late_written, t & 1);
+                        fence_proxy_async_smem();
+                        mbar_arrive_cluster(al0);
+                    }
+                    mbar_wait(&staged[b], use & 1);
+                    fence_proxy_async_smem();
+                    if (live) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_hst),
+                                     "r"(smem_u32(hst + b * HST_BYTES)), "r"(chunk_of(j) * CH), "r"(t * RS + row0)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(&stage_free[b]);
+                    // completion of the PREVIOUS position's store (a chunk period old: never stalls long); async-proxy write
+                    // -> async-proxy read by the reload, so no proxy fence is needed
+                    if (j >= 1) {
+                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                        mbar_arrive(&h_stored[chunk_of(j - 1) >> 1]);
+                    }
+                    if (j == NCHUNK - 1) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        mbar_arrive(&h_stored[late_slab]);
+                    }
+                }
+        }
     } else if (warp == 1) {
-        // ---- MMA issuer: the whole warp runs the (warp-uniform) control flow so descriptors stay in uniform registers;
-        //      one elected lane issues tcgen05.mma / tcgen05.commit ----
+        // ---- MMA issuer (leader CTA only): the warp runs the warp-uniform control flow, one elected lane issues ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        {
-            constexpr uint32_t idesc = umma_idesc_f16(ROWS, 128);
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * ROWS, 128);
+            constexpr uint32_t idesc_fc = umma_idesc_f16(2 * ROWS, 16);
             int stage = 0; uint32_t phase = 0;
-            uint32_t it = 0;  // chunk counter for the acc_empty parity
-            const uint32_t a_base = smem_u32(smem + RecSmem::A_OFF);
-            const uint32_t w_base = smem_u32(smem + RecSmem::W_OFF);
-            const uint32_t x_base = smem_u32(smem + RecSmem::X_OFF);
-            for (int t = 0; t < Tx; ++t) {
-                if (FUSE_FC && t >= 1) {   // y_{t-1}: [128 x 16] = h_{t-1} * W_fc^T into TMEM cols 0..15
-                    constexpr uint32_t idesc_fc = umma_idesc_f16(ROWS, 16);
-                    mbar_wait(acc_empty, (it & 1) ^ 1);
+            const uint32_t a_base = smem_u32(smem + S::A_OFF);
+            const uint32_t w_base = smem_u32(smem + S::W_OFF);
+            const uint32_t x_base = smem_u32(smem + S::X_OFF);
+            for (int t = 0; t < Tp + (FUSE_FC ? 1 : 0); ++t) {
+                if (FUSE_FC && t >= 1) {   // y_{t-1}: [256 x 16] = h_{t-1} * W_fc^T into the fc accumulator columns
+                    mbar_wait(fc_empty, (t & 1));   // (t-1)-th use: parity ((t-1) & 1) ^ 1
                     tcgen05_fence_after();
-                    for (int k = 0; k < NSLAB; ++k) {
-                        mbar_wait(&a_full[k], t & 1);
+                    for (int k = 0; k < NP; ++k) {
+                        const int kp = pair_of(k);
+                        mbar_wait(&a_full[2 * kp], t & 1);
+                        mbar_wait(&a_full[2 * kp + 1], t & 1);
                         mbar_wait(&w_full[stage], phase);
                         tcgen05_fence_after();
-                        const uint64_t da = umma_desc_k128(a_base + k * SLAB_BYTES);
-                        const uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
                         if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc_fc, (k | kk) != 0);
-                            if (CL == 1) umma_commit(&w_empty[stage]);
-                            else umma_commit_mcast(&w_empty[stage], CMASK);
-                            if (k == NSLAB - 1) umma_commit(acc_full);
+                            for (int s2 = 0; s2 < 2; ++s2) {
+                                const uint64_t da = umma_desc_k128(a_base + (2 * kp + s2) * SLAB_BYTES);
+                                const uint64_t db = umma_desc_k128(w_base + stage * S::WST_BYTES + s2 * FC_HALF);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_f16_pair(tmem_base + S::FC_COL, da + 2 * kk, db + 2 * kk, idesc_fc, (k | s2 | kk) != 0);
+                            }
+                            umma_commit_pair(&w_empty[stage], 3);
+                            if (k == NP - 1) umma_commit_pair(fc_full, 3);
                         }
                         __syncwarp();
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
-                    ++it;
                 }
                 if (t >= Tp) break;
-                for (int j = 0; j < NCHUNK; ++j, ++it) {
-                    mbar_wait(acc_empty, (it & 1) ^ 1);
+                for (int j = 0; j < NCHUNK; ++j) {
+                    const uint32_t as = j & 1, use = (uint32_t)t * (NCHUNK / 2) + (j >> 1);
+                    mbar_wait(&acc_empty[as], (use & 1) ^ 1);
                     TRACE(0);
                     tcgen05_fence_after();
                     for (int k = 0; k < NK; ++k) {
-                        const bool is_x = FUSE_X && k == NSLAB;
+                        const bool is_x = FUSE_X && k == 0;
+                        const int kp = pair_of(FUSE_X ? k - 1 : k);
                         if (j == 0) {
                             if (is_x) mbar_wait(x_full, t & 1);
-                            else mbar_wait(&a_full[k], t & 1);
+                            else { mbar_wait(&a_full[2 * kp], t & 1); mbar_wait(&a_full[2 * kp + 1], t & 1); }
                         }
                         mbar_wait(&w_full[stage], phase);
                         if (k == 0) TRACE(1);
-                        if (k == 3) TRACE(2);
-                        if (k == 5) TRACE(3);
+                        if (k == NK - 1) TRACE(3);
                         tcgen05_fence_after();
-                        const uint64_t da = umma_desc_k128(is_x ? x_base : a_base + k * SLAB_BYTES);
-                        const uint64_t db = umma_desc_k128(w_base + stage * SLAB_BYTES);
                         if (elect_one()) {
+                            if (!(dbg & 4)) {
+                                if (is_x) {
+                                    const uint64_t da = umma_desc_k128(x_base);
+                                    const uint64_t db = umma_desc_k128(w_base + stage * S::WST_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
-                            if (CL == 1) umma_commit(&w_empty[stage]);
-                            else umma_commit_mcast(&w_empty[stage], CMASK);
-                            if (k == NK - 1) umma_commit(acc_full);
-                            if (is_x && j == NCHUNK - 1) umma_commit(x_free);   // x_t consumed by every chunk of this step
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_f16_pair(tmem_base + as * 128, da + 2 * kk, db + 2 * kk, idesc, kk != 0);
+                                } else {
+#pragma unroll
+                                    for (int s2 = 0; s2 < 2; ++s2) {
+                                        const uint64_t da = umma_desc_k128(a_base + (2 * kp + s2) * SLAB_BYTES);
+                                        const uint64_t db = umma_desc_k128(w_base + stage * S::WST_BYTES + s2 * HALF_SLAB);
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            umma_f16_pair(tmem_base + as * 128, da + 2 * kk, db + 2 * kk, idesc, (k | s2 | kk) != 0);
+                                    }
+                                }
+                            }
+                            umma_commit_pair(&w_empty[stage], 3);
+                            if (k == NK - 1) umma_commit_pair(&acc_full[as], 3);
+                            if (is_x && j == NCHUNK - 1) umma_commit_pair(x_free, 3);   // x_t consumed by every chunk of this step
+                            if (k == NK - 1 && j == NCHUNK - 1) umma_commit_pair(a_free, 3);
                         }
                         __syncwarp();
                         if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -262,140 +372,178 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ---- epilogue: thread = (row = 32*(warp%4) + lane, half = (warp-4)/4) ----
+        // ---- epilogue (both CTAs): thread = (row = 32*(warp%4) + lane, half = (warp-4)/4), software-pipelined over positions:
+        //      the four 16-column TMEM loads of position p+1 are issued BEFORE h of position p is staged / stored, there is
+        //      ONE tcgen05.wait::ld per position (after which the accumulator stage is released at once) and the Zx registers
+        //      are refilled in place for the next position as soon as a block has consumed them.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int ew = warp & 3, half = (warp - 4) >> 2;
         const int rloc = ew * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
-        const uint32_t t_acc = t_lane + half * 64;
-        unsigned char* hst = smem + RecSmem::HST_OFF;
-        // c_0 = 0
+        unsigned char* hst = smem + S::HST_OFF;
+        const uint32_t ae0 = mapa_u32(smem_u32(acc_empty), 0);
+        const uint32_t fe0 = mapa_u32(smem_u32(fc_empty), 0);
+        // this thread's 32 bytes of a late-slab row, position parity 0 / 1 (SW128: 16-byte chunk index ^ (row & 7))
+        unsigned char* late_row = smem + S::A_OFF + late_slab * SLAB_BYTES + rloc * 128;
+        const int lsw = rloc & 7;
         {
-            uint32_t z[16];
+            uint32_t z[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = 0u;
-            for (int j = 0; j < NCHUNK; ++j) tmem_st16(t_lane + 128 + j * CH + half * 16, z);
+            for (int i = 0; i < 8; ++i) z[i] = 0u;
+            for (int j = 0; j < NCHUNK; ++j) tmem_st8(t_lane + S::C_COL + j * 16 + half * 8, z);   // c_0 = 0
             tmem_wait_st();
         }
-        uint32_t it = 0;
-        // software-pipelined Zx stream: piece q of this thread's 64 pre-activations (i,f,g,o x 16 units, fp16) for chunk
-        // (t, j) is the uint4 at ((((t*tiles + tile)*12 + j)*4 + ew)*2 + half)*256 + q*32 + lane  (layout written by the
-        // GEMM epilogue) -> each warp-wide load reads 512 contiguous bytes.  Chunk it+1 is requested while it is computed.
-        auto zx_ptr = [&](int t, int j) -> const uint4* {
-            return zx + (((((size_t)t * tiles + tile_c) * NCHUNK + j) * 4 + ew) * 2 + half) * 256 + lane;
+        auto zx_ptr = [&](int t, int jc) -> const uint4* {
+            return zx + (((((size_t)t * tiles + tile_c) * NCHUNK + jc) * 4 + ew) * 2 + half) * 256 + lane;
         };
-        uint4 zraw[8];
-        if (!FUSE_X) {
-            const uint4* zp = zx_ptr(0, 0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
-        }
         const bool valid = live && (row0 + rloc) < R;
-        for (int t = 0; t < Tx; ++t) {
-            if (FUSE_FC && t >= 1) {   // fc mini-chunk: y[row][o][t-1] from TMEM cols 0..15 (half 0 threads own the rows)
-                mbar_wait(acc_full, it & 1);
-                tcgen05_fence_after();
-                uint32_t yv[16];
-                if (half == 0) {
-                    tmem_ld16(t_lane, yv);
-                    tmem_wait_ld();
-                }
-                tcgen05_fence_before();
-                mbar_arrive(acc_empty);
-                if (half == 0 && valid) {
-                    float* dst = y + (size_t)(row0 + rloc) * O * Tp + (t - 1);
+        // h_t of position j: this thread's 16 units -> the CTA's staging tile [128 rows][32 units]; the store warp does the rest
+        auto stage_out = [&](const uint32_t (&hv)[8], int t, int j) {
+            const uint32_t b = j & 1, use = (uint32_t)t * (NCHUNK / 2) + (j >> 1);
+            mbar_wait(&stage_free[b], (use & 1) ^ 1);
+            uint4* dst = reinterpret_cast<uint4*>(hst + b * HST_BYTES + rloc * (CH * 2) + half * 32);
+            dst[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            dst[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&staged[b]);
+        };
+        auto fc_out = [&](int t) {   // fc mini-chunk of step t-1: y[row][o][t-1]; the half-0 warps own the rows
+            mbar_wait(fc_full, (t - 1) & 1);
+            tcgen05_fence_after();
+            uint32_t yv[16];
+            tmem_ld16(t_lane + S::FC_COL, yv);
+            tmem_wait_ld16(yv);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(fe0);
+            if (valid) {
+                float* dst = y + (size_t)(row0 + rloc) * O * Tp + (t - 1);
 #pragma unroll
-                    for (int o = 0; o < 16; ++o)
-                        if (o < O) dst[(size_t)o * Tp] = __uint_as_float(yv[o]) + __ldg(fc_b + o);
-                }
-                ++it;
+                for (int o = 0; o < 16; ++o)
+                    if (o < O) dst[(size_t)o * Tp] = __uint_as_float(yv[o]) + __ldg(fc_b + o);
             }
-            if (t >= Tp) break;
+        };
+        uint32_t g0[16], g1[16], g2[16], g3[16], cp[8], hp[8], hkeep[8];
+        uint4 zq[8];
+        // issue the TMEM loads of position (t, j): 4 blocks of accumulators + the packed c of the chunk
+        auto issue_loads = [&](int t, int j) {
+            const uint32_t as = j & 1, use = (uint32_t)t * (NCHUNK / 2) + (j >> 1);
+            mbar_wait(&acc_full[as], use & 1);
+            if (threadIdx.x == 128) TRACE(5);
+            tcgen05_fence_after();
+            const uint32_t t_acc = t_lane + as * 128 + half * 64;
+            tmem_ld16(t_acc, g0);
+            tmem_ld16(t_acc + 16, g1);
+            tmem_ld16(t_acc + 32, g2);
+            tmem_ld16(t_acc + 48, g3);
+            tmem_ld8(t_lane + S::C_COL + chunk_of(j) * 16 + half * 8, cp);
+        };
+        if (!FUSE_X) {
+            const uint4* zp = zx_ptr(0, chunk_of(0));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) zq[q] = __ldg(zp + q * 32);
+        }
+        issue_loads(0, 0);
+        for (int t = 0; t < Tp; ++t) {
 #pragma unroll 1
-            for (int j = 0; j < NCHUNK; ++j, ++it) {
-                mbar_wait(acc_full, it & 1);
-                if (threadIdx.x == 128) TRACE(5);
-                if (threadIdx.x == 352) TRACE(10);
-                tcgen05_fence_after();
-                uint32_t gi[16], gf[16], gg[16], go[16], cc[16];
-                tmem_ld16(t_acc + 0, gi);
-                tmem_ld16(t_acc + 16, gf);
-                tmem_ld16(t_acc + 32, gg);
-                tmem_ld16(t_acc + 48, go);
-                tmem_ld16(t_lane + 128 + j * CH + half * 16, cc);
-                tmem_wait_ld();
+            for (int j = 0; j < NCHUNK; ++j) {
+                const uint32_t as = j & 1;
+                const int jc = chunk_of(j);   // the chunk (32 hidden units) this pair processes at position j
+                // single wait for the 5 loads of this position; naming every destination keeps their uses below it
+                asm volatile("tcgen05.wait::ld.sync.aligned;"
+                             : "+r"(g0[0]), "+r"(g0[1]), "+r"(g0[2]), "+r"(g0[3]), "+r"(g0[4]), "+r"(g0[5]), "+r"(g0[6]), "+r"(g0[7]),
+                               "+r"(g0[8]), "+r"(g0[9]), "+r"(g0[10]), "+r"(g0[11]), "+r"(g0[12]), "+r"(g0[13]), "+r"(g0[14]), "+r"(g0[15])
+                             :: "memory");
+                tmem_wait_ld16(g1);
+                tmem_wait_ld16(g2);
+                tmem_wait_ld16(g3);
+                asm volatile("" : "+r"(cp[0]), "+r"(cp[1]), "+r"(cp[2]), "+r"(cp[3]), "+r"(cp[4]), "+r"(cp[5]), "+r"(cp[6]), "+r"(cp[7]));
                 tcgen05_fence_before();
-                mbar_arrive(acc_empty);  // accumulator is in registers: the next chunk's MMAs may start
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ae0 + as * 8);   // the stage is in registers: its next MMAs may start
                 if (threadIdx.x == 128) TRACE(6);
-                if (threadIdx.x == 352) TRACE(11);
-                uint4 zcur[8];
-                if (!FUSE_X) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) zcur[q] = zraw[q];
-                    int jn = j + 1, tn = t;
-                    if (jn == NCHUNK) { jn = 0; tn = t + 1; }
-                    if (tn < Tp) {
-                        const uint4* zp = zx_ptr(tn, jn);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) zraw[q] = __ldg(zp + q * 32);
-                    }
-                }
-                const __half2* zh = reinterpret_cast<const __half2*>(zcur);  // zh[gate*8 + u/2] = fp16 pair (u, u+1)
-                const float* bj = bias + j * 128 + half * 64;                // fused: warp-uniform (broadcast) bias loads
-                float hv[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    float ai, af, ag, ao;
+                int jn = j + 1, tn = t;
+                if (jn == NCHUNK) { jn = 0; tn = t + 1; }
+                const uint4* zn = zx_ptr(tn < Tp ? tn : t, chunk_of(jn));   // Zx of the next position (clamped at the very end)
+                const float* bj = bias + jc * 128 + half * 64;              // fused: warp-uniform (broadcast) bias loads
+                // one 4-unit block: g[gate*4 + uu] accumulators, pre-activations / bias, c pairs cp[2b], cp[2b+1] -> hp[2b], hp[2b+1]
+                auto block = [&](const uint32_t (&g)[16], int b) {
+                    float pi[4], pf[4], pg[4], po[4];
                     if (FUSE_X) {
-                        ai = __ldg(bj + u); af = __ldg(bj + 16 + u); ag = __ldg(bj + 32 + u); ao = __ldg(bj + 48 + u);
+                        const float4 vi = __ldg(reinterpret_cast<const float4*>(bj + b * 16));
+                        const float4 vf = __ldg(reinterpret_cast<const float4*>(bj + b * 16 + 4));
+                        const float4 vg = __ldg(reinterpret_cast<const float4*>(bj + b * 16 + 8));
+                        const float4 vo = __ldg(reinterpret_cast<const float4*>(bj + b * 16 + 12));
+                        pi[0] = vi.x; pi[1] = vi.y; pi[2] = vi.z; pi[3] = vi.w;
+                        pf[0] = vf.x; pf[1] = vf.y; pf[2] = vf.z; pf[3] = vf.w;
+                        pg[0] = vg.x; pg[1] = vg.y; pg[2] = vg.z; pg[3] = vg.w;
+                        po[0] = vo.x; po[1] = vo.y; po[2] = vo.z; po[3] = vo.w;
                     } else {
-                        const float2 pi = __half22float2(zh[u >> 1]), pf = __half22float2(zh[8 + (u >> 1)]);
-                        const float2 pg = __half22float2(zh[16 + (u >> 1)]), po = __half22float2(zh[24 + (u >> 1)]);
-                        ai = (u & 1) ? pi.y : pi.x; af = (u & 1) ? pf.y : pf.x;
-                        ag = (u & 1) ? pg.y : pg.x; ao = (u & 1) ? po.y : po.x;
+                        const uint4 za = zq[2 * b], zb = zq[2 * b + 1];
+                        const float2 i01 = __half22float2(*reinterpret_cast<const __half2*>(&za.x));
+                        const float2 i23 = __half22float2(*reinterpret_cast<const __half2*>(&za.y));
+                        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&za.z));
+                        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&za.w));
+                        const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&zb.x));
+                        const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&zb.y));
+                        const float2 o01 = __half22float2(*reinterpret_cast<const __half2*>(&zb.z));
+                        const float2 o23 = __half22float2(*reinterpret_cast<const __half2*>(&zb.w));
+                        pi[0] = i01.x; pi[1] = i01.y; pi[2] = i23.x; pi[3] = i23.y;
+                        pf[0] = f01.x; pf[1] = f01.y; pf[2] = f23.x; pf[3] = f23.y;
+                        pg[0] = g01.x; pg[1] = g01.y; pg[2] = g23.x; pg[3] = g23.y;
+                        po[0] = o01.x; po[1] = o01.y; po[2] = o23.x; po[3] = o23.y;
+                        if (tn < Tp) {   // refill in place: consumed one chunk period from now
+                            zq[2 * b] = __ldg(zn + (2 * b) * 32);
+                            zq[2 * b + 1] = __ldg(zn + (2 * b + 1) * 32);
+                        }
                     }
-                    float zi = __uint_as_float(gi[u]) + ai;
-                    float zf = __uint_as_float(gf[u]) + af;
-                    float zg = __uint_as_float(gg[u]) + ag;
-                    float zo = __uint_as_float(go[u]) + ao;
-                    float c = sigmoid_fast(zf) * __uint_as_float(cc[u]) + sigmoid_fast(zi) * tanh_fast(zg);
-                    cc[u] = __float_as_uint(c);
-                    hv[u] = sigmoid_fast(zo) * tanh_fast(c);
-                }
-                tmem_st16(t_lane + 128 + j * CH + half * 16, cc);
-                if (threadIdx.x == 128) TRACE(7);
-                if (threadIdx.x == 352) TRACE(12);
-                // h_t chunk -> staging tile [128 rows][32 units] bf16 -> one TMA store per chunk (full-line writes)
-                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging buffer (j & 1) is free
-                {
-                    uint32_t hp[8];
+                    float cn[4], hn[4];
+                    const float2 c01 = __half22float2(*reinterpret_cast<const __half2*>(&cp[2 * b]));
+                    const float2 c23 = __half22float2(*reinterpret_cast<const __half2*>(&cp[2 * b + 1]));
+                    const float cprev[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        __half2 p = __floats2half2_rn(hv[2 * u], hv[2 * u + 1]);
-                        hp[u] = *reinterpret_cast<uint32_t*>(&p);
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const float zi = __uint_as_float(g[uu]) + pi[uu];
+                        const float zf = __uint_as_float(g[4 + uu]) + pf[uu];
+                        const float zg = __uint_as_float(g[8 + uu]) + pg[uu];
+                        const float zo = __uint_as_float(g[12 + uu]) + po[uu];
+                        cn[uu] = sigmoid_fast(zf) * cprev[uu] + sigmoid_fast(zi) * tanh_fast(zg);
+                        hn[uu] = sigmoid_fast(zo) * tanh_fast(cn[uu]);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(hst + (j & 1) * HST_BYTES + rloc * (CH * 2) + half * 32);
-                    dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                    dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                    __half2 q;
+                    q = __floats2half2_rn(cn[0], cn[1]); cp[2 * b] = *reinterpret_cast<uint32_t*>(&q);
+                    q = __floats2half2_rn(cn[2], cn[3]); cp[2 * b + 1] = *reinterpret_cast<uint32_t*>(&q);
+                    q = __floats2half2_rn(hn[0], hn[1]); hp[2 * b] = *reinterpret_cast<uint32_t*>(&q);
+                    q = __floats2half2_rn(hn[2], hn[3]); hp[2 * b + 1] = *reinterpret_cast<uint32_t*>(&q);
+                };
+                block(g0, 0);
+                block(g1, 1);
+                block(g2, 2);
+                block(g3, 3);
+                tmem_st8(t_lane + S::C_COL + jc * 16 + half * 8, cp);
+                if (threadIdx.x == 128) TRACE(7);
+                if (j == NCHUNK - 1) {
+                    // acc_full of position 11 was seen: no MMA of this step reads the A operand any more -> positions 10, 11
+                    // (the late slab) go straight into it (the store warp fences and publishes them)
+                    const int c0 = half * 2, c1 = 4 + half * 2;   // 16-byte chunk of positions 10 / 11 inside the slab row
+                    *reinterpret_cast<uint4*>(late_row + (((c0 + 0) ^ lsw) << 4)) = make_uint4(hkeep[0], hkeep[1], hkeep[2], hkeep[3]);
+                    *reinterpret_cast<uint4*>(late_row + (((c0 + 1) ^ lsw) << 4)) = make_uint4(hkeep[4], hkeep[5], hkeep[6], hkeep[7]);
+                    *reinterpret_cast<uint4*>(late_row + (((c1 + 0) ^ lsw) << 4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    *reinterpret_cast<uint4*>(late_row + (((c1 + 1) ^ lsw) << 4)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(late_written);
                 }
-                fence_proxy_async_smem();
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                if (threadIdx.x == 128 && live) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_hst),
-                                 "r"(smem_u32(hst + (j & 1) * HST_BYTES)), "r"(j * CH), "r"(t * RS + row0)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                stage_out(hp, t, j);
+                if (j == NCHUNK - 1) {
+                    tmem_wait_st();   // c of this step is in TMEM before any load of the next step
+                    if (FUSE_FC && half == 0) fc_out(t + 1);
+                    if (t + 1 < Tp) issue_loads(t + 1, 0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hkeep[i] = hp[i];
+                    issue_loads(t, j + 1);
                 }
                 if (threadIdx.x == 128) TRACE(8);
-                if (threadIdx.x == 352) TRACE(13);
-            }
-            // end of step: h_t fully written (async proxy) -> let the A producer reload it for step t+1
-            tmem_wait_st();
-            if (threadIdx.x == 128) {
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                fence_proxy_async_all();
-                mbar_arrive(h_ready);
             }
         }
     }
@@ -404,20 +552,24 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 #ifdef NPPC_REC_TRACE
     if (blockIdx.x == 0) for (int i = threadIdx.x; i < 4 * 12 * 16; i += NTHREADS) g_trace[i] = trace_s[i];
 #endif
-    if (CL > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
+    cluster_sync_all();  // neither CTA may exit while the pair's MMAs / multicast commits / remote arrives can still target it
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc_pair<512>(tmem_base);
     }
 }
 
 // fp32 [4H][K] (nn.LSTM row order) -> bf16 [4H][KP] with permuted rows, zero-padded K
+// packed gate column p = chunk*128 + half*64 + blk*16 + gate*4 + uu  ->  nn.LSTM row gate*H + chunk*32 + half*16 + blk*4 + uu
+__device__ __forceinline__ int packed_to_lstm_row(int p) {
+    const int chunk = p >> 7, half = (p >> 6) & 1, blk = (p >> 4) & 3, gate = (p >> 2) & 3, uu = p & 3;
+    return gate * H + chunk * CH + half * 16 + blk * 4 + uu;
+}
 __global__ void pack_w_kernel(const float* __restrict__ w, int K, int KP, __half* __restrict__ out) {
     long long n = (long long)H4 * KP;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int p = (int)(i / KP), k = (int)(i - (long long)p * KP);
-        int chunk = p >> 7, half = (p >> 6) & 1, gate = (p >> 4) & 3, u = p & 15;
-        int src = gate * H + chunk * CH + half * 16 + u;
+        int src = packed_to_lstm_row(p);
         out[i] = __float2half_rn(k < K ? fminf(fmaxf(w[(size_t)src * K + k], -65504.f), 65504.f) : 0.f);
     }
 }
@@ -427,10 +579,7 @@ __global__ void pack_fc_kernel(const float* __restrict__ w, int O, __half* __res
 }
 __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < H4) {
-        int chunk = p >> 7, half = (p >> 6) & 1, gate = (p >> 4) & 3, u = p & 15;
-        out[p] = b[gate * H + chunk * CH + half * 16 + u];
-    }
+    if (p < H4) out[p] = b[packed_to_lstm_row(p)];
 }
 
 // fc_output_layer over the h sequence of the last layer: y[row][o][t] = b[o] + sum_k W[o][k] * h[t][row][k]
@@ -534,49 +683,18 @@ struct FcArgs {
     float* y;
 };
 
-template <int CL, bool FUSE_X, bool FUSE_FC>
-int launch_rec_cl(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
-                  const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc,
-                  cudaStream_t s) {
-    auto kern = lstm_rec_kernel<CL, FUSE_X, FUSE_FC>;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem::TOTAL));
-    int tiles = RS / ROWS;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nppc::cdiv(tiles, CL) * CL));  // padded CTAs keep the cluster protocol, store nothing
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = RecSmem::TOTAL;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    NPPC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, th, thst, tx, twx, *fc.tfc, (const uint4*)zx, bias, RS, Tp, fc.fc_b, fc.O,
-                                    fc.R, fc.y));
-    NPPC_COUNT_LAUNCH(1);
-    return NPPC_OK;
-}
-
-int rec_cluster_size() {
-    static int cl = -1;
-    if (cl < 0) {
-        const char* e = getenv("NPPC_LSTM_CLUSTER");
-        cl = e ? atoi(e) : 2;
-        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
-    }
-    return cl;
-}
-
 template <bool FUSE_X, bool FUSE_FC>
 int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
                const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc, cudaStream_t s) {
-    switch (rec_cluster_size()) {
-        case 1: return launch_rec_cl<1, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
-        case 2: return launch_rec_cl<2, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
-        default: return launch_rec_cl<4, FUSE_X, FUSE_FC>(tw, th, thst, tx, twx, zx, bias, RS, Tp, fc, s);
-    }
+    auto kern = lstm_rec_kernel<FUSE_X, FUSE_FC>;
+    NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<FUSE_X>::TOTAL));
+    const int tiles = RS / ROWS;
+    static const int dbg = getenv("NPPC_LSTM_DBG") ? atoi(getenv("NPPC_LSTM_DBG")) : 0;   // timing ablations only (wrong results)
+    kern<<<nppc::cdiv(tiles, 2) * 2, NTHREADS, RecSmem<FUSE_X>::TOTAL, s>>>(tw, th, thst, tx, twx, *fc.tfc, (const uint4*)zx, bias,
+                                                                            RS, Tp, fc.fc_b, fc.O, fc.R, fc.y, dbg);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
 }
 
 }  // namespace
@@ -631,43 +749,41 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     __nv_bfloat16* zx = (__nv_bfloat16*)base;
     __nv_bfloat16* hseq = zx + rows * H4;
     const long long M = (long long)rows;
-    CUtensorMap tw[2], th, thst;
+    // weight boxes are this CTA's HALF of a tile (64 of a chunk's 128 gate columns, 8 of the 16 fc rows) x two K slabs
+    CUtensorMap tw[2], th, thst, tx, twx, tfc;
+    int rc;
     for (int l = 0; l < 2; ++l) {
-        int rc = tc::make_tmap_bf16_2d(&tw[l], p->wp_hh[l], H4, H, H * 2, 128, 64);
+        rc = tc::make_tmap_f16_kslabs(&tw[l], p->wp_hh[l], H4, H, 64, 2);
         if (rc) return rc;
     }
-    int rc = tc::make_tmap_bf16_2d(&th, hseq, (uint64_t)M, H, H * 2, ROWS, 64);
+    rc = tc::make_tmap_bf16_2d(&th, hseq, (uint64_t)M, H, H * 2, ROWS, 64);
     if (rc) return rc;
     rc = tc::make_tmap_bf16_2d(&thst, hseq, (uint64_t)M, H, H * 2, ROWS, CH, 0);
     if (rc) return rc;
-    // layer 0: input projection (K = 64) fused into the recurrent kernel unless NPPC_LSTM_FUSE_X=0
-    static const bool fuse_x = !(getenv("NPPC_LSTM_FUSE_X") && atoi(getenv("NPPC_LSTM_FUSE_X")) == 0);
-    CUtensorMap tx, twx;
     rc = tc::make_tmap_bf16_2d(&tx, xs, (uint64_t)M, (uint64_t)KP, (uint64_t)KP * 2, ROWS, 64);
     if (rc) return rc;
-    rc = tc::make_tmap_bf16_2d(&twx, p->wp_ih[0], H4, (uint64_t)KP, (uint64_t)KP * 2, 128, 64);
+    rc = tc::make_tmap_bf16_2d(&twx, p->wp_ih[0], H4, (uint64_t)KP, (uint64_t)KP * 2, 64, 64);
     if (rc) return rc;
+    rc = tc::make_tmap_f16_kslabs(&tfc, p->wp_fc, 16, H, 8, 2);
+    if (rc) return rc;
+    // layer 0: input projection (K = 64) fused into the recurrent kernel unless NPPC_LSTM_FUSE_X=0
+    static const bool fuse_x = !(getenv("NPPC_LSTM_FUSE_X") && atoi(getenv("NPPC_LSTM_FUSE_X")) == 0);
     static const bool fuse_fc = !(getenv("NPPC_LSTM_FUSE_FC") && atoi(getenv("NPPC_LSTM_FUSE_FC")) == 0);
-    CUtensorMap tfc;
-    rc = tc::make_tmap_bf16_2d(&tfc, p->wp_fc, 16, H, H * 2, 16, 64);
-    if (rc) return rc;
-    const FcArgs no_fc{&tfc, nullptr, 0, R, nullptr};
+    const bool fc_in_rec = fuse_fc && p->O <= 16;   // fc fused into the last layer's recurrent kernel (mini-chunk per step)
+    const FcArgs fc{&tfc, p->fc_b, p->O, R, y};
     if (fuse_x && KP == 64) {
-        rc = launch_rec<true, false>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, no_fc, s);
+        rc = launch_rec<true, false>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, fc, s);
     } else {
         rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
         if (rc) return rc;
-        rc = launch_rec<false, false>(tw[0], th, thst, tx, twx, zx, nullptr, RS, Tp, no_fc, s);
+        rc = launch_rec<false, false>(tw[0], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
     }
     if (rc) return rc;
     // layer 1 (+ fc)
     rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
     if (rc) return rc;
-    if (fuse_fc && p->O <= 16) {   // fc fused into the last layer's recurrent kernel (13th mini-chunk per step)
-        const FcArgs fc{&tfc, p->fc_b, p->O, R, y};
-        return launch_rec<false, true>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
-    }
-    rc = launch_rec<false, false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, no_fc, s);
+    if (fc_in_rec) return launch_rec<false, true>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
+    rc = launch_rec<false, false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
     if (rc) return rc;
     switch ((p->O + 3) / 4) {
         case 1: return launch_fc<1>((const __half*)hseq, R, RS, Tp, p->fc_w, p->fc_b, p->O, y, s);

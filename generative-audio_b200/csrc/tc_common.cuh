@@ -176,9 +176,84 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------------
+// Two CTAs of a cluster (ranks 2p, 2p+1) run ONE tcgen05.mma of M = 256: each CTA contributes its own 128 A rows and
+// HALF of the B tile (N/2 columns), so the per-SM shared-memory operand traffic of B is halved.  The leader (even rank)
+// issues the MMAs; producers of both CTAs signal the LEADER's mbarriers (shared::cluster addresses from mapa).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (.release at CTA scope): a cluster-scope release costs ~700 cycles per arrive (measured, tools/micro)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+// 2D tiled load into THIS CTA's shared memory whose completion bytes are counted on an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {  // one full warp, same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 columns per CTA]^T ; issued by ONE thread of the leader
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the CTA-relative mbarrier of every CTA in cta_mask once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 // ---- host: TMA descriptor for a row-major bf16 matrix [rows][cols], box [box_rows][64 cols] with 128B swizzle ---
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                       uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
+
+// row-major fp16 matrix [rows][cols] (cols % 64 == 0) viewed as [cols/64 K slabs][rows][64]: box = [n_slabs][box_rows][64],
+// 128B swizzle -> n_slabs consecutive K-major SW128 operand tiles in shared memory from ONE TMA (coords: 0, row, first slab)
+int make_tmap_f16_kslabs(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t n_slabs);
 
 }  // namespace tc
 }  // namespace nppc

@@ -39,5 +39,26 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
     return NPPC_OK;
 }
 
+int make_tmap_f16_kslabs(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t n_slabs) {
+    auto enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return NPPC_ERR_CUDA;
+    }
+    cuuint64_t gdim[3] = {64, rows, cols / 64};
+    cuuint64_t gstride[2] = {cols * 2, 128};
+    cuuint32_t box[3] = {64, box_rows, n_slabs};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed (%d) rows=%llu cols=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+                  (unsigned long long)cols, box_rows, n_slabs);
+        return NPPC_ERR_CUDA;
+    }
+    return NPPC_OK;
+}
+
 }  // namespace tc
 }  // namespace nppc

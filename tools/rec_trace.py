@@ -18,9 +18,9 @@ lp = "sb_model.sequence_model."
 plan = g.ops.LstmPlan(*[p[lp + f"{k}_l{l}"].cuda() for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")],
                       p["sb_model.fc_output_layer.weight"].cuda(), p["sb_model.fc_output_layer.bias"].cuda())
 R, Tp = B * 257, 40
-RS = g.ops.padded_rows(R, torch.bfloat16)
+RS = g.ops.padded_rows(R, torch.float16)
 torch.manual_seed(0)
-xs = torch.randn(Tp, RS, 64, device="cuda").to(torch.bfloat16)
+xs = torch.randn(Tp, RS, 64, device="cuda").to(torch.float16); xs[:, :, 34:] = 0
 y = plan.forward(xs, 1, R)
 torch.cuda.synchronize()
 lib = g._lib.load()
@@ -29,8 +29,8 @@ lib.nppc_debug_rec_trace.argtypes = [C.c_void_p]
 assert lib.nppc_debug_rec_trace(buf) == 0
 a = np.array(buf, dtype=np.int64).reshape(4, 12, 16)
 t0 = a[0, 0, 0]
-print("MMA: 0 acc_empty ok | 1 w_full[0] ok | 2 w_full[3] ok | 3 w_full[5] ok | 4 commit issued || epi warp4: 5 acc_full seen | 6 arrived acc_empty | 7 math+STTM done | 8 h staged+TMA issued || epi warp11: 10..13 same")
+print("MMA: 0 acc_empty ok | 1 w_full[0] ok | 2 w_full[3] ok | 3 w_full[last] ok | 4 commit issued || epi warp4: 5 acc_full seen | 6 arrived acc_empty | 7 math+STTM done | 8 h staged+TMA issued || W producer: 9 w_empty ok (k=0) | 14 w_empty ok (k=last) || 12 staged prev | 10 token | 11 math done | warp8: 13 token | 15 math done")
 for t in range(3):
     for j in range(12):
         r = a[t, j] - t0
-        print(f"t={t+5} j={j:2d} " + " ".join(f"{int(v):7d}" if a[t, j, i] != 0 else "      -" for i, v in enumerate(r[:14])))
+        print(f"t={t+5} j={j:2d} " + " ".join(f"{int(v):7d}" if a[t, j, i] != 0 else "      -" for i, v in enumerate(r[:16])))
