@@ -3,7 +3,7 @@
 Drop-in surface of the reference's `nppc_audio` package for this path: NPPCModel, AudioPCWrapper,
 MultiDirectionFullSubNet_Plus, FullSubNet_Plus, gram_schmidt_to_crm and their pydantic configs.
 Import as `generative_audio_b200` (alias package at the repo root; a hyphen cannot be imported directly)."""
-from . import _lib, modules, ops, sharding, training  # noqa: F401
+from . import _lib, inpainting, modules, ops, sharding, training  # noqa: F401
 from .config import (AudioPCWrapperConfig, FullSubNetPlusConfig, MultiDirectionConfig, NPPCModelConfig,  # noqa: F401
                      StftConfig)
 from .fullsubnet_plus import FullSubNet_Plus  # noqa: F401

@@ -32,10 +32,15 @@ PROTOTYPES = {
     "nppc_gram_schmidt_real": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
     "nppc_gs_loss_fused": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "nppc_projection_loss": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "nppc_gs_loss_fused_real": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "nppc_projection_loss_real": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "nppc_logmag_stats": (_i, [_p, _i, _ll, _p, _p]),
+    "nppc_logmag_apply": (_i, [_p, _i, _ll, _p, _ll, _p, _p]),
+    "nppc_mask_blend": (_i, [_p, _i, _p, _p, _i, _i, _ll, _p, _p]),
     "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_tsse": (_i, [_p, _i, _i, _i, C.POINTER(_i), C.POINTER(_p), C.POINTER(_p)] + [_p] * 6 + [_i, _p, _p, _p]),
-    "nppc_prelu_stats": (_i, [_p, _i, _ll, _p, _p, _p]),
-    "nppc_tcn_mid": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "nppc_prelu_stats": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_tcn_mid": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "nppc_tcn_out": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "nppc_lstm_plan_create": (_i, [C.POINTER(_p), _i, _i, _i] + [_p] * 10 + [_p]),
     "nppc_lstm_plan_destroy": (None, [_p]),

@@ -155,15 +155,20 @@ __global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n_rt
             v[i][k] = gk;
         }
         if (has_err) {
-            // trainer.py:270-295
+            // complex: trainer.py:270-295 (nu/(eps+1e-8), W/(nu+1e-8));  real: inpainting nppc_trainer.py:354-373
+            // (1e-6 is added to BOTH norms before any division, and the logged err_norm includes it)
             double eps_n = sqrt(fmax(G(n, n).x, 0.0));
             cd pr{0.0, 0.0};
             for (int k = 0; k <= i; ++k) { cd t = cmul(cconj(a[k]), G(k, n)); pr.x += t.x; pr.y += t.y; }
-            double den = (nrm + 1e-8) * (eps_n + 1e-8);
+            const double den = COMPLEX ? (nrm + 1e-8) * (eps_n + 1e-8) : (nrm + 1e-6) * (eps_n + 1e-6);
             pr.x /= den; pr.y /= den;
-            err_proj[((size_t)b * n + i) * 2] = (float)pr.x;
-            err_proj[((size_t)b * n + i) * 2 + 1] = (float)pr.y;
-            double wn = nrm / (eps_n + 1e-8);
+            if (COMPLEX) {
+                err_proj[((size_t)b * n + i) * 2] = (float)pr.x;
+                err_proj[((size_t)b * n + i) * 2 + 1] = (float)pr.y;
+            } else {
+                err_proj[(size_t)b * n + i] = (float)pr.x;
+            }
+            double wn = COMPLEX ? nrm / (eps_n + 1e-8) : (nrm + 1e-6) / (eps_n + 1e-6);
             w_norms[(size_t)b * n + i] = (float)wn;
             double pm2 = pr.x * pr.x + pr.y * pr.y;
             double d = wn * wn - pm2;
@@ -175,9 +180,8 @@ __global__ void gs_solve_kernel(SampleScratch* __restrict__ scr, int B, int n_rt
         double acc = 0.0;
         for (int i = 0; i < n; ++i) acc += nu[i];
         reconst_err[b] = (float)(1.0 - acc);
-        err_norm[b] = (float)sqrt(fmax(G(n, n).x, 0.0));
+        err_norm[b] = (float)(sqrt(fmax(G(n, n).x, 0.0)) + (COMPLEX ? 0.0 : 1e-6));
     }
-    (void)COMPLEX;
 }
 
 // out_i[p] = sum_{k<=i} A[i][k] x_k[p]. grid (chunks, B)
@@ -341,4 +345,25 @@ extern "C" int nppc_projection_loss(const float* x, const float* gt, const float
                    "nppc_projection_loss: null pointer");
     return run<true>(x, gt, pred, B, n, P, scratch, 0, nullptr, err_norm, err_proj, w_norms, reconst_err, second_moment_mse,
                      (cudaStream_t)stream);
+}
+
+// Real (inpainting) variants: x [B,n,P], gt / pred [B,P]; err_proj is [B,n] real.
+extern "C" int nppc_gs_loss_fused_real(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                                       void* scratch, float* w_mat, float* err_norm, float* err_proj, float* w_norms,
+                                       float* reconst_err, float* second_moment_mse, void* stream) {
+    GS_ARGS_OK("nppc_gs_loss_fused_real");
+    NPPC_CHECK_ARG(gt && pred && w_mat && err_norm && err_proj && w_norms && reconst_err && second_moment_mse,
+                   "nppc_gs_loss_fused_real: null pointer");
+    return run<false>(x, gt, pred, B, n, P, scratch, 1, w_mat, err_norm, err_proj, w_norms, reconst_err, second_moment_mse,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int nppc_projection_loss_real(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                                         void* scratch, float* err_norm, float* err_proj, float* w_norms,
+                                         float* reconst_err, float* second_moment_mse, void* stream) {
+    GS_ARGS_OK("nppc_projection_loss_real");
+    NPPC_CHECK_ARG(gt && pred && err_norm && err_proj && w_norms && reconst_err && second_moment_mse,
+                   "nppc_projection_loss_real: null pointer");
+    return run<false>(x, gt, pred, B, n, P, scratch, 0, nullptr, err_norm, err_proj, w_norms, reconst_err, second_moment_mse,
+                      (cudaStream_t)stream);
 }

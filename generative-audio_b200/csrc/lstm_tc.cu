@@ -13,6 +13,7 @@
 namespace nppc {
 int gemm_16bit_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, int f16,
                   cudaStream_t s);
+int gemm_zx_pair(const void* A, const void* W, const float* bias, void* zx, long long M, cudaStream_t s);
 }
 
 namespace {
@@ -780,7 +781,9 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     }
     if (rc) return rc;
     // layer 1 (+ fc)
-    rc = gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
+    static const bool zx_pair = !(getenv("NPPC_GEMM_ZX") && atoi(getenv("NPPC_GEMM_ZX")) == 0);   // 0 = single-CTA GEMM
+    rc = zx_pair ? gemm_zx_pair(hseq, p->wp_ih[1], p->bias_p[1], zx, M, s)
+                 : gemm_16bit_tn(hseq, p->wp_ih[1], p->bias_p[1], zx, M, H4, H, 2, s);
     if (rc) return rc;
     if (fc_in_rec) return launch_rec<false, true>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);
     rc = launch_rec<false, false>(tw[1], th, thst, tx, twx, zx, nullptr, RS, Tp, fc, s);

@@ -5,7 +5,7 @@
 // TCNBlock (causal_conv.py:96-108):  y1 = conv1x1(x);  h = GroupNorm1(PReLU1(y1));  z = PReLU2(depthwise(h));
 //                                    x' = x + sconv(GroupNorm2(z))
 // GroupNorm(1, C) needs per-SAMPLE statistics over all C*T' elements, so the block is cut at the two reductions:
-//   prelu_stats : one read of y1            -> stats1[b] = (sum, sum of squares) of PReLU1(y1)          (fp64 atomics)
+//   prelu_stats : one read of y1            -> stats1[b] = (sum, sum of squares) of PReLU1(y1 + b1)     (fp64 atomics)
 //   tcn_mid     : one read of y1, one write -> z = PReLU2(dw_b + sum_j k_j * norm1(PReLU1(y1))[t+(j-1)d]), stats2[b] of z
 //   (library)   : o = conv1x1(z; W2 * diag(gamma2))            (GroupNorm2's affine folded into the weights)
 //   tcn_out     : x' = x + o * rstd2[b] + (W2 beta2 + b2)[c] - mean2[b] * rstd2[b] * (W2 gamma2)[c]
@@ -16,28 +16,27 @@ constexpr int TPB = 256;
 
 __device__ __forceinline__ float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
 
-__global__ void __launch_bounds__(TPB) prelu_stats_kernel(const float* __restrict__ y, long long n,
+// grid (blocks per sample, B): each warp owns whole channel rows (coalesced along T'); y + bias[c] is the conv1x1 output
+// (the bias of the 1x1 convolution is folded in here and in tcn_mid, so the library GEMM runs without a bias pass).
+__global__ void __launch_bounds__(TPB) prelu_stats_kernel(const float* __restrict__ y, int C, int T, const float* __restrict__ bias,
                                                          const float* __restrict__ a_ptr, double* __restrict__ stats) {
     __shared__ double red[32];
     const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float a = *a_ptr;
-    const float4* yb = reinterpret_cast<const float4*>(y + (size_t)b * n);
-    const long long n4 = n >> 2;
-    float s = 0.f, ss = 0.f;
     double ds = 0.0, dss = 0.0;
-    int cnt = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 v = yb[i];
-        float p0 = prelu(v.x, a), p1 = prelu(v.y, a), p2 = prelu(v.z, a), p3 = prelu(v.w, a);
-        s += (p0 + p1) + (p2 + p3);
-        ss += (p0 * p0 + p1 * p1) + (p2 * p2 + p3 * p3);
-        if (++cnt == 16) { ds += s; dss += ss; s = ss = 0.f; cnt = 0; }
+    for (int c = blockIdx.x * nw + warp; c < C; c += gridDim.x * nw) {
+        const float bc = bias ? bias[c] : 0.f;
+        const float* row = y + ((size_t)b * C + c) * T;
+        float s = 0.f, ss = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            const float p = prelu(row[t] + bc, a);
+            s += p;
+            ss += p * p;
+        }
+        ds += (double)s;
+        dss += (double)ss;
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail (n not a multiple of 4)
-        float p = prelu(y[(size_t)b * n + (n4 << 2) + threadIdx.x], a);
-        s += p; ss += p * p;
-    }
-    ds += s; dss += ss;
     ds = nppc::block_sum(ds, red);
     dss = nppc::block_sum(dss, red);
     if (threadIdx.x == 0) {
@@ -48,7 +47,8 @@ __global__ void __launch_bounds__(TPB) prelu_stats_kernel(const float* __restric
 
 // grid (blocks per sample, B), 8 warps per block: each warp owns whole channel rows (coalesced along T', the 3 taps hit
 // L1), moments are accumulated per thread in fp32 over one row, per block in fp64, ONE atomic pair per block.
-__global__ void __launch_bounds__(TPB) tcn_mid_kernel(const float* __restrict__ y1, int C, int T, const float* __restrict__ a1_ptr,
+__global__ void __launch_bounds__(TPB) tcn_mid_kernel(const float* __restrict__ y1, int C, int T, const float* __restrict__ bias1,
+                                                     const float* __restrict__ a1_ptr,
                                                      const double* __restrict__ stats1, const float* __restrict__ g1,
                                                      const float* __restrict__ b1, const float* __restrict__ dw_w,
                                                      const float* __restrict__ dw_b, int dil, const float* __restrict__ a2_ptr,
@@ -65,15 +65,16 @@ __global__ void __launch_bounds__(TPB) tcn_mid_kernel(const float* __restrict__ 
     for (int c = blockIdx.x * nw + warp; c < C; c += gridDim.x * nw) {
         const float sc = rstd * g1[c], sh = b1[c] - mu * rstd * g1[c];   // norm1(v) = v * sc + sh
         const float k0 = dw_w[c * 3], k1 = dw_w[c * 3 + 1], k2 = dw_w[c * 3 + 2], kb = dw_b[c];
+        const float bc = bias1 ? bias1[c] : 0.f;
         const float* row = y1 + ((size_t)b * C + c) * T;
         float* zrow = z + ((size_t)b * C + c) * T;
         float s = 0.f, ss = 0.f;
         for (int t = lane; t < T; t += 32) {
             float acc = kb;
             int tm = t - dil, tp = t + dil;
-            if (tm >= 0) acc += k0 * (prelu(row[tm], a1) * sc + sh);   // zero padding applies to the NORMALISED signal
-            acc += k1 * (prelu(row[t], a1) * sc + sh);
-            if (tp < T) acc += k2 * (prelu(row[tp], a1) * sc + sh);
+            if (tm >= 0) acc += k0 * (prelu(row[tm] + bc, a1) * sc + sh);   // zero padding applies to the NORMALISED signal
+            acc += k1 * (prelu(row[t] + bc, a1) * sc + sh);
+            if (tp < T) acc += k2 * (prelu(row[tp] + bc, a1) * sc + sh);
             float out = prelu(acc, a2);
             zrow[t] = out;
             s += out;
@@ -191,21 +192,21 @@ int blocks_for(long long n, int mult) {
 }
 }  // namespace
 
-extern "C" int nppc_prelu_stats(const float* y, int B, long long n, const float* prelu_a, double* stats, void* stream) {
-    NPPC_CHECK_ARG(y && prelu_a && stats && B > 0 && n > 0, "nppc_prelu_stats: bad arguments");
-    NPPC_CHECK_ARG(((uintptr_t)y % 16 == 0) && (n % 4 == 0 || B == 1), "nppc_prelu_stats: rows must be 16-byte aligned");
+extern "C" int nppc_prelu_stats(const float* y, int B, int C, int T, const float* bias, const float* prelu_a, double* stats,
+                                void* stream) {
+    NPPC_CHECK_ARG(y && prelu_a && stats && B > 0 && C > 0 && T > 0 && B <= 65535, "nppc_prelu_stats: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     NPPC_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B, s));
     int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
-    int gx = blocks_for(n / 4, 8);
+    int gx = nppc::cdiv(C, TPB / 32);
     if (gx > per) gx = per < 1 ? 1 : per;
-    prelu_stats_kernel<<<dim3(gx, B), TPB, 0, s>>>(y, n, prelu_a, stats);
+    prelu_stats_kernel<<<dim3(gx, B), TPB, 0, s>>>(y, C, T, bias, prelu_a, stats);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
 }
 
-extern "C" int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* prelu1_a, const double* stats1,
+extern "C" int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* bias1, const float* prelu1_a, const double* stats1,
                             const float* gamma1, const float* beta1, const float* dw_w, const float* dw_b, int dilation,
                             const float* prelu2_a, float* z, double* stats2, void* stream) {
     NPPC_CHECK_ARG(y1 && prelu1_a && stats1 && gamma1 && beta1 && dw_w && dw_b && prelu2_a && z && stats2, "nppc_tcn_mid: null pointer");
@@ -216,7 +217,7 @@ extern "C" int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* p
         int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
         int gx = nppc::cdiv(C, TPB / 32);
         if (gx > per) gx = per < 1 ? 1 : per;
-        tcn_mid_kernel<<<dim3(gx, B), TPB, 0, s>>>(y1, C, T, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation,
+        tcn_mid_kernel<<<dim3(gx, B), TPB, 0, s>>>(y1, C, T, bias1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation,
                                                    prelu2_a, z, stats2);
     }
     NPPC_COUNT_LAUNCH(1);

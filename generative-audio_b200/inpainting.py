@@ -1,0 +1,255 @@
+"""a16 — the NPPC audio *inpainting* variant (masked-gap restoration) behind the reference's call surface:
+
+    UNetConfig / UNet                    nppc_audio/inpainting/networks/unet.py:117-290 (+ tmp_utils.py:8-101)
+    RestorationWrapper                   nppc_audio/inpainting/networks/unet.py:293-313
+    AudioInpaintingPCWrapper(Config)     nppc_audio/inpainting/nppc/pc_wrapper.py:61-88
+    NPPCModel(Config) (inpainting)       nppc_audio/inpainting/nppc/nppc_model.py:22-159
+    preprocess_data                      utils.py:294-306
+    InpaintingNPPCStep.base_step         nppc_audio/inpainting/trainer/nppc_trainer.py:338-385 (forward statistics)
+
+Same module tree / state_dict keys as the reference (`inc.conv.conv.0.weight`, `down1.mpconv.1.conv.4.running_var`, ...),
+so reference checkpoints (`{"model_state_dict": ...}`) load with strict=True.  CUDA only, inference (eval-mode BatchNorm,
+dropout off).  The 3x3 convolutions run on the library (cuDNN) — SURVEY.md §8f row N4 — with BatchNorm folded into their
+weights; everything around them is hand-written: log-magnitude normalisation, mask blending, the real Gram-Schmidt and
+the projection / second-moment loss (two HBM passes, csrc/gram_schmidt.cu)."""
+from pathlib import Path
+from typing import Literal, Optional
+
+import pydantic
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class UNetConfig(pydantic.BaseModel):
+    in_channels: int = 1
+    out_channels: int = 1
+    dropout: float = 0.0
+
+
+def _double_conv(in_ch, out_ch, dropout=0.0):
+    """(conv3x3 -> BN -> LeakyReLU(0.2)) x 2 [-> Dropout]; index positions match tmp_utils.double_conv's Sequential."""
+    layers = [nn.Conv2d(in_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.LeakyReLU(0.2),
+              nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.LeakyReLU(0.2)]
+    if dropout:
+        layers.append(nn.Dropout(dropout))
+    return nn.Sequential(*layers)
+
+
+class _DoubleConv(nn.Module):
+    def __init__(self, in_ch, out_ch, dropout=0.0):
+        super().__init__()
+        self.conv = _double_conv(in_ch, out_ch, dropout)
+        self._fold = None
+        self._fold_key = None
+
+    def _folded(self):
+        """Eval-mode BatchNorm folded into the preceding conv: w' = w * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(..) + beta.
+        Derived cache keyed on the parameter versions; never serialised."""
+        ps = [p for m in (self.conv[0], self.conv[1], self.conv[3], self.conv[4]) for p in list(m.parameters()) + list(m.buffers())]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._fold is None or key != self._fold_key:
+            out = []
+            with torch.no_grad():
+                for ci, bi in ((0, 1), (3, 4)):
+                    conv, bn = self.conv[ci], self.conv[bi]
+                    sc = (bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps))
+                    w = (conv.weight.double() * sc[:, None, None, None]).float().contiguous()
+                    b = ((conv.bias.double() - bn.running_mean.double()) * sc + bn.bias.double()).float().contiguous()
+                    out.append((w, b))
+            self._fold, self._fold_key = out, key
+        return self._fold
+
+    def forward(self, x):
+        (w0, b0), (w1, b1) = self._folded()
+        x = F.leaky_relu(F.conv2d(x, w0, b0, padding=1), 0.2, inplace=True)
+        return F.leaky_relu(F.conv2d(x, w1, b1, padding=1), 0.2, inplace=True)
+
+
+class _InConv(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv = _DoubleConv(in_ch, out_ch)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class _Down(nn.Module):
+    def __init__(self, in_ch, out_ch, dropout=0.0):
+        super().__init__()
+        self.mpconv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(in_ch, out_ch, dropout))
+
+    def forward(self, x):
+        return self.mpconv(x)
+
+
+class _Up(nn.Module):
+    """bilinear x2 (align_corners=True) -> zero-pad to the skip's size -> cat([skip, up]) -> double conv (tmp_utils.py:59-88)."""
+
+    def __init__(self, in_ch, out_ch, dropout=0.0):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = _DoubleConv(in_ch, out_ch, dropout)
+
+    def forward(self, x1, x2):
+        x1 = self.up(x1)
+        dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return self.conv(torch.cat([x2, x1], dim=1))
+
+
+class _OutConv(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv = nn.Conv2d(in_ch, out_ch, 1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class UNet(nn.Module):
+    """unet.py:247-290: 64-128-256-512-512 encoder, bilinear decoder, 1x1 output conv."""
+
+    def __init__(self, config: UNetConfig):
+        super().__init__()
+        self.config = config
+        d = config.dropout
+        self.inc = _InConv(config.in_channels, 64)
+        self.down1 = _Down(64, 128)
+        self.down2 = _Down(128, 256)
+        self.down3 = _Down(256, 512, d)
+        self.down4 = _Down(512, 512, d)
+        self.up1 = _Up(1024, 256, d)
+        self.up2 = _Up(512, 128, d)
+        self.up3 = _Up(256, 64)
+        self.up4 = _Up(128, 64)
+        self.outc = _OutConv(64, config.out_channels)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("generative_audio_b200.inpainting.UNet: CUDA tensors only (no CPU fallback)")
+        if self.training:
+            raise RuntimeError("inference only: call .eval() (BatchNorm is folded into the convolutions, dropout is off)")
+        x1 = self.inc(x)
+        x2 = self.down1(x1)
+        x3 = self.down2(x2)
+        x4 = self.down3(x3)
+        x5 = self.down4(x4)
+        x = self.up1(x5, x4)
+        x = self.up2(x, x3)
+        x = self.up3(x, x2)
+        x = self.up4(x, x1)
+        return self.outc(x)
+
+
+class RestorationWrapper(nn.Module):
+    """unet.py:293-313: keep the known bins, take the network's output inside the gap."""
+
+    def __init__(self, base_net: UNet):
+        super().__init__()
+        self.net = base_net
+
+    def forward(self, x_in: torch.Tensor, mask: torch.Tensor):
+        return ops.mask_blend(x_in, self.net(x_in), mask)
+
+
+def gram_schmidt_to_spec_mag(x: torch.Tensor) -> torch.Tensor:
+    """inpainting/nppc/pc_wrapper.py:43-59: real MGS over [B, n_dirs, F*T]; un-normalised directions are returned."""
+    return ops.gram_schmidt_real(x)
+
+
+class AudioInpaintingPCWrapperConfig(pydantic.BaseModel):
+    model_configuration: UNetConfig
+    n_dirs: int
+
+
+class AudioInpaintingPCWrapper(nn.Module):
+    """pc_wrapper.py:61-88: UNet(2 -> n_dirs) -> * (1 - mask) -> real Gram-Schmidt.  (The reference's two debug
+    `.cpu().numpy()` host syncs at :83,86 are not reproduced.)"""
+
+    def __init__(self, pc_wrapper_config: AudioInpaintingPCWrapperConfig):
+        super().__init__()
+        self.config = pc_wrapper_config
+        self.net = UNet(self.config.model_configuration)
+
+    def head(self, mag_spec: torch.Tensor, mask: torch.Tensor):
+        return ops.mask_blend(None, self.net(mag_spec), mask)
+
+    def forward(self, mag_spec: torch.Tensor, mask: torch.Tensor):
+        return gram_schmidt_to_spec_mag(self.head(mag_spec, mask))
+
+
+class NPPCModelConfig(pydantic.BaseModel):
+    pretrained_restoration_model_configuration: UNetConfig
+    pretrained_restoration_model_path: Optional[str] = None
+    audio_pc_wrapper_configuration: AudioInpaintingPCWrapperConfig
+    device: Literal["cpu", "cuda"] = "cuda"
+
+
+class NPPCModel(nn.Module):
+    """nppc_model.py:31-159 (local-checkpoint path; the wandb artifact loader is out of scope)."""
+
+    def __init__(self, config: NPPCModelConfig):
+        super().__init__()
+        if config.device != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("generative_audio_b200.inpainting.NPPCModel runs on CUDA (sm_100a) only: no CPU fallback")
+        self.config = config
+        self.device = torch.device("cuda")
+        if not config.pretrained_restoration_model_path:
+            raise ValueError("pretrained_restoration_model_path must be provided")
+        checkpoint = torch.load(Path(config.pretrained_restoration_model_path).absolute(), map_location=self.device)
+        base_net = UNet(config.pretrained_restoration_model_configuration)
+        base_net.load_state_dict(checkpoint["model_state_dict"])
+        base_net.to(self.device)
+        self.pretrained_restoration_model = RestorationWrapper(base_net)
+        self.pretrained_restoration_model.eval()
+        self.pc_wrapper = AudioInpaintingPCWrapper(config.audio_pc_wrapper_configuration)
+        self.pc_wrapper.to(self.device)
+        self.eval()
+
+    def get_pred_spec_mag_norm(self, masked_spec_mag_log, mask):
+        with torch.no_grad():
+            return self.pretrained_restoration_model(masked_spec_mag_log, mask)
+
+    def forward(self, masked_spec_mag_norm: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """masked_spec_mag_norm, mask [B,1,F,T] -> w_mat [B,n_dirs,F,T] (nppc_model.py:119-145)."""
+        pred = self.get_pred_spec_mag_norm(masked_spec_mag_norm, mask)
+        with torch.no_grad():
+            return self.pc_wrapper(torch.cat((masked_spec_mag_norm, pred), dim=1), mask)
+
+
+def preprocess_data(clean_spec: torch.Tensor, masked_spec: torch.Tensor, mask: torch.Tensor):
+    """utils.py:294-306: spec [B,2,F,T] (re, im), mask [B,T] -> (clean_log_norm, mask [B,1,F,T], masked_log_norm)."""
+    clean, masked, _, _ = ops.logmag_normalize(clean_spec, masked_spec)
+    m = mask.unsqueeze(1).unsqueeze(2).expand(-1, 1, clean_spec.shape[2], -1).contiguous()
+    return clean, m, masked
+
+
+def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
+    return max(min(-1.0 + 2.0 * step / grace, 1.0), 1e-6) * lambda0
+
+
+class InpaintingNPPCStep:
+    """Forward statistics of the inpainting NPPC trainer's base_step (nppc_trainer.py:338-385): one restoration pass is
+    shared by the PC head and the error (the reference runs it twice), Gram-Schmidt and the loss statistics are fused."""
+
+    def __init__(self, nppc_model: NPPCModel, second_moment_loss_lambda: float = 1.0, second_moment_loss_grace: float = 500.0):
+        self.nppc_model = nppc_model
+        self.lambda0, self.grace = second_moment_loss_lambda, second_moment_loss_grace
+        self.step = 0
+
+    @torch.no_grad()
+    def base_step(self, batch):
+        masked_spec, mask, clean_spec = batch
+        clean, m, masked = preprocess_data(clean_spec.cuda(), masked_spec.cuda(), mask.cuda())
+        pred = self.nppc_model.get_pred_spec_mag_norm(masked, m)
+        head = self.nppc_model.pc_wrapper.head(torch.cat((masked, pred), dim=1), m)
+        w_mat, st = ops.gs_loss_fused_real(head, clean, pred)
+        lam = second_moment_lambda(self.step, self.grace, self.lambda0)
+        objective = st["reconst_err"].mean() + lam * st["second_moment_mse"].mean()
+        log = dict(w_mat=w_mat, err_norm=st["err_norm"], err_proj=st["err_proj"], w_norms=st["w_norms"],
+                   reconst_err=st["reconst_err"], second_moment_mse=st["second_moment_mse"], objective=objective)
+        return st["reconst_err"], objective, log

@@ -76,10 +76,11 @@ class TCNBlock(nn.Module):
         """x [B,C,T'] -> x + sconv(norm2(prelu2(dwconv(norm1(prelu1(conv1x1(x)))))))  (causal_conv.py:96-108).
         1x1 convolutions: library GEMM; everything between them: 3 fused kernels (prelu_stats, tcn_mid, tcn_out)."""
         x = x.contiguous()
-        y1 = F.conv1d(x, self.conv1x1.weight, self.conv1x1.bias)
-        stats1 = ops.prelu_stats(y1, self.prelu1.weight)
+        y1 = F.conv1d(x, self.conv1x1.weight)   # bias folded into the two kernels that read y1
+        stats1 = ops.prelu_stats(y1, self.prelu1.weight, self.conv1x1.bias)
         z, stats2 = ops.tcn_mid(y1, self.prelu1.weight, stats1, self.norm1.weight, self.norm1.bias,
-                                self.depthwise_conv.weight, self.depthwise_conv.bias, self.dilation, self.prelu2.weight)
+                                self.depthwise_conv.weight, self.depthwise_conv.bias, self.dilation, self.prelu2.weight,
+                                self.conv1x1.bias)
         w2f, u, vb = self._folded()
         o = F.conv1d(z, w2f)
         return ops.tcn_out(o, x, z.shape[1], stats2, u, vb)

@@ -227,6 +227,83 @@ def projection_loss(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
                 second_moment_mse=sm)
 
 
+def _loss_outputs_real(B, n, device):
+    f = dict(device=device, dtype=torch.float32)
+    return (torch.empty(B, **f), torch.empty(B, n, **f), torch.empty(B, n, **f), torch.empty(B, **f), torch.empty(B, n, **f))
+
+
+def gs_loss_fused_real(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """Real Gram-Schmidt + the inpainting trainer's loss statistics (nppc_trainer.py:338-385). head [B,n,F,T]; gt/pred [B,1,F,T]."""
+    head, gt, pred = _f32(head), _f32(gt), _f32(pred)
+    _chk(head, gt, pred)
+    B, n = head.shape[:2]
+    P = head[0, 0].numel()
+    assert gt.shape == pred.shape and gt[0].numel() == P
+    w = torch.empty_like(head)
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs_real(B, n, head.device)
+    scr = _gs_scratch(B, n, head.device)
+    _lib.check(_lib.load().nppc_gs_loss_fused_real(head.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, scr.data_ptr(),
+                                                   w.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(),
+                                                   w_norms.data_ptr(), reconst.data_ptr(), sm.data_ptr(), _stream()),
+               "nppc_gs_loss_fused_real")
+    return w, dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm)
+
+
+def projection_loss_real(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """Loss statistics of the inpainting NPPC trainer's base_step for an explicit w_mat [B,n,F,T]."""
+    w_mat, gt, pred = _f32(w_mat), _f32(gt), _f32(pred)
+    _chk(w_mat, gt, pred)
+    B, n = w_mat.shape[:2]
+    P = w_mat[0, 0].numel()
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs_real(B, n, w_mat.device)
+    scr = _gs_scratch(B, n, w_mat.device)
+    _lib.check(_lib.load().nppc_projection_loss_real(w_mat.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P,
+                                                     scr.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(),
+                                                     w_norms.data_ptr(), reconst.data_ptr(), sm.data_ptr(), _stream()),
+               "nppc_projection_loss_real")
+    return dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm)
+
+
+def logmag_normalize(clean_spec: torch.Tensor, masked_spec: torch.Tensor):
+    """utils.preprocess_data (utils.py:294-306) without the mask expansion: spec [B,2,F,T] (re, im) ->
+    (clean_log_norm [B,1,F,T], masked_log_norm [B,1,F,T], mean, std) with ONE global mean / unbiased std of the clean batch."""
+    clean_spec, masked_spec = _f32(clean_spec), _f32(masked_spec)
+    _chk(clean_spec, masked_spec)
+    B, two, Fq, T = clean_spec.shape
+    assert two == 2 and masked_spec.shape == clean_spec.shape
+    P = Fq * T
+    lib = _lib.load()
+    sums = torch.empty(2, device=clean_spec.device, dtype=torch.float64)
+    _lib.check(lib.nppc_logmag_stats(clean_spec.data_ptr(), B, P, sums.data_ptr(), _stream()), "nppc_logmag_stats")
+    outs = []
+    for sp in (clean_spec, masked_spec):
+        o = torch.empty(B, 1, Fq, T, device=sp.device, dtype=torch.float32)
+        _lib.check(lib.nppc_logmag_apply(sp.data_ptr(), B, P, sums.data_ptr(), B * P, o.data_ptr(), _stream()), "nppc_logmag_apply")
+        outs.append(o)
+    n = float(B * P)
+    mean = sums[0] / n
+    std = torch.sqrt((sums[1] - n * mean * mean) / (n - 1.0))
+    return outs[0], outs[1], mean.float(), std.float()
+
+
+def mask_blend(x_in, x: torch.Tensor, mask: torch.Tensor):
+    """x_in[:, :1] * mask + x * (1 - mask)  (RestorationWrapper.forward, unet.py:298-313); x_in=None -> x * (1 - mask).
+    x [B,C,F,T], mask [B,1,F,T] (or anything with B*F*T elements), x_in [B,Cin,F,T]."""
+    x, mask = _f32(x), _f32(mask)
+    _chk(x, mask)
+    B, Cc = x.shape[:2]
+    P = x[0, 0].numel()
+    assert mask.numel() == B * P, "mask must be [B,1,F,T]"
+    out = torch.empty_like(x)
+    if x_in is not None:
+        x_in = _f32(x_in)
+        _chk(x_in)
+        assert x_in.shape[0] == B and x_in[0, 0].numel() == P
+    _lib.check(_lib.load().nppc_mask_blend(x_in.data_ptr() if x_in is not None else None, x_in.shape[1] if x_in is not None else 0,
+                                           x.data_ptr(), mask.data_ptr(), B, Cc, P, out.data_ptr(), _stream()), "nppc_mask_blend")
+    return out
+
+
 TC_ROW_TILE = 128  # the tensor-core LSTM owns 128 sequences per CTA; its time-major buffers pad rows to this
 
 
@@ -309,23 +386,24 @@ def tsse(x: torch.Tensor, kersize, conv_w, conv_b, fcat_w, fcat_b, fc1_w, fc1_b,
     return y
 
 
-def prelu_stats(y: torch.Tensor, prelu_a: torch.Tensor):
-    """[B,2] fp64 (sum, sum of squares) of PReLU(y) per sample."""
+def prelu_stats(y: torch.Tensor, prelu_a: torch.Tensor, bias: torch.Tensor = None):
+    """[B,2] fp64 (sum, sum of squares) of PReLU(y + bias[c]) per sample, y [B,C,T]."""
     _chk(y, prelu_a)
-    B = y.shape[0]
+    B, Cc, T = y.shape
     stats = torch.empty(B, 2, device=y.device, dtype=torch.float64)
-    _lib.check(_lib.load().nppc_prelu_stats(y.data_ptr(), B, y.numel() // B, prelu_a.data_ptr(), stats.data_ptr(), _stream()),
-               "nppc_prelu_stats")
+    _lib.check(_lib.load().nppc_prelu_stats(y.data_ptr(), B, Cc, T, bias.data_ptr() if bias is not None else None,
+                                            prelu_a.data_ptr(), stats.data_ptr(), _stream()), "nppc_prelu_stats")
     return stats
 
 
-def tcn_mid(y1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation: int, prelu2_a):
-    """z = PReLU2(depthwise(GroupNorm1(PReLU1(y1)))) and the per-sample moments of z (causal_conv.py:100-104)."""
+def tcn_mid(y1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation: int, prelu2_a, bias1=None):
+    """z = PReLU2(depthwise(GroupNorm1(PReLU1(y1 + bias1)))) and the per-sample moments of z (causal_conv.py:100-104)."""
     _chk(y1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, prelu2_a)
     B, Cc, T = y1.shape
     z = torch.empty_like(y1)
     stats2 = torch.empty(B, 2, device=y1.device, dtype=torch.float64)
-    _lib.check(_lib.load().nppc_tcn_mid(y1.data_ptr(), B, Cc, T, prelu1_a.data_ptr(), stats1.data_ptr(), gamma1.data_ptr(),
+    _lib.check(_lib.load().nppc_tcn_mid(y1.data_ptr(), B, Cc, T, bias1.data_ptr() if bias1 is not None else None,
+                                        prelu1_a.data_ptr(), stats1.data_ptr(), gamma1.data_ptr(),
                                         beta1.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), dilation, prelu2_a.data_ptr(),
                                         z.data_ptr(), stats2.data_ptr(), _stream()), "nppc_tcn_mid")
     return z, stats2

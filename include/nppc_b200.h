@@ -100,6 +100,27 @@ int nppc_projection_loss(const float* w_mat, const float* gt, const float* pred,
                          void* scratch, float* err_norm, float* err_proj, float* w_norms, float* reconst_err,
                          float* second_moment_mse, void* stream);
 
+/* Real (inpainting) variants (nppc_audio/inpainting/trainer/nppc_trainer.py:338-385, 1e-6 added to both norms before the
+ * divisions): x / w_mat [B,n,P], gt / pred [B,P]; err_proj [B,n] real, err_norm includes the 1e-6. */
+int nppc_gs_loss_fused_real(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                            void* scratch, float* w_mat, float* err_norm, float* err_proj, float* w_norms,
+                            float* reconst_err, float* second_moment_mse, void* stream);
+int nppc_projection_loss_real(const float* w_mat, const float* gt, const float* pred, int B, int n, long long P,
+                              void* scratch, float* err_norm, float* err_proj, float* w_norms, float* reconst_err,
+                              float* second_moment_mse, void* stream);
+
+/* ---- a16: inpainting variant glue ---------------------------------------------------------------
+ * utils.preprocess_data / preprocess_log_magnitude (utils.py:281-306): spec [B,2,P] (re, im) -> log(|S| + 1e-6);
+ * nppc_logmag_stats accumulates (sum, sum of squares) over the whole batch tensor into sums[2] (fp64);
+ * nppc_logmag_apply writes (log|S| - mean) / std with the UNBIASED std over n_stat elements (torch.std default).
+ * nppc_mask_blend: RestorationWrapper.forward (nppc_audio/inpainting/networks/unet.py:298-313)
+ *   out[b,c,p] = x_in[b,0,p] * mask[b,p] + x[b,c,p] * (1 - mask[b,p]);  x_in == NULL gives x * (1 - mask)
+ *   (AudioInpaintingPCWrapper.forward, nppc_audio/inpainting/nppc/pc_wrapper.py:75-81). */
+int nppc_logmag_stats(const float* spec, int B, long long P, double* sums, void* stream);
+int nppc_logmag_apply(const float* spec, int B, long long P, const double* sums, long long n_stat, float* out, void* stream);
+int nppc_mask_blend(const float* x_in, int Cin, const float* x, const float* mask, int B, int C, long long P, float* out,
+                    void* stream);
+
 /* ---- a5+a2 fused for the sub-band LSTM: feature packing ------------------------------------------
  * Builds the sub-band model input of fullsubnet_plus.py:203-223 / networks.py:133-151 without materialising
  * the [B,F,34,T'] tensor: unfold(nbr_src, N) ++ fb ++ fbr ++ fbi, offline_laplace_norm over (F,S,T') per
@@ -122,12 +143,13 @@ int nppc_tsse(const float* x, int B, int C, int T, const int* kersize, const flo
 
 /* ---- a4: TCN block, normalisation / depthwise half (causal_conv.py:96-108) ------------------------------
  * stats buffers are [B,2] fp64 (sum, sum of squares) on the device; prelu_* point to the 1-element PReLU weight.
- * nppc_prelu_stats: stats = moments of PReLU(y) per sample, y [B,n].
+ * nppc_prelu_stats: stats = moments of PReLU(y + bias[c]) per sample, y [B,C,T] (bias = the 1x1 convolution's, or NULL).
  * nppc_tcn_mid:     z = PReLU2(depthwise_dilated(GroupNorm1(PReLU1(y1)))) [B,C,T] and stats2 = moments of z.
  * nppc_tcn_out:     xnew = x + o*rstd2[b] + vb[c] - mean2[b]*rstd2[b]*u[c], where o = conv1x1(z; W2*diag(gamma2)),
  *                   u = W2 gamma2, vb = W2 beta2 + b2  (GroupNorm2 folded into the second 1x1 convolution). */
-int nppc_prelu_stats(const float* y, int B, long long n, const float* prelu_a, double* stats, void* stream);
-int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* prelu1_a, const double* stats1, const float* gamma1,
+int nppc_prelu_stats(const float* y, int B, int C, int T, const float* bias /* [C] or NULL: added to y first */, const float* prelu_a,
+                     double* stats, void* stream);
+int nppc_tcn_mid(const float* y1, int B, int C, int T, const float* bias1 /* [C] or NULL */, const float* prelu1_a, const double* stats1, const float* gamma1,
                  const float* beta1, const float* dw_w, const float* dw_b, int dilation, const float* prelu2_a, float* z,
                  double* stats2, void* stream);
 int nppc_tcn_out(const float* o, const float* x, int B, int C, int T, int C_hidden, const double* stats2, const float* u,

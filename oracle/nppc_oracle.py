@@ -429,3 +429,86 @@ def base_step(p: Params, noisy, clean, *, n_dirs, head_groups, step, grace, lamb
     out = nppc_loss(w_mat, gt, pred, step=step, grace=grace, lambda0=lambda0)
     out.update(w_mat=w_mat, pred_crm=pred, gt_crm=gt)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# a16  inpainting variant (CPU restatement; parity pinned by tests/golden/inpaint_*.npz, generated
+#      from the unmodified reference by oracle/make_golden_inpainting.py)
+# --------------------------------------------------------------------------------------------
+def _bn_eval(x, p: Params, pre: str, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (running statistics)."""
+    sc = p[f"{pre}.weight"] / torch.sqrt(p[f"{pre}.running_var"] + eps)
+    return (x - p[f"{pre}.running_mean"][None, :, None, None]) * sc[None, :, None, None] + p[f"{pre}.bias"][None, :, None, None]
+
+
+def _double_conv(x, p: Params, pre: str):
+    """tmp_utils.py:8-35: (conv3x3 pad 1 -> BN -> LeakyReLU(0.2)) x 2 (dropout is identity in eval)."""
+    for ci, bi in ((0, 1), (3, 4)):
+        x = F.conv2d(x, p[f"{pre}.{ci}.weight"], p[f"{pre}.{ci}.bias"], padding=1)
+        x = F.leaky_relu(_bn_eval(x, p, f"{pre}.{bi}"), 0.2)
+    return x
+
+
+def unet_forward(p: Params, x: torch.Tensor) -> torch.Tensor:
+    """nppc_audio/inpainting/networks/unet.py:279-290 (+ tmp_utils.py:38-101)."""
+    def down(x, name):
+        return _double_conv(F.max_pool2d(x, 2), p, f"{name}.mpconv.1.conv")
+
+    def up(x1, x2, name):
+        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return _double_conv(torch.cat([x2, x1], dim=1), p, f"{name}.conv.conv")
+
+    x1 = _double_conv(x, p, "inc.conv.conv")
+    x2 = down(x1, "down1")
+    x3 = down(x2, "down2")
+    x4 = down(x3, "down3")
+    x5 = down(x4, "down4")
+    y = up(x5, x4, "up1")
+    y = up(y, x3, "up2")
+    y = up(y, x2, "up3")
+    y = up(y, x1, "up4")
+    return F.conv2d(y, p["outc.conv.weight"], p["outc.conv.bias"])
+
+
+def inpaint_restore(p_rest: Params, x_in, mask):
+    """RestorationWrapper.forward, unet.py:298-313 (single-channel x_in)."""
+    return x_in * mask + unet_forward(p_rest, x_in) * (1 - mask)
+
+
+def inpaint_forward(p_rest: Params, p_head: Params, masked, mask, taps: Optional[dict] = None):
+    """inpainting NPPCModel.forward (nppc_model.py:119-145) + AudioInpaintingPCWrapper.forward (pc_wrapper.py:75-88)."""
+    pred = inpaint_restore(p_rest, masked, mask)
+    head = unet_forward(p_head, torch.cat((masked, pred), dim=1)) * (1 - mask)
+    if taps is not None:
+        taps.update(pred=pred, head=head)
+    return gram_schmidt_real(head)
+
+
+def inpaint_preprocess(clean_spec, masked_spec, mask):
+    """utils.preprocess_data, utils.py:294-306 (global scalar mean / unbiased std of the clean log-magnitude)."""
+    m = mask[:, None, None, :].expand(-1, 1, clean_spec.shape[2], -1)
+    cmag = torch.sqrt(clean_spec[:, 0] ** 2 + clean_spec[:, 1] ** 2)[:, None]
+    mmag = torch.sqrt(masked_spec[:, 0] ** 2 + masked_spec[:, 1] ** 2)[:, None]
+    lc = torch.log(cmag + 1e-6)
+    mean, std = lc.mean(), lc.std()
+    return (lc - mean) / std, m, (torch.log(mmag + 1e-6) - mean) / std
+
+
+def inpaint_loss(w_mat, clean, pred, *, step: int, grace: float, lambda0: float):
+    """inpainting base_step statistics, nppc_trainer.py:347-373."""
+    w = w_mat.flatten(2)
+    w_norms = w.norm(dim=2) + 1e-6
+    w_hat = w / w_norms[:, :, None]
+    err = (clean - pred).flatten(1)
+    err_norm = err.norm(dim=1) + 1e-6
+    err = err / err_norm[:, None]
+    w_norms = w_norms / err_norm[:, None]
+    err_proj = torch.einsum("bki,bi->bk", w_hat, err)
+    reconst_err = 1 - err_proj.pow(2).sum(dim=1)
+    second_moment_mse = (w_norms.pow(2) - err_proj.pow(2)).pow(2)
+    lam = second_moment_lambda(step, grace, lambda0)
+    objective = reconst_err.mean() + lam * second_moment_mse.mean()
+    return dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst_err,
+                second_moment_mse=second_moment_mse, objective=objective)

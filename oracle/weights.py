@@ -54,3 +54,28 @@ def synth_state_dict(n_dirs: int = 5, seed: int = 0, prefix: str = ""):
         if name.startswith(prefix):
             sd[name[len(prefix):]] = synth_tensor(name, shape, seed)
     return sd
+
+
+# ---- inpainting variant (a16): UNet tensors by name; scales keep 18 conv layers of activations O(1) ----------------
+def synth_unet_tensor(name: str, shape, seed: int) -> torch.Tensor:
+    rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
+    leaf = name.split(".")[-1]
+    shape = tuple(shape)
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.int64)
+    if leaf == "running_mean":
+        return torch.from_numpy(rng.uniform(-0.1, 0.1, size=shape).astype(np.float32))
+    if leaf == "running_var":
+        return torch.from_numpy((1.0 + rng.uniform(-0.2, 0.2, size=shape)).astype(np.float32))
+    if len(shape) == 1 and leaf == "weight":   # BatchNorm gamma
+        return torch.from_numpy((1.0 + rng.uniform(-0.1, 0.1, size=shape)).astype(np.float32))
+    if leaf == "bias":
+        return torch.from_numpy(rng.uniform(-0.05, 0.05, size=shape).astype(np.float32))
+    fan_in = int(np.prod(shape[1:]))
+    bound = float(np.sqrt(6.0 / (1.04 * fan_in)))   # kaiming-uniform for LeakyReLU(0.2)
+    return torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
+
+
+def synth_unet_state_dict(shapes, seed: int = 0, tag: str = ""):
+    """shapes: iterable of (name, shape) (e.g. from module.state_dict()); `tag` separates the two UNets of the model."""
+    return {name: synth_unet_tensor(tag + name, shape, seed) for name, shape in shapes}

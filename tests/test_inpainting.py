@@ -1,0 +1,118 @@
+"""a16 — the inpainting variant.  CPU: the oracle restatement is pinned against outputs of the UNMODIFIED reference
+(tests/golden/inpaint_model_b2.npz, made by oracle/make_golden_inpainting.py) and the product UNet keeps the
+reference's state_dict keys.  GPU: product (C-ABI kernels + library convolutions) vs golden and oracle."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+import nppc_oracle as O
+import weights
+from conftest import GOLD, load_golden, rel_err
+
+torch.set_grad_enabled(False)
+N_DIRS = 3
+
+
+def _shapes(m):
+    return [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+
+
+def _params(in_ch, out_ch, tag):
+    import generative_audio_b200 as g
+    net = g.inpainting.UNet(g.inpainting.UNetConfig(in_channels=in_ch, out_channels=out_ch))
+    return net, weights.synth_unet_state_dict(_shapes(net), 0, tag)
+
+
+def test_unet_state_dict_keys_match_reference():
+    net, _ = _params(1, 1, "rest.")
+    with open(os.path.join(GOLD, "unet_manifest.json")) as f:
+        ref = [(k, tuple(s)) for k, s in json.load(f)["entries"]]
+    assert _shapes(net) == ref
+
+
+def test_oracle_inpainting_vs_golden():
+    g = load_golden("inpaint_model_b2")
+    _, p_rest = _params(1, 1, "rest.")
+    _, p_head = _params(2, N_DIRS, "head.")
+    clean_n, m4, masked_n = O.inpaint_preprocess(g["clean_spec"], g["masked_spec"], g["mask"])
+    assert rel_err(clean_n, g["clean_n"]) < 1e-6 and rel_err(masked_n, g["masked_n"]) < 1e-6
+    taps = {}
+    w = O.inpaint_forward(p_rest, p_head, masked_n, m4, taps)
+    assert rel_err(taps["pred"], g["pred"]) < 1e-5
+    assert rel_err(w, g["w_mat"]) < 1e-4
+    for step in (0, 300, 600):
+        st = O.inpaint_loss(g["w_mat"], g["clean_n"], g["pred"], step=step, grace=500, lambda0=1.0)
+        for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse"):
+            assert rel_err(st[k], g[f"s{step}_{k}"]) < 1e-5, (step, k)
+        assert abs(st["objective"].item() - g[f"s{step}_objective"].item()) <= 1e-5 * abs(g[f"s{step}_objective"].item()) + 1e-7
+
+
+def _product_model():
+    import generative_audio_b200 as g
+    I = g.inpainting
+    rest, p_rest = _params(1, 1, "rest.")
+    rest.load_state_dict(p_rest)
+    ck = os.path.join(tempfile.mkdtemp(), "rest.pt")
+    torch.save({"model_state_dict": rest.state_dict()}, ck)
+    cfg = I.NPPCModelConfig(pretrained_restoration_model_configuration=I.UNetConfig(in_channels=1, out_channels=1),
+                            pretrained_restoration_model_path=ck,
+                            audio_pc_wrapper_configuration=I.AudioInpaintingPCWrapperConfig(
+                                model_configuration=I.UNetConfig(in_channels=2, out_channels=N_DIRS), n_dirs=N_DIRS))
+    m = I.NPPCModel(cfg)
+    m.pc_wrapper.net.load_state_dict(weights.synth_unet_state_dict(_shapes(m.pc_wrapper.net), 0, "head."))
+    return m
+
+
+@pytest.mark.gpu
+def test_inpainting_model_vs_golden():
+    import generative_audio_b200 as g
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gd = load_golden("inpaint_model_b2")
+    m = _product_model()
+    clean_n, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"].cuda(), gd["masked_spec"].cuda(), gd["mask"].cuda())
+    assert rel_err(clean_n.cpu(), gd["clean_n"]) < 1e-5 and rel_err(masked_n.cpu(), gd["masked_n"]) < 1e-5
+    pred = m.get_pred_spec_mag_norm(masked_n, m4)
+    assert rel_err(pred.cpu(), gd["pred"]) < 1e-4
+    w = m(masked_n, m4)
+    assert w.shape == (2, N_DIRS, 40, 50)
+    assert rel_err(w.cpu(), gd["w_mat"]) < 1e-3
+    # PCs are supported on the gap only
+    assert torch.all(w[:, :, :, :11] == 0)
+    for step in (0, 300, 600):
+        stepper = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+        stepper.step = step
+        reconst, objective, log = stepper.base_step((gd["masked_spec"], gd["mask"], gd["clean_spec"]))
+        for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse"):
+            assert rel_err(log[k].cpu(), gd[f"s{step}_{k}"]) < 2e-3, (step, k)
+        assert abs(objective.item() - gd[f"s{step}_objective"].item()) < 2e-3 * abs(gd[f"s{step}_objective"].item()) + 1e-6
+
+
+@pytest.mark.gpu
+def test_inpainting_kernels_vs_oracle():
+    import generative_audio_b200 as g
+    rng = torch.Generator().manual_seed(5)
+    B, n, Fq, T = 3, 4, 33, 47
+    head = torch.randn(B, n, Fq, T, generator=rng)
+    gt, pred = torch.randn(B, 1, Fq, T, generator=rng), torch.randn(B, 1, Fq, T, generator=rng)
+    mask = (torch.rand(B, 1, Fq, T, generator=rng) > 0.3).float()
+    x_in = torch.randn(B, 2, Fq, T, generator=rng)
+    assert torch.equal(g.ops.mask_blend(None, head.cuda(), mask.cuda()).cpu(), head * (1 - mask))
+    ref = x_in[:, :1] * mask + head * (1 - mask)
+    assert rel_err(g.ops.mask_blend(x_in.cuda(), head.cuda(), mask.cuda()).cpu(), ref) < 1e-6
+    w, st = g.ops.gs_loss_fused_real(head.cuda(), gt.cuda(), pred.cuda())
+    w_ref = O.gram_schmidt_real(head)
+    assert rel_err(w.cpu(), w_ref) < 1e-4
+    so = O.inpaint_loss(w_ref, gt, pred, step=600, grace=500, lambda0=1.0)
+    for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse"):
+        assert rel_err(st[k].cpu(), so[k]) < 1e-4, k
+    st2 = g.ops.projection_loss_real(w_ref.cuda(), gt.cuda(), pred.cuda())
+    for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse"):
+        assert rel_err(st2[k].cpu(), so[k]) < 1e-4, k
+    spec_c, spec_m = torch.randn(B, 2, Fq, T, generator=rng), torch.randn(B, 2, Fq, T, generator=rng)
+    c, mm, mean, std = g.ops.logmag_normalize(spec_c.cuda(), spec_m.cuda())
+    co, _, mo = O.inpaint_preprocess(spec_c, spec_m, torch.ones(B, T))
+    assert rel_err(c.cpu(), co) < 1e-5 and rel_err(mm.cpu(), mo) < 1e-5
