@@ -45,6 +45,51 @@ __global__ void __launch_bounds__(TPB) crm_apply_kernel(const float* __restrict_
     }
 }
 
+// N1 (NPPCAudioValidator._crm_directions_to_spectograms + the alpha sweep of visualize_pc_spectrograms,
+// nppc_audio/validator.py:55-102,246-290): for every direction d of w_mat, pc = decompress(w_d) * noisy (M*N, utils.py:252-256)
+// and for every alpha a, var = enhanced + alpha_a * pc.  One read of w_mat / noisy / enhanced, all n*A variations written.
+// grid (chunks, n, B)
+__global__ void __launch_bounds__(TPB) pc_variations_kernel(const float* __restrict__ w_mat, const float* __restrict__ nre,
+                                                           const float* __restrict__ nim, const float* __restrict__ ere,
+                                                           const float* __restrict__ eim, int n, int FT,
+                                                           const float* __restrict__ alphas, int A,
+                                                           float* __restrict__ pc_re, float* __restrict__ pc_im,
+                                                           float* __restrict__ var_re, float* __restrict__ var_im) {
+    const int b = blockIdx.z, d = blockIdx.y;
+    const float* m0p = w_mat + ((size_t)(b * n + d) * 2) * FT;
+    const float* m1p = m0p + FT;
+    const size_t off = (size_t)b * FT, poff = (size_t)(b * n + d) * FT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FT; i += gridDim.x * blockDim.x) {
+        const float m0 = decompress1(m0p[i]), m1 = decompress1(m1p[i]);
+        const float r = nre[off + i], q = nim[off + i];
+        const float pr = m0 * r - m1 * q, pi = m1 * r + m0 * q;
+        if (pc_re) { pc_re[poff + i] = pr; pc_im[poff + i] = pi; }
+        const float er = ere[off + i], ei = eim[off + i];
+        for (int a = 0; a < A; ++a) {
+            const float al = alphas[a];
+            const size_t vo = ((size_t)(b * n + d) * A + a) * FT + i;
+            var_re[vo] = er + al * pr;
+            var_im[vo] = ei + al * pi;
+        }
+    }
+}
+
+// save_audio_files' peak normalisation (validator.py:118-119,133-134,281-282): x[r] /= max|x[r]| + 1e-8, one CTA per row
+__global__ void __launch_bounds__(TPB) peak_normalize_kernel(float* __restrict__ x, int L) {
+    __shared__ float red[32];
+    float* row = x + (size_t)blockIdx.x * L;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(row[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    const float denom = m + 1e-8f;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] = row[i] / denom;
+}
+
 __global__ void __launch_bounds__(TPB) decompress_kernel(const float* __restrict__ m, long long n, float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = decompress1(m[i]);
@@ -339,6 +384,31 @@ extern "C" int nppc_crm_decompress_apply(const float* crm, const float* real, co
     int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
     if (gx > per && per >= 1) gx = per;
     crm_apply_kernel<<<dim3(gx, B), TPB, 0, (cudaStream_t)stream>>>(crm, real, imag, FT, conj, out_mag, out_real, out_imag);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_pc_variations(const float* w_mat, const float* noisy_real, const float* noisy_imag,
+                                  const float* enh_real, const float* enh_imag, int B, int n, int FT, const float* alphas,
+                                  int A, float* pc_real, float* pc_imag, float* var_real, float* var_imag, void* stream) {
+    NPPC_CHECK_ARG(w_mat && noisy_real && noisy_imag && enh_real && enh_imag && alphas && var_real && var_imag,
+                   "nppc_pc_variations: null pointer");
+    NPPC_CHECK_ARG((pc_real == nullptr) == (pc_imag == nullptr), "nppc_pc_variations: pc_real / pc_imag must both be set or NULL");
+    NPPC_CHECK_ARG(B > 0 && n > 0 && FT > 0 && A > 0 && n <= 65535 && B <= 65535, "nppc_pc_variations: bad sizes");
+    int gx = grid_for(FT, 4);
+    int per = nppc::cdiv((long long)nppc::sm_count() * 8, (long long)B * n);
+    if (gx > per && per >= 1) gx = per;
+    pc_variations_kernel<<<dim3(gx, n, B), TPB, 0, (cudaStream_t)stream>>>(w_mat, noisy_real, noisy_imag, enh_real, enh_imag, n,
+                                                                         FT, alphas, A, pc_real, pc_imag, var_real, var_imag);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_peak_normalize(float* x, int rows, int L, void* stream) {
+    NPPC_CHECK_ARG(x && rows > 0 && L > 0, "nppc_peak_normalize: bad arguments");
+    peak_normalize_kernel<<<rows, TPB, 0, (cudaStream_t)stream>>>(x, L);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

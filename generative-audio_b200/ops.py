@@ -304,6 +304,37 @@ def mask_blend(x_in, x: torch.Tensor, mask: torch.Tensor):
     return out
 
 
+def pc_variations(w_mat: torch.Tensor, noisy_real, noisy_imag, enh_real, enh_imag, alphas: torch.Tensor, want_pc=True):
+    """N1: pc[b,d] = decompress(w_mat[b,d]) * noisy[b], var[b,d,a] = enhanced[b] + alphas[a] * pc[b,d] (validator.py:55-102,
+    246-290) in one pass.  w_mat [B,n,2,F,T]; noisy/enh [B,F,T] (or [B,1,F,T]); returns (pc_re, pc_im [B,n,F,T] | None,
+    var_re, var_im [B,n,A,F,T])."""
+    w_mat, noisy_real, noisy_imag, enh_real, enh_imag = (_f32(t) for t in (w_mat, noisy_real, noisy_imag, enh_real, enh_imag))
+    alphas = alphas.to(device=w_mat.device, dtype=torch.float32).contiguous()
+    _chk(w_mat, noisy_real, noisy_imag, enh_real, enh_imag, alphas)
+    B, n, two, Fq, T = w_mat.shape
+    assert two == 2
+    FT, A = Fq * T, alphas.numel()
+    for t in (noisy_real, noisy_imag, enh_real, enh_imag):
+        assert t.numel() == B * FT
+    f = dict(device=w_mat.device, dtype=torch.float32)
+    pc_re = torch.empty(B, n, Fq, T, **f) if want_pc else None
+    pc_im = torch.empty(B, n, Fq, T, **f) if want_pc else None
+    var_re, var_im = torch.empty(B, n, A, Fq, T, **f), torch.empty(B, n, A, Fq, T, **f)
+    _lib.check(_lib.load().nppc_pc_variations(w_mat.data_ptr(), noisy_real.data_ptr(), noisy_imag.data_ptr(), enh_real.data_ptr(),
+                                              enh_imag.data_ptr(), B, n, FT, alphas.data_ptr(), A,
+                                              pc_re.data_ptr() if want_pc else None, pc_im.data_ptr() if want_pc else None,
+                                              var_re.data_ptr(), var_im.data_ptr(), _stream()), "nppc_pc_variations")
+    return pc_re, pc_im, var_re, var_im
+
+
+def peak_normalize_(x: torch.Tensor):
+    """In place x[r] /= max|x[r]| + 1e-8 over the last dimension (validator.py:118-134)."""
+    _chk(x)
+    L = x.shape[-1]
+    _lib.check(_lib.load().nppc_peak_normalize(x.data_ptr(), x.numel() // L, L, _stream()), "nppc_peak_normalize")
+    return x
+
+
 TC_ROW_TILE = 128  # the tensor-core LSTM owns 128 sequences per CTA; its time-major buffers pad rows to this
 
 

@@ -63,6 +63,16 @@ int nppc_decompress_cirm(const float* m, long long n, float* out, void* stream);
 int nppc_build_cirm(const float* nr, const float* ni, const float* cr, const float* ci, int B, int FT,
                     float* gt /* [B,2,FT] */, void* stream);
 
+/* ---- N1: PC directions -> spectrogram variations (NPPCAudioValidator._crm_directions_to_spectograms and the alpha
+ * sweep of visualize_pc_spectrograms, nppc_audio/validator.py:55-102,246-290; utils.crm_to_spectogram utils.py:252-256):
+ *   pc[b,d] = decompress_cIRM(w_mat[b,d]) * noisy[b]   (M*N),   var[b,d,a] = enhanced[b] + alphas[a] * pc[b,d]
+ * w_mat [B,n,2,FT]; noisy_* / enh_* [B,FT]; alphas [A] (device); pc_* [B,n,FT] (optional, both or NULL); var_* [B,n,A,FT].
+ * nppc_peak_normalize: save_audio_files' x /= max|x| + 1e-8 per waveform row (validator.py:118-134,281-282), in place. */
+int nppc_pc_variations(const float* w_mat, const float* noisy_real, const float* noisy_imag, const float* enh_real,
+                       const float* enh_imag, int B, int n, int FT, const float* alphas, int A, float* pc_real,
+                       float* pc_imag, float* var_real, float* var_imag, void* stream);
+int nppc_peak_normalize(float* x, int rows, int L, void* stream);
+
 /* ---- a2: laplace norms --------------------------------------------------------------------------
  * offline_laplace_norm (audio_zen/model/base_model.py:210-224): y = x / (mean_{per sample}(x) + 1e-5).
  * x [B, n] -> y [B, n] (n = C*F*T).  `sums` is a [B] fp64 scratch (device). In-place (y == x) allowed. */

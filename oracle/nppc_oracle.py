@@ -512,3 +512,22 @@ def inpaint_loss(w_mat, clean, pred, *, step: int, grace: float, lambda0: float)
     objective = reconst_err.mean() + lam * second_moment_mse.mean()
     return dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst_err,
                 second_moment_mse=second_moment_mse, objective=objective)
+
+
+# --------------------------------------------------------------------------------------------
+# N1  validator consumer: PC directions -> spectrogram / audio variations
+# --------------------------------------------------------------------------------------------
+def pc_variations(w_mat, noisy_real, noisy_imag, enh_real, enh_imag, alphas, length, n_fft=512, hop=256):
+    """nppc_audio/validator.py:55-102 (_crm_directions_to_spectograms) + :246-290 (alpha sweep, istft, peak normalisation).
+    w_mat [B,n,2,F,T]; noisy/enh [B,F,T].  Returns pc (re, im) [B,n,F,T] and normalised variation waveforms [B,n,A,L]."""
+    B, n = w_mat.shape[:2]
+    m = decompress_cirm(w_mat)
+    pc_re = m[:, :, 0] * noisy_real[:, None] - m[:, :, 1] * noisy_imag[:, None]   # utils.crm_to_spectogram, utils.py:252-256
+    pc_im = m[:, :, 1] * noisy_real[:, None] + m[:, :, 0] * noisy_imag[:, None]
+    out = []
+    for a in alphas.tolist():
+        vr, vi = enh_real[:, None] + a * pc_re, enh_imag[:, None] + a * pc_im
+        w = istft(vr.reshape(B * n, *vr.shape[2:]), vi.reshape(B * n, *vi.shape[2:]), length, n_fft, hop)
+        w = w / (w.abs().amax(dim=-1, keepdim=True) + 1e-8)
+        out.append(w.reshape(B, n, -1))
+    return pc_re, pc_im, torch.stack(out, dim=2)
