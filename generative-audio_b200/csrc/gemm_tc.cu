@@ -239,3 +239,9 @@ extern "C" int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias
                                  void* stream) {
     return nppc::gemm_16bit_tn(A, W, bias, C, M, N, K, 0, (cudaStream_t)stream);
 }
+
+// same with IEEE fp16 operands / output (the TCN 1x1 convolutions, tcn_cl.cu)
+extern "C" int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
+                                void* stream) {
+    return nppc::gemm_16bit_tn(A, W, bias, C, M, N, K, 1, (cudaStream_t)stream);
+}

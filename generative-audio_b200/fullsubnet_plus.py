@@ -59,6 +59,10 @@ class FullSubNet_Plus(nn.Module):
         self.fb_model = SequenceModel(**kw)
         self.fb_model_real = SequenceModel(**kw)
         self.fb_model_imag = SequenceModel(**kw)
+        import os
+        tc = self.lstm_impl == "tc" and os.environ.get("NPPC_TCN_TC", "1") != "0"   # 1x1 convs on the tcgen05 GEMM (row N2)
+        for m in (self.fb_model, self.fb_model_real, self.fb_model_imag):
+            m.use_tc_convs = tc
 
     # -- helpers --------------------------------------------------------------------------------------
     def _pad_norm(self, x):

@@ -120,9 +120,67 @@ class SequenceModel(nn.Module):
         self._plan_key = None
 
     # ---- TCN path ----
+    use_tc_convs = False   # set by the owning model when lstm_impl == "tc": 1x1 convolutions on the tcgen05 GEMM (row N2)
+
+    def _tcn_plan(self):
+        """fp16 / padded copies of the 1x1-conv weights for the channel-last tcgen05 path (derived cache, never serialised)."""
+        blocks = [m for m in self.sequence_model if isinstance(m, TCNBlock)]
+        ps = [p for blk in blocks for p in (blk.conv1x1.weight, blk.sconv.weight, blk.sconv.bias, blk.norm2.weight, blk.norm2.bias)]
+        ps += [self.fc_output_layer.weight, self.fc_output_layer.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_tplan", None) is None or key != self._tplan_key:
+            C = blocks[0].conv1x1.weight.shape[1]
+            Kp, Np = -(-C // 64) * 64, -(-C // 128) * 128
+            dev = blocks[0].conv1x1.weight.device
+            with torch.no_grad():
+                plan = dict(C=C, Kp=Kp, Np=Np, blocks=[])
+                for blk in blocks:
+                    w1 = torch.zeros(512, Kp, device=dev, dtype=torch.float16)
+                    w1[:, :C] = blk.conv1x1.weight[:, :, 0].clamp(-65504, 65504).half()
+                    w2f, u, vb = blk._folded()
+                    w2 = torch.zeros(Np, 512, device=dev, dtype=torch.float16)
+                    w2[:C] = w2f[:, :, 0].clamp(-65504, 65504).half()
+                    plan["blocks"].append((w1, w2, u, vb))
+                O = self.fc_output_layer.weight.shape[0]
+                Op = -(-O // 128) * 128
+                wfc = torch.zeros(Op, Kp, device=dev, dtype=torch.float16)
+                wfc[:O, :C] = self.fc_output_layer.weight.clamp(-65504, 65504).half()
+                plan.update(O=O, Op=Op, wfc=wfc)
+            self._tplan, self._tplan_key = plan, key
+        return self._tplan
+
+    def forward_tc(self, x):
+        """x [B,C,T'] f32 -> [B,O,T'] f32: the whole stack channel-last, every 1x1 convolution and the output Linear on the
+        tcgen05 fp16 GEMM (fp32 accumulate, fp32 residual stream), everything between them in three fused kernels per block."""
+        pl = self._tcn_plan()
+        B, C, T = x.shape
+        M = B * T
+        dev = x.device
+        x32 = torch.empty(M, C, device=dev, dtype=torch.float32)
+        xh = torch.zeros(M, pl["Kp"], device=dev, dtype=torch.float16)
+        # per-sample fp16 scale: the real / imag streams are normalised by a cancelling mean and can be huge (see tcn_cl.cu)
+        scale = x.abs().amax(dim=(1, 2)).clamp_min(1e-30).float().contiguous()
+        inv_scale = (1.0 / scale).contiguous()
+        ops.tcn_cl_pack(x.contiguous(), pl["Kp"], inv_scale, x32, xh)
+        blocks = [m for m in self.sequence_model if isinstance(m, TCNBlock)]
+        for i, (blk, (w1, w2, u, vb)) in enumerate(zip(blocks, pl["blocks"])):
+            y1 = ops.gemm_f16_tn(xh, w1)
+            stats1 = ops.prelu_stats_cl(y1, B, T, scale, blk.conv1x1.bias, blk.prelu1.weight)
+            z, stats2 = ops.tcn_mid_cl(y1, B, T, scale, blk.conv1x1.bias, blk.prelu1.weight, stats1, blk.norm1.weight, blk.norm1.bias,
+                                       blk.depthwise_conv.weight, blk.depthwise_conv.bias, blk.dilation, blk.prelu2.weight)
+            o = ops.gemm_f16_tn(z, w2)
+            ops.tcn_out_cl(o, x32, B, T, C, pl["Np"], pl["Kp"], stats2, u, vb, inv_scale, xh, relu_h=(i == len(blocks) - 1))
+        o = ops.gemm_f16_tn(xh, pl["wfc"])
+        relu = {"ReLU": 1, None: 0, "": 0, False: 0}.get(self.output_activate_function, None)
+        if relu is None:
+            raise NotImplementedError("tcgen05 TCN path: only ReLU / no output activation (every reference config)")
+        return ops.tcn_cl_unpack(o, B, pl["O"], T, pl["Op"], scale, self.fc_output_layer.bias, relu)
+
     def forward(self, x):
         if self.sequence_model_type != "TCN":
             raise RuntimeError("the LSTM SequenceModel runs through lstm_forward(xs) on packed input")
+        if self.use_tc_convs and x.is_cuda and not torch.is_grad_enabled():
+            return self.forward_tc(x)
         o = self.fc_output_layer(self.sequence_model(x).permute(0, 2, 1))
         if self.output_activate_function:
             o = self.activate_function(o)

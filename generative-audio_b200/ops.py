@@ -450,6 +450,58 @@ def tcn_out(o, x, c_hidden: int, stats2, u, vb):
     return xn
 
 
+# ---- N2: channel-last TCN stack on the tcgen05 GEMM ------------------------------------------------------------------
+def gemm_f16_tn(a: torch.Tensor, w: torch.Tensor, bias=None):
+    """C[M,N] fp16 = A[M,K] fp16 @ W[N,K]^T fp16 (+ bias f32), fp32 accumulate (tcgen05).  K % 64 == 0, N % 128 == 0."""
+    _chk(a, w, bias)
+    assert a.dtype == torch.float16 and w.dtype == torch.float16
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty(M, N, device=a.device, dtype=torch.float16)
+    _lib.check(_lib.load().nppc_gemm_f16_tn(a.data_ptr(), w.data_ptr(), _ptr(bias), c.data_ptr(), M, N, K, _stream()),
+               "nppc_gemm_f16_tn")
+    return c
+
+
+def tcn_cl_pack(x: torch.Tensor, Kp: int, inv_scale: torch.Tensor, x32: torch.Tensor, xh: torch.Tensor):
+    _chk(x, inv_scale, x32, xh)
+    B, C, T = x.shape
+    _lib.check(_lib.load().nppc_tcn_cl_pack(x.data_ptr(), B, C, T, Kp, inv_scale.data_ptr(), x32.data_ptr(), xh.data_ptr(), _stream()),
+               "nppc_tcn_cl_pack")
+
+
+def tcn_cl_unpack(o: torch.Tensor, B: int, C: int, T: int, Np: int, scale, bias, relu: int):
+    _chk(o, scale, bias)
+    out = torch.empty(B, C, T, device=o.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_tcn_cl_unpack(o.data_ptr(), B, C, T, Np, _ptr(scale), _ptr(bias), int(relu), out.data_ptr(), _stream()),
+               "nppc_tcn_cl_unpack")
+    return out
+
+
+def prelu_stats_cl(y1: torch.Tensor, B: int, T: int, scale, bias, prelu_a):
+    _chk(y1, scale, bias, prelu_a)
+    stats = torch.empty(B, 2, device=y1.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_prelu_stats_cl(y1.data_ptr(), B, T, y1.shape[1], scale.data_ptr(), bias.data_ptr(), prelu_a.data_ptr(),
+                                               stats.data_ptr(), _stream()), "nppc_prelu_stats_cl")
+    return stats
+
+
+def tcn_mid_cl(y1, B: int, T: int, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, dilation: int, prelu2_a):
+    _chk(y1, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w, dw_b, prelu2_a)
+    z = torch.empty_like(y1)
+    stats2 = torch.empty(B, 2, device=y1.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_tcn_mid_cl(y1.data_ptr(), B, T, y1.shape[1], scale.data_ptr(), bias1.data_ptr(), prelu1_a.data_ptr(), stats1.data_ptr(),
+                                           gamma1.data_ptr(), beta1.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), dilation,
+                                           prelu2_a.data_ptr(), z.data_ptr(), stats2.data_ptr(), _stream()), "nppc_tcn_mid_cl")
+    return z, stats2
+
+
+def tcn_out_cl(o, x32, B: int, T: int, C: int, Np: int, Kp: int, stats2, u, vb, inv_scale, xh, relu_h: bool):
+    _chk(o, x32, stats2, u, vb, inv_scale, xh)
+    _lib.check(_lib.load().nppc_tcn_out_cl(o.data_ptr(), x32.data_ptr(), B, T, C, Np, Kp, 512, stats2.data_ptr(), u.data_ptr(),
+                                           vb.data_ptr(), inv_scale.data_ptr(), xh.data_ptr(), int(relu_h), _stream()), "nppc_tcn_out_cl")
+
+
 def assemble_mask(y: torch.Tensor, B: int, Fp: int, look_ahead: int):
     """y [B*F', O, T'] -> [B, O, F', T'-la] (fullsubnet_plus.py:227-229)."""
     _chk(y)

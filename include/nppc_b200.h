@@ -196,6 +196,31 @@ int nppc_assemble_mask(const float* y, int B, int Fp, int O, int Tp, int look_ah
  * tcgen05.mma + TMA + TMEM. K % 64 == 0, N % 128 == 0. */
 int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
                       void* stream);
+/* same with IEEE fp16 operands and output */
+int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, void* stream);
+
+/* ---- N2: TCN stack in channel-last layout with its 1x1 convolutions on the tcgen05 GEMM ------------------------
+ * (audio_zen/model/module/causal_conv.py:96-108, sequence_model.py:47-58,106-112).  M = B*T' rows, row = b*T' + t.
+ * fp16 range: xh holds x / scale[b] (scale[b] = max|x| of the sample on entry, inv_scale = 1/scale); y1 and the final Linear
+ * are multiplied back by scale[b] in fp32 where they are read.
+ * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,C] f32 (residual stream) and xh [M,Kp] fp16 (GEMM operand; columns >= C
+ *                      must be zero on entry and stay zero).
+ * nppc_prelu_stats_cl: stats[b] = (sum, sum^2) of PReLU(y1 + bias[c]) over the sample, y1 [M,512] fp16.
+ * nppc_tcn_mid_cl:     z [M,512] fp16 = PReLU2(depthwise_dilated(GroupNorm1(PReLU1(y1 + bias1)))), stats2 = moments of z.
+ * nppc_tcn_out_cl:     x32 += o*rstd2 + vb - mean2*rstd2*u (o [M,Np] fp16 = z*(W2 diag(gamma2))^T); xh = fp16(x32), or
+ *                      fp16(relu(x32)) when relu_h (the stack's trailing ReLU before fc_output_layer).
+ * nppc_tcn_cl_unpack:  o [M,Np] fp16 (+bias, optional ReLU) -> [B,C,T'] f32. */
+int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh, void* stream);
+int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, const float* scale /* [B] or NULL */, const float* bias,
+                       int relu, float* out, void* stream);
+int nppc_prelu_stats_cl(const void* y1, int B, int T, int H, const float* scale, const float* bias, const float* prelu_a,
+                        double* stats, void* stream);
+int nppc_tcn_mid_cl(const void* y1, int B, int T, int H, const float* scale, const float* bias1, const float* prelu1_a,
+                    const double* stats1, const float* gamma1, const float* beta1, const float* dw_w, const float* dw_b,
+                    int dilation, const float* prelu2_a, void* z, double* stats2, void* stream);
+int nppc_tcn_out_cl(const void* o, float* x32, int B, int T, int C, int Np, int Kp, int H, const double* stats2, const float* u,
+                    const float* vb, const float* inv_scale, void* xh, int relu_h, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -91,3 +91,31 @@ def test_model_tc_matches_f32_at_bench_like_batch():
     e = rel_err(wt.cpu(), wf.cpu())
     print(f"tc vs f32 (B=8 x 4 s): {e:.3e}")
     assert e < TOL_BF16
+
+
+@pytest.mark.parametrize("C", [257, 514])
+def test_tcn_stack_tcgen05_vs_fp32_path(C):
+    """Row N2: channel-last TCN stack with its 1x1 convolutions on the tcgen05 fp16 GEMM vs the fp32 channel-first path
+    (library convolutions + tcn.cu kernels) and vs the CPU oracle."""
+    import generative_audio_b200 as g
+    import nppc_oracle as O
+    import weights
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = g.modules.SequenceModel(input_size=C, output_size=257, hidden_size=512, num_layers=2, bidirectional=False,
+                                sequence_model="TCN", output_activate_function="ReLU")
+    sd = {k: weights.synth_tensor("pretrained_restoration_model.fb_model." + k, tuple(v.shape), 3) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(3, C, 61, generator=gen) * 2.0
+    x[1] = (x[1] - 1.0) * 3.0e4   # the real / imag streams: signed and far outside the fp16 range
+    with torch.no_grad():
+        ref = m(x.cuda())
+        m.use_tc_convs = True
+        out = m(x.cuda())
+        cpu = O.tcn_sequence_model(x, {"fb." + k: v for k, v in sd.items()}, "fb")
+    e_ref, e_tc = rel_err(ref.cpu(), cpu), rel_err(out.cpu(), cpu)
+    print(f"tcn C={C}: fp32 path vs oracle {e_ref:.3e}, tcgen05 path vs oracle {e_tc:.3e}")
+    assert e_ref < 1e-4
+    assert e_tc < 5e-3
