@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(TPB) crm_apply_kernel(const float* __restrict_
     const float* m0p = crm + (size_t)b * 2 * FT;
     const float* m1p = m0p + FT;
     const size_t off = (size_t)b * FT;
+#pragma unroll 4
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < FT; i += gridDim.x * blockDim.x) {
         float m0 = decompress1(m0p[i]), m1 = decompress1(m1p[i]);
         float r = re[off + i], q = im[off + i];
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(TPB) pad_norm_kernel(const float* __restrict__
     const float* xb = x + (size_t)b * F * T;
     float* yb = y + (size_t)b * F * Tp;
     const int n = F * Tp;
+#pragma unroll 4
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int f = i / Tp, t = i - f * Tp;
         yb[i] = (t < T) ? xb[f * T + t] * inv : 0.0f;

@@ -5,6 +5,7 @@
 //   solve   gs_solve    : per sample, replay the reference's MGS recurrences symbolically on coefficient vectors
 //                         (w_i = sum_k a_i[k] x_k) in fp64 -> lower-triangular A, norms, projections, loss terms
 //   pass 2  apply_kernel: out_i = sum_{k<=i} A[i][k] x_k  (fp32 streaming FMA), one read + one write
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -282,12 +283,10 @@ int dispatch_apply(int n, const float* x, int B, long long P, const SampleScratc
 }
 
 template <bool COMPLEX>
-int run(const float* x, const float* gt, const float* pred, int B, int n, long long P, void* scratch, int do_gs,
-        float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
-        cudaStream_t s) {
+int run_chunk(const float* x, const float* gt, const float* pred, int B, int n, long long P, SampleScratch* scr, int do_gs,
+              float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
+              cudaStream_t s) {
     const int has_err = gt != nullptr;
-    SampleScratch* scr = (SampleScratch*)scratch;
-    NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
     int rc = dispatch_gram<COMPLEX>(n + has_err, x, gt, pred, B, n, P, scr, s);
     if (rc) return rc;
 #define SOLVE(NT) gs_solve_kernel<COMPLEX, NT><<<B, 32, 0, s>>>(scr, B, n, do_gs, has_err, err_norm, err_proj, w_norms, reconst_err, second_moment)
@@ -301,6 +300,33 @@ int run(const float* x, const float* gt, const float* pred, int B, int n, long l
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     if (out) return dispatch_apply<COMPLEX>(n, x, B, P, scr, out, s);
+    return NPPC_OK;
+}
+
+// Optional L2-resident chunking (NPPC_GS_L2_MB=<MiB>): walk the batch in chunks of samples whose vectors fit in L2 so the
+// apply pass re-reads from L2.  Measured on B200 (B = 64, n = 5): 146 us unchunked vs 161 / 226 / 382 us at 80 / 40 / 20 MiB —
+// every chunk pays the serial fp64 coefficient solve (~28 us) and a small-grid launch, so the default is ONE chunk.
+template <bool COMPLEX>
+int run(const float* x, const float* gt, const float* pred, int B, int n, long long P, void* scratch, int do_gs,
+        float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
+        cudaStream_t s) {
+    SampleScratch* scr = (SampleScratch*)scratch;
+    NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
+    static const long long budget = getenv("NPPC_GS_L2_MB") ? atoll(getenv("NPPC_GS_L2_MB")) << 20 : (1LL << 50);
+    const long long per_sample = (long long)n * (COMPLEX ? 2 : 1) * P * 4;
+    int chunk = out ? (int)(budget / (per_sample > 0 ? per_sample : 1)) : B;   // no apply pass -> nothing to re-read
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    const size_t vs = (size_t)(COMPLEX ? 2 : 1) * P;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int bc = B - b0 < chunk ? B - b0 : chunk;
+        int rc = run_chunk<COMPLEX>(x + (size_t)b0 * n * vs, gt ? gt + (size_t)b0 * vs : nullptr, pred ? pred + (size_t)b0 * vs : nullptr,
+                                    bc, n, P, scr + b0, do_gs, out ? out + (size_t)b0 * n * vs : nullptr,
+                                    err_norm ? err_norm + b0 : nullptr, err_proj ? err_proj + (size_t)b0 * n * (COMPLEX ? 2 : 1) : nullptr,
+                                    w_norms ? w_norms + (size_t)b0 * n : nullptr, reconst_err ? reconst_err + b0 : nullptr,
+                                    second_moment ? second_moment + (size_t)b0 * n : nullptr, s);
+        if (rc) return rc;
+    }
     return NPPC_OK;
 }
 

@@ -1,9 +1,11 @@
 // a1 STFT front end and a15 iSTFT back end (n_fft = win = 512, hop = 256).
 //
 // HBM-bound kernels: one CTA transforms 16 consecutive frames of one utterance so that the [B,F,T]
-// (T contiguous) planes are read/written in 64-byte runs; the 512-point real FFT of each frame is done by one
-// warp as a 256-point complex radix-2 FFT in shared memory (even/odd packing), twiddles and the periodic hann
-// window staged in shared memory once per CTA.
+// (T contiguous) planes are read/written in 64-byte runs.  The 512-point real FFT of a frame is a 256-point complex
+// FFT (even/odd packing) done by a HALF warp as 16 x 16: two register-resident 16-point FFTs per lane (radix 4 x 4)
+// with one conflict-free (17-padded) shared-memory transpose in between — two frames per warp at a time, 3 warp
+// syncs per transform instead of the 8 shared-memory radix-2 stages this replaced.  Twiddles and the periodic hann
+// window are staged in shared memory once per CTA.
 #include "common.cuh"
 
 namespace {
@@ -19,30 +21,68 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// In-place 256-point complex FFT on `buf` (input in bit-reversed order), forward (e^{-i..}) or inverse (e^{+i..}),
-// unnormalised. tw[k] = exp(-2*pi*i*k/512), k < 256. Executed by one full warp.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// 4-point DFT in place (forward: W4 = -i, inverse: +i); outputs k = 0..3 land in x0..x3
 template <bool INVERSE>
-__device__ __forceinline__ void warp_fft256(float2* buf, const float2* tw, int lane) {
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const int half = 1 << s;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int j = lane + 32 * q;
-            int grp = j >> s, pos = j & (half - 1);
-            int i0 = (grp << (s + 1)) + pos, i1 = i0 + half;
-            float2 w = tw[pos << (8 - s)];
-            if (INVERSE) w.y = -w.y;
-            float2 a = buf[i0];
-            float2 b = cmul(buf[i1], w);
-            buf[i0] = make_float2(a.x + b.x, a.y + b.y);
-            buf[i1] = make_float2(a.x - b.x, a.y - b.y);
-        }
-        __syncwarp();
-    }
+__device__ __forceinline__ void fft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 s02 = cadd(x0, x2), d02 = csub(x0, x2), s13 = cadd(x1, x3), d13 = csub(x1, x3);
+    const float2 jd = INVERSE ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);   // (-/+ i) * d13
+    x0 = cadd(s02, s13);
+    x2 = csub(s02, s13);
+    x1 = cadd(d02, jd);
+    x3 = csub(d02, jd);
 }
 
-__device__ __forceinline__ int bitrev8(int m) { return (int)(__brev((unsigned)m) >> 24); }
+// 16-point DFT in registers (radix 4 x 4).  In: a[n] natural order.  Out: A[k] is found at a[4*(k & 3) + (k >> 2)].
+template <bool INVERSE>
+__device__ __forceinline__ void fft16(float2 (&a)[16]) {
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) fft4<INVERSE>(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);   // -> b[k1][n2] at a[4*k1 + n2]
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
+    // W16^m = (cos, -/+ sin)(2 pi m / 16) for m = n2 * k1
+    const float sg = INVERSE ? 1.f : -1.f;
+    const float2 w1 = make_float2(C1, sg * S1), w2 = make_float2(R, sg * R), w3 = make_float2(S1, sg * C1);
+    const float2 w4 = make_float2(0.f, sg), w6 = make_float2(-R, sg * R), w9 = make_float2(-C1, -sg * S1);
+    a[4 + 1] = cmul(a[4 + 1], w1); a[4 + 2] = cmul(a[4 + 2], w2); a[4 + 3] = cmul(a[4 + 3], w3);
+    a[8 + 1] = cmul(a[8 + 1], w2); a[8 + 2] = cmul(a[8 + 2], w4); a[8 + 3] = cmul(a[8 + 3], w6);
+    a[12 + 1] = cmul(a[12 + 1], w3); a[12 + 2] = cmul(a[12 + 2], w6); a[12 + 3] = cmul(a[12 + 3], w9);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) fft4<INVERSE>(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);   // -> A[k1 + 4*k2] at a[4*k1 + k2]
+}
+
+constexpr int FBUF = 16 * 17;   // float2 per frame buffer: 256 natural-order points, or the 17-padded 16 x 16 transpose
+
+// In-place 256-point complex FFT of `buf` (natural order in, natural order out), forward (e^{-i..}) or inverse (e^{+i..}),
+// unnormalised, executed by ONE HALF WARP (hl = lane & 15); both halves of the warp must call it together (it contains
+// __syncwarp), each on its own buffer.  tw[k] = exp(-2*pi*i*k/512), k < 256.
+//   Z[k1 + 16 k2] = sum_m2 W16^(m2 k2) [ W256^(m2 k1) sum_m1 z[16 m1 + m2] W16^(m1 k1) ]
+template <bool INVERSE>
+__device__ __forceinline__ void half_warp_fft256(float2* buf, const float2* tw, int hl) {
+    float2 a[16];
+#pragma unroll
+    for (int m1 = 0; m1 < 16; ++m1) a[m1] = buf[16 * m1 + hl];       // z[16 m1 + m2], m2 = hl
+    __syncwarp();
+    fft16<INVERSE>(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        float2 v = a[4 * (k1 & 3) + (k1 >> 2)];
+        const int m = hl * k1;                                        // W256^m, m <= 225
+        float2 w = tw[(2 * m) & 255];
+        if (m >= 128) { w.x = -w.x; w.y = -w.y; }
+        if (INVERSE) w.y = -w.y;
+        buf[k1 * 17 + hl] = cmul(v, w);                               // Y[k1][m2]
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m2 = 0; m2 < 16; ++m2) a[m2] = buf[hl * 17 + m2];       // lane = k1
+    __syncwarp();
+    fft16<INVERSE>(a);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) buf[hl + 16 * k2] = a[4 * (k2 & 3) + (k2 >> 2)];
+    __syncwarp();
+}
 
 struct __align__(16) SmemTables {
     float2 tw[M];     // exp(-2 pi i k / 512)
@@ -79,45 +119,56 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const float* __restric
                                                          float* __restrict__ im) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem_raw);
-    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));       // [WARPS][M]
-    float2* tile = fftbuf + WARPS * M;                                               // [NBIN][FRAMES+1]
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));       // [2*WARPS][FBUF]
+    float2* tile = fftbuf + 2 * WARPS * FBUF;                                        // [NBIN][FRAMES+1]
     const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, hl = lane & 15;
     fill_tables(tb);
     __syncthreads();
     const float* x = wave + (size_t)b * L;
-    float2* buf = fftbuf + warp * M;
-    for (int fi = warp; fi < FRAMES; fi += WARPS) {
-        int t = t0 + fi;
-        if (t >= T) break;  // warp-uniform
-        long long base = (long long)t * HOP - NFFT / 2;
-        // load 512 windowed samples (reflect padding, no edge repeat), pack even/odd into complex, bit-reversed
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            int m = lane + 32 * q;
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int n = 2 * m + e;
-                long long p = base + n;
-                if (p < 0) p = -p;
-                if (p > L - 1) p = 2LL * (L - 1) - p;
-                v[e] = x[p] * tb->win[n];
-            }
-            buf[bitrev8(m)] = make_float2(v[0], v[1]);
+    // the CTA's span of the reflect-padded signal, (FRAMES + 1) hops, loaded ONCE (coalesced); every sample feeds two frames.
+    // It aliases the output tile: all frames are in their FFT buffers (barrier below) before the first tile write.
+    float* xs = reinterpret_cast<float*>(tile);
+    {
+        const int p0 = t0 * HOP - NFFT / 2;
+        for (int i = threadIdx.x; i < (FRAMES + 1) * HOP; i += blockDim.x) {
+            int p = p0 + i;
+            if (p < 0) p = -p;
+            if (p > L - 1) p = 2 * (L - 1) - p;
+            xs[i] = (p >= 0 && p < L) ? x[p] : 0.f;   // frames beyond T never read their samples
         }
+    }
+    __syncthreads();
+    float2* buf = fftbuf + (warp * 2 + hw) * FBUF;
+    static_assert(FRAMES == 2 * WARPS, "one pass: every half warp owns exactly one frame");
+    {
+        const int fi0 = warp * 2;
+        const int fi = fi0 + hw, t = t0 + fi;
+        const bool ok = fi < FRAMES && t < T;   // per half warp; both halves run the transform (it syncs the warp)
+        // 512 windowed samples packed even/odd into 256 complex points, natural order
+        const float2* xf = reinterpret_cast<const float2*>(xs + fi * HOP);
+        const float2* wf = reinterpret_cast<const float2*>(tb->win);
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+            const int m = hl + 16 * q;
+            const float2 xv = xf[m], wv = wf[m];
+            buf[m] = ok ? make_float2(xv.x * wv.x, xv.y * wv.y) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();   // xs is dead from here on (the tile may overwrite it)
         __syncwarp();
-        warp_fft256<false>(buf, tb->tw, lane);
+        half_warp_fft256<false>(buf, tb->tw, hl);
         // real-FFT recovery: X[k] = E[k] + W512^k O[k], E = (Z[k]+conj Z[M-k])/2, O = (Z[k]-conj Z[M-k])/(2i)
-        for (int k = lane; k <= M; k += 32) {
-            float2 zk = buf[k & (M - 1)];
-            float2 zm = buf[(M - k) & (M - 1)];
-            float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-            float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));  // (Zk - conj Zm)/2
-            float2 O = make_float2(D.y, -D.x);                                     // D / i
-            float2 w = (k < M) ? tb->tw[k] : make_float2(-1.0f, 0.0f);
-            float2 wo = cmul(w, O);
-            tile[k * (FRAMES + 1) + fi] = make_float2(E.x + wo.x, E.y + wo.y);
+        if (ok) {
+            for (int k = hl; k <= M; k += 16) {
+                float2 zk = buf[k & (M - 1)];
+                float2 zm = buf[(M - k) & (M - 1)];
+                float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));  // (Zk - conj Zm)/2
+                float2 O = make_float2(D.y, -D.x);                                     // D / i
+                float2 w = (k < M) ? tb->tw[k] : make_float2(-1.0f, 0.0f);
+                float2 wo = cmul(w, O);
+                tile[k * (FRAMES + 1) + fi] = make_float2(E.x + wo.x, E.y + wo.y);
+            }
         }
         __syncwarp();
     }
@@ -141,12 +192,12 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const float* __restri
                                                           int T, int length, float* __restrict__ wave) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem_raw);
-    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));  // [WARPS][M]
-    float* frames = reinterpret_cast<float*>(fftbuf + WARPS * M);                // [FRAMES+1][NFFT] windowed
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));  // [2*WARPS][FBUF]
+    float* frames = reinterpret_cast<float*>(fftbuf + 2 * WARPS * FBUF);         // [FRAMES+1][NFFT] windowed
     float2* xin = reinterpret_cast<float2*>(frames + (FRAMES + 1) * NFFT);       // [NBIN][FRAMES+2] spectrum tile
     constexpr int XS = FRAMES + 2;
     const int b = blockIdx.y, hb0 = 1 + blockIdx.x * FRAMES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, hl = lane & 15;
     fill_tables(tb);
     const size_t plane = (size_t)b * NBIN * T;
     const int tf0 = hb0 - 1;  // first frame needed
@@ -161,32 +212,35 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const float* __restri
         xin[k * XS + fi] = v;
     }
     __syncthreads();
-    float2* buf = fftbuf + warp * M;
-    for (int fi = warp; fi < FRAMES + 1; fi += WARPS) {
-        int t = tf0 + fi;
-        float* fr = frames + fi * NFFT;
-        if (t >= T) {  // warp-uniform
-            for (int n = lane; n < NFFT; n += 32) fr[n] = 0.f;
-            continue;
-        }
+    float2* buf = fftbuf + (warp * 2 + hw) * FBUF;
+    for (int fi0 = warp * 2; fi0 < FRAMES + 1; fi0 += WARPS * 2) {
+        const int fi = fi0 + hw, t = tf0 + fi;
+        const bool active = fi < FRAMES + 1, has = active && t < T;   // per half warp; both halves run the transform
         // Z[k] = E[k] + i O[k]; E = (X[k] + conj X[M-k])/2 ; O = (X[k] - conj X[M-k])/2 * conj(W512^k)
-        for (int k = lane; k < M; k += 32) {
-            float2 xk = xin[k * XS + fi];
-            float2 xm = xin[(M - k) * XS + fi];
-            if (k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores Im of the DC and Nyquist bins
-            float2 E = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
-            float2 D = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
-            float2 w = tb->tw[k];
-            w.y = -w.y;
-            float2 O = cmul(D, w);
-            buf[bitrev8(k)] = make_float2(E.x - O.y, E.y + O.x);  // E + i*O
+        for (int k = hl; k < M; k += 16) {
+            float2 z = make_float2(0.f, 0.f);
+            if (has) {
+                float2 xk = xin[k * XS + fi];
+                float2 xm = xin[(M - k) * XS + fi];
+                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores Im of the DC and Nyquist bins
+                float2 E = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
+                float2 D = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
+                float2 w = tb->tw[k];
+                w.y = -w.y;
+                float2 O = cmul(D, w);
+                z = make_float2(E.x - O.y, E.y + O.x);  // E + i*O
+            }
+            buf[k] = z;
         }
         __syncwarp();
-        warp_fft256<true>(buf, tb->tw, lane);
-        for (int m = lane; m < M; m += 32) {
-            float2 z = buf[m];
-            fr[2 * m] = z.x * (1.0f / 256.0f) * tb->win[2 * m];
-            fr[2 * m + 1] = z.y * (1.0f / 256.0f) * tb->win[2 * m + 1];
+        half_warp_fft256<true>(buf, tb->tw, hl);
+        if (active) {
+            float* fr = frames + fi * NFFT;
+            for (int m = hl; m < M; m += 16) {
+                float2 z = buf[m];
+                fr[2 * m] = z.x * (1.0f / 256.0f) * tb->win[2 * m];
+                fr[2 * m + 1] = z.y * (1.0f / 256.0f) * tb->win[2 * m + 1];
+            }
         }
         __syncwarp();
     }
@@ -220,7 +274,7 @@ extern "C" int nppc_stft_mri(const float* wave, int B, int L, int n_fft, int hop
     NPPC_CHECK_ARG(wave && mag && real && imag, "nppc_stft_mri: null pointer");
     int T = 1 + L / HOP;
     NPPC_CHECK_ARG(ensure_tables((cudaStream_t)stream) == 0, "nppc_stft_mri: table init failed");
-    size_t smem = sizeof(SmemTables) + sizeof(float2) * WARPS * M + sizeof(float2) * NBIN * (FRAMES + 1);
+    size_t smem = sizeof(SmemTables) + sizeof(float2) * 2 * WARPS * FBUF + sizeof(float2) * NBIN * (FRAMES + 1);
     NPPC_CUDA_OK(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nppc::cdiv(T, FRAMES), B);
     stft_kernel<<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(wave, L, T, mag, real, imag);
@@ -235,7 +289,7 @@ extern "C" int nppc_istft(const float* real, const float* imag, int B, int T, in
     NPPC_CHECK_ARG(B > 0 && T > 0 && length > 0, "nppc_istft: bad sizes B=%d T=%d length=%d", B, T, length);
     NPPC_CHECK_ARG(real && imag && wave, "nppc_istft: null pointer");
     NPPC_CHECK_ARG(ensure_tables((cudaStream_t)stream) == 0, "nppc_istft: table init failed");
-    size_t smem = sizeof(SmemTables) + sizeof(float2) * WARPS * M + sizeof(float) * (FRAMES + 1) * NFFT +
+    size_t smem = sizeof(SmemTables) + sizeof(float2) * 2 * WARPS * FBUF + sizeof(float) * (FRAMES + 1) * NFFT +
                   sizeof(float2) * NBIN * (FRAMES + 2);
     NPPC_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nblocks = nppc::cdiv(length, HOP);  // hop-blocks hb = 1 .. ceil((length+256)/256)-1
