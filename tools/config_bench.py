@@ -1,0 +1,83 @@
+"""Throughput of the other BASELINE.json configurations on one B200 (synthetic data, deterministic synthetic weights):
+  #2 enhance-only (STFT -> FullSubNet+ -> cRM -> iSTFT), batch 64 x 4 s
+  #3 NPPC-audio training step (frozen backbone on the kernels, PC head through autograd, Adam), batch 32, groups 2
+  #4 inpainting NPPC forward, batch 128 x [128 x 500] log-mag spectrograms, n_dirs = 10 (library convolutions)
+  N1 validator consumer (pc_variations: 5 directions x 6 alphas -> audio), batch 8 x 4 s
+CUDA events, 3 warm-up + 5 timed iterations, 256 MiB L2 flush between iterations.  usage: python tools/config_bench.py"""
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch
+
+import generative_audio_b200 as g
+import weights
+from helpers import build_model, wave
+
+dev = "cuda"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+out = {}
+with torch.no_grad():
+    m, _ = build_model(5, 1, "tc")
+    x = wave(64, 64000, 1).cuda()
+    ms = timeit(lambda: m.enhance(x))
+    out["config2_enhance_only_b64"] = {"ms_per_step": ms, "audio_s_per_s": 64 * 4.0 / (ms * 1e-3)}
+    x8 = wave(8, 64000, 2).cuda()
+    ms = timeit(lambda: m.pc_variations(x8))
+    out["n1_pc_variations_b8"] = {"ms_per_step": ms, "waveforms_per_step": 8 * 5 * 6 + 8, "audio_s_per_s": 8 * 4.0 / (ms * 1e-3)}
+
+m2, _ = build_model(5, 2, "tc")
+stepper = g.NPPCAudioStep(m2, 500, 1.0)
+opt = torch.optim.Adam(m2.audio_pc_wrapper.parameters(), lr=1e-4)
+clean = wave(32, 64000, 3, 0.03)
+noisy = clean + 0.3 * wave(32, 64000, 4, 1.0)
+ms = timeit(lambda: stepper.train_step((noisy.cuda(), clean.cuda()), opt), reps=3, warm=2)
+out["config3_train_step_b32_g2"] = {"ms_per_step": ms, "audio_s_per_s": 32 * 4.0 / (ms * 1e-3),
+                                     "note": "frozen half on the kernels, PC head fwd+bwd on torch autograd (fp32/TF32 off), Adam step"}
+del stepper, opt, m2
+torch.cuda.empty_cache()
+
+with torch.no_grad():
+    I = g.inpainting
+    N_DIRS = 10
+    rest = I.UNet(I.UNetConfig(in_channels=1, out_channels=1))
+    shp = lambda mod: [(k, tuple(v.shape)) for k, v in mod.state_dict().items()]
+    rest.load_state_dict(weights.synth_unet_state_dict(shp(rest), 0, "rest."))
+    ck = os.path.join(tempfile.mkdtemp(), "rest.pt")
+    torch.save({"model_state_dict": rest.state_dict()}, ck)
+    cfg = I.NPPCModelConfig(pretrained_restoration_model_configuration=I.UNetConfig(in_channels=1, out_channels=1),
+                            pretrained_restoration_model_path=ck,
+                            audio_pc_wrapper_configuration=I.AudioInpaintingPCWrapperConfig(
+                                model_configuration=I.UNetConfig(in_channels=2, out_channels=N_DIRS), n_dirs=N_DIRS))
+    mi = I.NPPCModel(cfg)
+    mi.pc_wrapper.net.load_state_dict(weights.synth_unet_state_dict(shp(mi.pc_wrapper.net), 0, "head."))
+    B = 128
+    spec = torch.randn(B, 2, 128, 500, device=dev)
+    mask = torch.ones(B, 500, device=dev)
+    mask[:, 200:218] = 0
+    clean_n, m4, masked_n = I.preprocess_data(spec, spec * mask[:, None, None, :], mask)
+    ms = timeit(lambda: mi(masked_n, m4), reps=3, warm=2)
+    out["config4_inpainting_b128_ndirs10"] = {"ms_per_step": ms, "audio_s_per_s": B * 4.0 / (ms * 1e-3),
+                                              "note": "UNet convolutions on cuDNN (row N4), glue + real Gram-Schmidt on the kernels"}
+print(json.dumps(out, indent=1))
