@@ -18,8 +18,10 @@ def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
 class NPPCAudioStep:
     """Holds what base_step reads from the reference trainer: model, step counter, loss hyper-parameters."""
 
-    def __init__(self, nppc_model: NPPCModel, second_moment_loss_grace: float = 500, second_moment_loss_lambda: float = 1.0):
+    def __init__(self, nppc_model: NPPCModel, second_moment_loss_grace: float = 500, second_moment_loss_lambda: float = 1.0,
+                 amp_dtype=None):
         self.nppc_model = nppc_model
+        self.amp_dtype = amp_dtype   # e.g. torch.bfloat16: autocast for the head's GEMM-shaped ops (BASELINE config 3)
         self.step = 0
         self.second_moment_loss_grace = second_moment_loss_grace
         self.second_moment_loss_lambda = second_moment_loss_lambda
@@ -51,7 +53,7 @@ class NPPCAudioStep:
         feats, gt, pred = self._frozen_half(noisy, clean)
         lam = second_moment_lambda(self.step, self.second_moment_loss_grace, self.second_moment_loss_lambda)
         with torch.enable_grad():
-            head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats)
+            head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats, amp_dtype=self.amp_dtype)
             w_mat = training.gram_schmidt_autograd(head)
             st = training.nppc_loss_autograd(w_mat, gt, pred, lam)
         log = {"noisy_complex": noisy, "clean_complex": clean, "pred_crm": pred, "w_mat": w_mat.detach(),

@@ -59,8 +59,11 @@ def _drop_band(x, G):
     return torch.cat([x[g::G, :, g:Fq:G, :] for g in range(G)], dim=0)
 
 
-def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag):
-    """MultiDirectionFullSubNet_Plus.forward (networks.py:63-163) in differentiable torch ops -> [B, n, 2, F', T]."""
+def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag, amp_dtype=None):
+    """MultiDirectionFullSubNet_Plus.forward (networks.py:63-163) in differentiable torch ops -> [B, n, 2, F', T].
+    amp_dtype (e.g. torch.bfloat16, BASELINE config 3): the GEMM-shaped parts (TCN convolutions, LSTM, fc) run under
+    torch.autocast in that dtype; normalisers, attention, Gram-Schmidt and the loss stay fp32."""
+    amp = lambda: torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None)
     la = net.look_ahead
     nmag, nreal, nimag, emag, ereal, eimag = (F.pad(v, [0, la]) for v in (nmag, nreal, nimag, emag, ereal, eimag))
     B, _, Fq, Tp = nmag.shape
@@ -68,7 +71,8 @@ def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag):
     def stream(noisy, enh, att, model):
         a = _tsse(att, _offline_norm(noisy).reshape(B, Fq, Tp))
         b = _tsse(att, _offline_norm(enh).reshape(B, Fq, Tp))
-        return _tcn(model, torch.cat([a, b], dim=1))
+        with amp():
+            return _tcn(model, torch.cat([a, b], dim=1)).float()
 
     fb = stream(nmag, emag, net.channel_attention, net.fb_model)
     fbr = stream(nreal, ereal, net.channel_attention_real, net.fb_model_real)
@@ -83,10 +87,12 @@ def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag):
     was_training = lstm.training
     lstm.train(True)   # cuDNN's RNN backward needs the training-mode forward (no dropout here: identical numerics)
     try:
-        o, _ = lstm(seq)
+        with amp():
+            o, _ = lstm(seq)
+            y = net.sb_model.fc_output_layer(o).float()
     finally:
         lstm.train(was_training)
-    y = net.sb_model.fc_output_layer(o).permute(0, 2, 1)  # [B*F', 2n, T']
+    y = y.permute(0, 2, 1)  # [B*F', 2n, T']
     n = net.n_directions
     return y.reshape(B, Fp, n, 2, Tp).permute(0, 2, 3, 1, 4)[..., la:]
 

@@ -115,3 +115,25 @@ def test_training_step_autograd_matches_reference_gradients():
         assert st.step == 601
     finally:
         torch.backends.cudnn.allow_tf32 = True
+
+
+def test_training_step_bf16_autocast_close_to_fp32():
+    """BASELINE config 3 runs the head's GEMM-shaped ops in bf16 (autocast): objective and gradient norm stay within the
+    1e-2 bf16 budget of the fp32 autograd step (which is itself pinned against the reference's gradients above)."""
+    import generative_audio_b200 as G
+    g = load_golden("model_step_g2_b4")
+    m, sd = build_model(5, 2, "f32")
+    batch = (g["noisy"].cuda(), g["clean"].cuda())
+    res = {}
+    for name, dt in (("fp32", None), ("bf16", torch.bfloat16)):
+        st = G.NPPCAudioStep(m, 500, 1.0, amp_dtype=dt)
+        st.step = 600
+        m.zero_grad(set_to_none=True)
+        _, obj, _ = st.base_step(batch, requires_grad=True)
+        with torch.enable_grad():
+            obj.backward()
+        gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.audio_pc_wrapper.net.parameters() if p.grad is not None)).item()
+        res[name] = (obj.item(), gn)
+    print("train step fp32 vs bf16 (objective, grad norm):", res)
+    assert abs(res["bf16"][0] - res["fp32"][0]) < 1e-2 * abs(res["fp32"][0]) + 1e-3
+    assert abs(res["bf16"][1] - res["fp32"][1]) < 5e-2 * res["fp32"][1]
