@@ -43,7 +43,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// sigmoid(z) = 0.5 tanh(z / 2) + 0.5; the 1/2 is folded into the packed i, f, o rows of W_ih, W_hh and the bias (exact:
+// a power-of-two scale), so the MMAs already deliver z / 2 for those gates
+__device__ __forceinline__ float sigmoid_half_arg(float hx) { return fmaf(0.5f, tanh_fast(hx), 0.5f); }
 
 // tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
@@ -508,8 +510,8 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         const float zf = __uint_as_float(g[4 + uu]) + pf[uu];
                         const float zg = __uint_as_float(g[8 + uu]) + pg[uu];
                         const float zo = __uint_as_float(g[12 + uu]) + po[uu];
-                        cn[uu] = sigmoid_fast(zf) * cprev[uu] + sigmoid_fast(zi) * tanh_fast(zg);
-                        hn[uu] = sigmoid_fast(zo) * tanh_fast(cn[uu]);
+                        cn[uu] = sigmoid_half_arg(zf) * cprev[uu] + sigmoid_half_arg(zi) * tanh_fast(zg);
+                        hn[uu] = sigmoid_half_arg(zo) * tanh_fast(cn[uu]);
                     }
                     __half2 q;
                     q = __floats2half2_rn(cn[0], cn[1]); cp[2 * b] = *reinterpret_cast<uint32_t*>(&q);
@@ -566,12 +568,14 @@ __device__ __forceinline__ int packed_to_lstm_row(int p) {
     const int chunk = p >> 7, half = (p >> 6) & 1, blk = (p >> 4) & 3, gate = (p >> 2) & 3, uu = p & 3;
     return gate * H + chunk * CH + half * 16 + blk * 4 + uu;
 }
+// i, f, o rows carry the 1/2 of sigmoid(z) = 0.5 tanh(z/2) + 0.5 (gate order i, f, g, o)
+__device__ __forceinline__ float packed_gate_scale(int p) { return ((p >> 2) & 3) == 2 ? 1.0f : 0.5f; }
 __global__ void pack_w_kernel(const float* __restrict__ w, int K, int KP, __half* __restrict__ out) {
     long long n = (long long)H4 * KP;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int p = (int)(i / KP), k = (int)(i - (long long)p * KP);
         int src = packed_to_lstm_row(p);
-        out[i] = __float2half_rn(k < K ? fminf(fmaxf(w[(size_t)src * K + k], -65504.f), 65504.f) : 0.f);
+        out[i] = __float2half_rn(k < K ? fminf(fmaxf(packed_gate_scale(p) * w[(size_t)src * K + k], -65504.f), 65504.f) : 0.f);
     }
 }
 __global__ void pack_fc_kernel(const float* __restrict__ w, int O, __half* __restrict__ out) {  // [O][H] f32 -> [16][H] fp16
@@ -580,7 +584,7 @@ __global__ void pack_fc_kernel(const float* __restrict__ w, int O, __half* __res
 }
 __global__ void pack_b_kernel(const float* __restrict__ b, float* __restrict__ out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < H4) out[p] = b[packed_to_lstm_row(p)];
+    if (p < H4) out[p] = packed_gate_scale(p) * b[packed_to_lstm_row(p)];
 }
 
 // fc_output_layer over the h sequence of the last layer: y[row][o][t] = b[o] + sum_k W[o][k] * h[t][row][k]

@@ -74,11 +74,21 @@ __global__ void __launch_bounds__(TPB) prelu_stats_cl_kernel(const __half2* __re
     const float a = *a_ptr, b0 = bias[2 * c2], b1 = bias[2 * c2 + 1];
     const __half2* base = y1 + (size_t)b * T * (HID / 2) + c2;
     float s = 0.f, ss = 0.f;
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
-        const float2 v = __half22float2(base[(size_t)t * (HID / 2)]);
-        const float p0 = prelu(fmaf(v.x, sb, b0), a), p1 = prelu(fmaf(v.y, sb, b1), a);
-        s += p0 + p1;
-        ss += p0 * p0 + p1 * p1;
+    // each CTA owns a contiguous run of rows; 4 independent row loads in flight per thread
+    const int rows = (T + gridDim.x - 1) / gridDim.x, tb = blockIdx.x * rows, te = min(T, tb + rows);
+    for (int t = tb; t < te; t += 4) {
+        __half2 raw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (t + q < te) raw[q] = base[(size_t)(t + q) * (HID / 2)];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (t + q < te) {
+                const float2 v = __half22float2(raw[q]);
+                const float p0 = prelu(fmaf(v.x, sb, b0), a), p1 = prelu(fmaf(v.y, sb, b1), a);
+                s += p0 + p1;
+                ss += p0 * p0 + p1 * p1;
+            }
     }
     double ds = nppc::block_sum((double)s, red);
     double dss = nppc::block_sum((double)ss, red);
@@ -117,7 +127,9 @@ __global__ void __launch_bounds__(TPB) tcn_mid_cl_kernel(const __half2* __restri
     __half2* zb = z + (size_t)b * T * (HID / 2) + c2;
     auto nrm = [&](int t, int e, float2 v) { return prelu(fmaf(e ? v.y : v.x, sb, bb[e]), a1) * sc[e] + sh[e]; };
     float s = 0.f, ss = 0.f;
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    const int rows = (T + gridDim.x - 1) / gridDim.x, tb = blockIdx.x * rows, te = min(T, tb + rows);
+#pragma unroll 2
+    for (int t = tb; t < te; ++t) {
         const int tm = t - dil, tp = t + dil;
         const float2 vc = __half22float2(base[(size_t)t * (HID / 2)]);
         float2 vm = make_float2(0.f, 0.f), vp = make_float2(0.f, 0.f);
@@ -143,11 +155,14 @@ __global__ void __launch_bounds__(TPB) tcn_mid_cl_kernel(const __half2* __restri
     }
 }
 
-// x32 <- x32 + o * rstd + (vb - mean * rstd * u); xh <- fp16(x32) or fp16(relu(x32)) (last block: the stack's trailing ReLU)
-__global__ void __launch_bounds__(TPB) tcn_out_cl_kernel(const __half* __restrict__ o, float* __restrict__ x32, int T, int C, int Np,
-                                                        int Kp, const double* __restrict__ stats2, const float* __restrict__ u,
-                                                        const float* __restrict__ vb, const float* __restrict__ inv_scale,
-                                                        __half* __restrict__ xh, int relu_h) {
+// x32 <- x32 + o * rstd + (vb - mean * rstd * u); xh <- fp16(x32 / scale) or fp16(relu(x32) / scale) (last block: the stack's
+// trailing ReLU).  thread = channel (per-channel constant hoisted, accesses coalesced along c), each CTA owns a contiguous
+// run of rows with 4 independent rows in flight; grid (row chunks, B).
+constexpr int OUT_TPB = 288;   // 9 warps: one pass covers C = 257, two passes C = 514
+__global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __restrict__ o, float* __restrict__ x32, int T, int C, int Np,
+                                                            int Kp, const double* __restrict__ stats2, const float* __restrict__ u,
+                                                            const float* __restrict__ vb, const float* __restrict__ inv_scale,
+                                                            __half* __restrict__ xh, int relu_h) {
     const int b = blockIdx.y;
     const float is = inv_scale[b];
     const double n = (double)HID * T;
@@ -155,14 +170,29 @@ __global__ void __launch_bounds__(TPB) tcn_out_cl_kernel(const __half* __restric
     const double var_d = stats2[2 * b + 1] / n - mu_d * mu_d;
     const float rstd = (float)(1.0 / sqrt(fmax(var_d, 0.0) + 1e-8));
     const float mr = (float)mu_d * rstd;
-    const int total = T * C;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int t = i / C, c = i - t * C;
-        const size_t row = (size_t)b * T + t;
-        const float v = x32[row * C + c] + __half2float(o[row * Np + c]) * rstd + (vb[c] - mr * u[c]);
-        x32[row * C + c] = v;
-        const float h = relu_h ? fmaxf(v, 0.f) : v;
-        xh[row * Kp + c] = __float2half_rn(fminf(fmaxf(h * is, -65504.f), 65504.f));
+    const int rows = (T + gridDim.x - 1) / gridDim.x, tb = blockIdx.x * rows, te = min(T, tb + rows);
+    for (int c = threadIdx.x; c < C; c += OUT_TPB) {
+        const float kc = vb[c] - mr * u[c];
+        for (int t = tb; t < te; t += 4) {
+            float xv[4];
+            __half ov[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (t + q < te) {
+                    const size_t row = (size_t)b * T + t + q;
+                    xv[q] = x32[row * C + c];
+                    ov[q] = o[row * Np + c];
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (t + q < te) {
+                    const size_t row = (size_t)b * T + t + q;
+                    const float v = xv[q] + __half2float(ov[q]) * rstd + kc;
+                    x32[row * C + c] = v;
+                    const float h = relu_h ? fmaxf(v, 0.f) : v;
+                    xh[row * Kp + c] = __float2half_rn(fminf(fmaxf(h * is, -65504.f), 65504.f));
+                }
+        }
     }
 }
 }  // namespace
@@ -185,10 +215,12 @@ extern "C" int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, co
     return NPPC_OK;
 }
 
+// CTAs per sample: contiguous row chunks, ~4 waves of 8 CTAs/SM over the whole batch, at least 8 rows per CTA
 static int rows_grid(int T, int B) {
-    int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
-    if (per < 1) per = 1;
-    return per > T ? T : per;
+    int per = nppc::cdiv((long long)nppc::sm_count() * 32, B);
+    int cap = nppc::cdiv(T, 8);
+    if (per > cap) per = cap;
+    return per < 1 ? 1 : per;
 }
 
 extern "C" int nppc_prelu_stats_cl(const void* y1, int B, int T, int H, const float* scale, const float* bias, const float* prelu_a,
@@ -223,10 +255,7 @@ extern "C" int nppc_tcn_out_cl(const void* o, float* x32, int B, int T, int C, i
                                const float* u, const float* vb, const float* inv_scale, void* xh, int relu_h, void* stream) {
     NPPC_CHECK_ARG(o && x32 && stats2 && u && vb && inv_scale && xh && B > 0 && T > 0 && C > 0 && Np >= C && Kp >= C && B <= 65535 && H == HID,
                    "nppc_tcn_out_cl: bad arguments");
-    int gx = nppc::cdiv((long long)T * C, TPB * 4);
-    int per = nppc::cdiv((long long)nppc::sm_count() * 8, B);
-    if (gx > per && per >= 1) gx = per;
-    tcn_out_cl_kernel<<<dim3(gx, B), TPB, 0, (cudaStream_t)stream>>>((const __half*)o, x32, T, C, Np, Kp, stats2, u, vb, inv_scale, (__half*)xh, relu_h);
+    tcn_out_cl_kernel<<<dim3(rows_grid(T, B), B), OUT_TPB, 0, (cudaStream_t)stream>>>((const __half*)o, x32, T, C, Np, Kp, stats2, u, vb, inv_scale, (__half*)xh, relu_h);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
