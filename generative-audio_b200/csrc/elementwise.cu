@@ -9,8 +9,10 @@ constexpr int TPB = 256;
 
 __device__ __forceinline__ float decompress1(float m) {
     // mask.py:57-60: limit*(m>=limit) - limit*(m<=-limit) + m*(|m|<limit); -K*log((K-m)/(K+m)), K=10, limit=9.9
+    // = K ln2 (lg2(K + c) - lg2(K - c)): two MUFU.LG2 instead of a division + libm logf (this kernel was instruction-bound:
+    // 48 us for 115 MB); arguments lie in [0.1, 19.9], absolute error ~3e-6 on values up to 52.9
     float c = (m >= 9.9f) ? 9.9f : ((m <= -9.9f) ? -9.9f : m);
-    return -10.0f * logf((10.0f - c) / (10.0f + c));
+    return 6.931471805599453f * (__log2f(10.0f + c) - __log2f(10.0f - c));
 }
 
 __device__ __forceinline__ float compress1(float m) {
