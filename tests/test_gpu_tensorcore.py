@@ -37,10 +37,11 @@ def _plan(ops, p, pre="sb_model"):
                         p[pre + ".fc_output_layer.weight"].cuda(), p[pre + ".fc_output_layer.bias"].cuda())
 
 
-@pytest.mark.parametrize("R,Tp,which", [(50, 23, "backbone"), (300, 40, "head"), (257, 253, "backbone")])
+@pytest.mark.parametrize("R,Tp,which", [(50, 23, "backbone"), (300, 40, "head"), (257, 253, "backbone"), (200, 30, "head10")])
 def test_lstm_tc_vs_oracle(ops, R, Tp, which):
+    """O = 2 (backbone) and O = 10 (head, n_dirs = 5): fc fused into the recurrent kernel; O = 20 (n_dirs = 10): separate fc kernel."""
     pre = "pretrained_restoration_model." if which == "backbone" else "audio_pc_wrapper.net."
-    p = weights.synth_state_dict(5, 0, pre)
+    p = weights.synth_state_dict(10 if which == "head10" else 5, 0, pre)
     g = torch.Generator().manual_seed(R)
     x = torch.randn(R, 34, Tp, generator=g)
     ref = O.lstm_fc(x, p, "sb_model", fast=True)
