@@ -137,3 +137,18 @@ def test_training_step_bf16_autocast_close_to_fp32():
     print("train step fp32 vs bf16 (objective, grad norm):", res)
     assert abs(res["bf16"][0] - res["fp32"][0]) < 1e-2 * abs(res["fp32"][0]) + 1e-3
     assert abs(res["bf16"][1] - res["fp32"][1]) < 5e-2 * res["fp32"][1]
+
+
+@pytest.mark.parametrize("B,L,seed", [(3, 5000, 5), (1, 7777, 6), (5, 2600, 8)])
+def test_ragged_lengths_and_batches(B, L, seed):
+    """Lengths that are not a multiple of the hop, odd batch sizes, very short utterances: both LSTM implementations against
+    the CPU oracle (w_mat and the enhance-only iSTFT path)."""
+    x = wave(B, L, seed)
+    for impl, tol_w, tol_e in (("f32", 1e-3, 1e-4), ("tc", 1e-2, 2e-3)):
+        m, sd = build_model(5, 1, impl)
+        ref = O.nppc_forward(sd, x, n_dirs=5)
+        w = m(x.cuda())
+        assert w.shape == ref.shape == (B, 5, 2, 257, 1 + L // 256)
+        assert rel_err(w.cpu(), ref) < tol_w, impl
+        enh_ref = O.enhance(O._sub(sd, "pretrained_restoration_model."), x)
+        assert rel_err(m.enhance(x.cuda()).cpu(), enh_ref) < tol_e, impl
