@@ -37,7 +37,8 @@ def _plan(ops, p, pre="sb_model"):
                         p[pre + ".fc_output_layer.weight"].cuda(), p[pre + ".fc_output_layer.bias"].cuda())
 
 
-@pytest.mark.parametrize("R,Tp,which", [(50, 23, "backbone"), (300, 40, "head"), (257, 253, "backbone"), (200, 30, "head10")])
+@pytest.mark.parametrize("R,Tp,which", [(50, 23, "backbone"), (300, 40, "head"), (257, 253, "backbone"), (200, 30, "head10"),
+                                          (1, 1, "head"), (130, 3, "backbone")])
 def test_lstm_tc_vs_oracle(ops, R, Tp, which):
     """O = 2 (backbone) and O = 10 (head, n_dirs = 5): fc fused into the recurrent kernel; O = 20 (n_dirs = 10): separate fc kernel."""
     pre = "pretrained_restoration_model." if which == "backbone" else "audio_pc_wrapper.net."
