@@ -114,21 +114,20 @@ int ensure_tables(cudaStream_t s) {
 }
 
 // grid: (ceil(T/32), B), block 256. dynamic smem: tables + per-warp FFT buffers + output tile.
+constexpr int SFB = FBUF + 1;   // per-frame buffer stride in the STFT kernel: odd, so the output stage (lanes = frames) is conflict-free
+
 __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const float* __restrict__ wave, int L, int T,
                                                          float* __restrict__ mag, float* __restrict__ re,
                                                          float* __restrict__ im) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem_raw);
-    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));       // [2*WARPS][FBUF]
-    float2* tile = fftbuf + 2 * WARPS * FBUF;                                        // [NBIN][FRAMES+1]
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw + sizeof(SmemTables));       // [FRAMES][SFB]: Z, then X[0..256] in place
+    float* xs = reinterpret_cast<float*>(fftbuf + FRAMES * SFB);                     // [(FRAMES + 1) * HOP] signal span
     const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hw = lane >> 4, hl = lane & 15;
     fill_tables(tb);
-    __syncthreads();
     const float* x = wave + (size_t)b * L;
-    // the CTA's span of the reflect-padded signal, (FRAMES + 1) hops, loaded ONCE (coalesced); every sample feeds two frames.
-    // It aliases the output tile: all frames are in their FFT buffers (barrier below) before the first tile write.
-    float* xs = reinterpret_cast<float*>(tile);
+    // the CTA's span of the reflect-padded signal, (FRAMES + 1) hops, loaded ONCE (coalesced); every sample feeds two frames
     {
         const int p0 = t0 * HOP - NFFT / 2;
         for (int i = threadIdx.x; i < (FRAMES + 1) * HOP; i += blockDim.x) {
@@ -139,12 +138,11 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const float* __restric
         }
     }
     __syncthreads();
-    float2* buf = fftbuf + (warp * 2 + hw) * FBUF;
     static_assert(FRAMES == 2 * WARPS, "one pass: every half warp owns exactly one frame");
     {
-        const int fi0 = warp * 2;
-        const int fi = fi0 + hw, t = t0 + fi;
-        const bool ok = fi < FRAMES && t < T;   // per half warp; both halves run the transform (it syncs the warp)
+        const int fi = warp * 2 + hw, t = t0 + fi;
+        float2* buf = fftbuf + fi * SFB;
+        const bool ok = t < T;   // per half warp; both halves run the transform (it syncs the warp)
         // 512 windowed samples packed even/odd into 256 complex points, natural order
         const float2* xf = reinterpret_cast<const float2*>(xs + fi * HOP);
         const float2* wf = reinterpret_cast<const float2*>(tb->win);
@@ -154,32 +152,36 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const float* __restric
             const float2 xv = xf[m], wv = wf[m];
             buf[m] = ok ? make_float2(xv.x * wv.x, xv.y * wv.y) : make_float2(0.f, 0.f);
         }
-        __syncthreads();   // xs is dead from here on (the tile may overwrite it)
         __syncwarp();
         half_warp_fft256<false>(buf, tb->tw, hl);
-        // real-FFT recovery: X[k] = E[k] + W512^k O[k], E = (Z[k]+conj Z[M-k])/2, O = (Z[k]-conj Z[M-k])/(2i)
-        if (ok) {
-            for (int k = hl; k <= M; k += 16) {
-                float2 zk = buf[k & (M - 1)];
-                float2 zm = buf[(M - k) & (M - 1)];
-                float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));  // (Zk - conj Zm)/2
-                float2 O = make_float2(D.y, -D.x);                                     // D / i
-                float2 w = (k < M) ? tb->tw[k] : make_float2(-1.0f, 0.0f);
-                float2 wo = cmul(w, O);
-                tile[k * (FRAMES + 1) + fi] = make_float2(E.x + wo.x, E.y + wo.y);
+        // real-FFT recovery, in place and two bins at a time.  With E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i),
+        // T = W512^k O:   X[k] = E + T,   X[M-k] = conj(E - T)   (E[M-k] = conj E[k], O[M-k] = conj O[k], W^(M-k) = -conj W^k)
+        for (int k = hl; k <= M / 2; k += 16) {
+            const float2 zk = buf[k];
+            if (k == 0) {
+                buf[0] = make_float2(zk.x + zk.y, 0.f);
+                buf[M] = make_float2(zk.x - zk.y, 0.f);
+            } else if (k == M / 2) {
+                buf[k] = make_float2(zk.x, -zk.y);   // W^(M/2) = -i
+            } else {
+                const float2 zm = buf[M - k];
+                const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                const float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));  // (Zk - conj Zm)/2
+                const float2 Tw = cmul(tb->tw[k], make_float2(D.y, -D.x));                  // W^k * (D / i)
+                buf[k] = make_float2(E.x + Tw.x, E.y + Tw.y);
+                buf[M - k] = make_float2(E.x - Tw.x, Tw.y - E.y);
             }
         }
-        __syncwarp();
     }
     __syncthreads();
+    // output: consecutive threads = consecutive frames (64-byte runs along T in each of the three planes)
     const size_t plane = (size_t)b * NBIN * T;
     for (int idx = threadIdx.x; idx < NBIN * FRAMES; idx += blockDim.x) {
-        int k = idx / FRAMES, fi = idx % FRAMES;
-        int t = t0 + fi;
+        const int k = idx / FRAMES, fi = idx % FRAMES;
+        const int t = t0 + fi;
         if (t < T) {
-            float2 v = tile[k * (FRAMES + 1) + fi];
-            size_t o = plane + (size_t)k * T + t;
+            const float2 v = fftbuf[fi * SFB + k];
+            const size_t o = plane + (size_t)k * T + t;
             re[o] = v.x;
             im[o] = v.y;
             mag[o] = sqrtf(v.x * v.x + v.y * v.y);
@@ -274,7 +276,7 @@ extern "C" int nppc_stft_mri(const float* wave, int B, int L, int n_fft, int hop
     NPPC_CHECK_ARG(wave && mag && real && imag, "nppc_stft_mri: null pointer");
     int T = 1 + L / HOP;
     NPPC_CHECK_ARG(ensure_tables((cudaStream_t)stream) == 0, "nppc_stft_mri: table init failed");
-    size_t smem = sizeof(SmemTables) + sizeof(float2) * 2 * WARPS * FBUF + sizeof(float2) * NBIN * (FRAMES + 1);
+    size_t smem = sizeof(SmemTables) + sizeof(float2) * FRAMES * SFB + sizeof(float) * (FRAMES + 1) * HOP;
     NPPC_CUDA_OK(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nppc::cdiv(T, FRAMES), B);
     stft_kernel<<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(wave, L, T, mag, real, imag);
