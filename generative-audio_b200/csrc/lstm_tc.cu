@@ -253,6 +253,9 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
     } else if (warp == 2) {
         // ---- store warp (both CTAs): everything slow about getting h_t out of the SM lives here, off the epilogue warps'
+        //      (Proxy ordering: the epilogue warps' generic st.shared are released by their mbarrier arrive, acquired by this
+        //      thread's wait, and only then does THIS thread's fence.proxy.async order them before the TMA store / the MMA
+        //      that read the same bytes through the async proxy.  tests: bitwise determinism over many CTA pairs.)
         //      critical path: the generic->async proxy fence (a MEMBAR that in an epilogue warp would also wait for its
         //      in-flight Zx loads), the TMA store of the staged [128 x 32] tile, its read / write completion, and the
         //      hand-over of the late slab to the MMA issuer.

@@ -121,3 +121,20 @@ def test_tcn_stack_tcgen05_vs_fp32_path(C):
     print(f"tcn C={C}: fp32 path vs oracle {e_ref:.3e}, tcgen05 path vs oracle {e_tc:.3e}")
     assert e_ref < 1e-4
     assert e_tc < 5e-3
+
+
+def test_lstm_tc_bitwise_deterministic(ops):
+    """The recurrent kernel hands h_t between warps, CTAs and proxies (TMEM, shared memory written by the epilogue and read
+    by the tensor core, TMA store -> TMA reload): any race would show up as run-to-run differences.  Three runs, many CTA
+    pairs, must agree bit for bit."""
+    p = weights.synth_state_dict(5, 0, "audio_pc_wrapper.net.")
+    plan = _plan(ops, p)
+    R, Tp = 3000, 48
+    g = torch.Generator().manual_seed(1)
+    RS = ops.padded_rows(R, torch.float16)
+    xs = torch.zeros(Tp, RS, 64, dtype=torch.float16)
+    xs[:, :R, :34] = torch.randn(Tp, R, 34, generator=g).half()
+    xs = xs.cuda()
+    y0 = plan.forward(xs, 1, R).clone()
+    for _ in range(2):
+        assert torch.equal(plan.forward(xs, 1, R), y0)
