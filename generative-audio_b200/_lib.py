@@ -39,6 +39,9 @@ PROTOTYPES = {
     "nppc_mask_blend": (_i, [_p, _i, _p, _p, _i, _i, _ll, _p, _p]),
     "nppc_pc_variations": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "nppc_peak_normalize": (_i, [_p, _i, _i, _p]),
+    "nppc_mix_scratch_bytes": (_sz, [_i]),
+    "nppc_mix_with_snr": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "nppc_time_to_spec_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_tsse": (_i, [_p, _i, _i, _i, C.POINTER(_i), C.POINTER(_p), C.POINTER(_p)] + [_p] * 6 + [_i, _p, _p, _p]),
     "nppc_prelu_stats": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),

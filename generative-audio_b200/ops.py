@@ -335,6 +335,37 @@ def peak_normalize_(x: torch.Tensor):
     return x
 
 
+# ---- N3: GPU data preparation ---------------------------------------------------------------------------------------------
+def mix_with_snr(clean: torch.Tensor, noise: torch.Tensor, snr_db, target_db=-25.0):
+    """Batched AudioDataset._mix_with_snr (dataset/audio_dataset.py:92-158): clean / noise [B,L]; snr_db, target_db: scalar or
+    [B].  Returns (noisy [B,L], clean_normalised [B,L])."""
+    clean, noise = _f32(clean), _f32(noise)
+    _chk(clean, noise)
+    B, L = clean.shape
+    assert noise.shape == clean.shape
+    as_vec = lambda v: (v.to(device=clean.device, dtype=torch.float32).reshape(-1).expand(B) if torch.is_tensor(v)
+                        else torch.full((B,), float(v), device=clean.device, dtype=torch.float32)).contiguous()
+    snr, tgt = as_vec(snr_db), as_vec(target_db)
+    lib = _lib.load()
+    scr = torch.empty(lib.nppc_mix_scratch_bytes(B), device=clean.device, dtype=torch.uint8)
+    noisy, clean_out = torch.empty_like(clean), torch.empty_like(clean)
+    _lib.check(lib.nppc_mix_with_snr(clean.data_ptr(), noise.data_ptr(), B, L, snr.data_ptr(), tgt.data_ptr(), scr.data_ptr(),
+                                     noisy.data_ptr(), clean_out.data_ptr(), _stream()), "nppc_mix_with_snr")
+    return noisy, clean_out
+
+
+def time_to_spec_mask(mask_time: torch.Tensor, T_frames: int, win_length: int, hop_length: int, center: bool = True):
+    """Batched AudioInpaintingDataset.time_to_spec_mask (dataset/audio_dataset_inpainting.py:223-251): mask_time [B,L] (1 = keep)
+    -> [B,T_frames] with 1 where the whole analysis window of the frame is unmasked."""
+    mask_time = _f32(mask_time)
+    _chk(mask_time)
+    B, L = mask_time.shape
+    out = torch.empty(B, T_frames, device=mask_time.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_time_to_spec_mask(mask_time.data_ptr(), B, L, T_frames, win_length, hop_length, int(center),
+                                                  out.data_ptr(), _stream()), "nppc_time_to_spec_mask")
+    return out
+
+
 TC_ROW_TILE = 128  # the tensor-core LSTM owns 128 sequences per CTA; its time-major buffers pad rows to this
 
 

@@ -73,6 +73,18 @@ int nppc_pc_variations(const float* w_mat, const float* noisy_real, const float*
                        float* pc_imag, float* var_real, float* var_imag, void* stream);
 int nppc_peak_normalize(float* x, int rows, int L, void* stream);
 
+/* ---- N3: GPU data preparation (batched versions of the reference's per-item CPU dataset code) -------------------
+ * nppc_mix_with_snr: AudioDataset._normalize_audio + _mix_with_snr (dataset/audio_dataset.py:92-158): clean' = clean
+ *   RMS-normalised to target_db[b] dBFS, noisy = clean' + noise * sqrt(P_clean' / (10^(snr_db[b]/10) P_noise + 1e-8)),
+ *   both scaled by 0.99 / max|noisy| when that peak exceeds 0.99.  clean / noise [B,L]; scratch: nppc_mix_scratch_bytes(B).
+ * nppc_time_to_spec_mask: AudioInpaintingDataset.time_to_spec_mask (dataset/audio_dataset_inpainting.py:223-251):
+ *   out[b,t] = 1 iff min(mask_time[b, window of frame t]) == 1 (window clipped to [0,L); empty window -> 0). */
+size_t nppc_mix_scratch_bytes(int B);
+int nppc_mix_with_snr(const float* clean, const float* noise, int B, int L, const float* snr_db, const float* target_db,
+                      void* scratch, float* noisy, float* clean_out, void* stream);
+int nppc_time_to_spec_mask(const float* mask_time, int B, int L, int T_frames, int win_length, int hop_length, int center,
+                           float* out, void* stream);
+
 /* ---- a2: laplace norms --------------------------------------------------------------------------
  * offline_laplace_norm (audio_zen/model/base_model.py:210-224): y = x / (mean_{per sample}(x) + 1e-5).
  * x [B, n] -> y [B, n] (n = C*F*T).  `sums` is a [B] fp64 scratch (device). In-place (y == x) allowed. */

@@ -531,3 +531,38 @@ def pc_variations(w_mat, noisy_real, noisy_imag, enh_real, enh_imag, alphas, len
         w = w / (w.abs().amax(dim=-1, keepdim=True) + 1e-8)
         out.append(w.reshape(B, n, -1))
     return pc_re, pc_im, torch.stack(out, dim=2)
+
+
+# --------------------------------------------------------------------------------------------
+# N3  data preparation (batched restatement of the reference's per-item dataset code)
+# --------------------------------------------------------------------------------------------
+def mix_with_snr(clean, noise, snr_db, target_db):
+    """dataset/audio_dataset.py:92-108 (_normalize_audio, fixed target level) + :134-158 (_mix_with_snr), per row of [B,L]."""
+    outs_n, outs_c = [], []
+    for b in range(clean.shape[0]):
+        c, n = clean[b:b + 1], noise[b:b + 1]
+        rms = c.pow(2).mean().sqrt()
+        gain = 10 ** ((float(target_db[b]) - 20 * torch.log10(rms + 1e-8)) / 20)
+        c = c * gain
+        scale = torch.sqrt(c.pow(2).mean() / (10 ** (float(snr_db[b]) / 10) * n.pow(2).mean() + 1e-8))
+        noisy = c + n * scale
+        mx = noisy.abs().max()
+        if mx > 0.99:
+            noisy, c = noisy * (0.99 / mx), c * (0.99 / mx)
+        outs_n.append(noisy[0])
+        outs_c.append(c[0])
+    return torch.stack(outs_n), torch.stack(outs_c)
+
+
+def time_to_spec_mask(mask_time, T_frames, win_length, hop_length, center=True):
+    """dataset/audio_dataset_inpainting.py:223-251, per row of mask_time [B,L]."""
+    B, L = mask_time.shape
+    out = torch.zeros(B, T_frames)
+    for b in range(B):
+        for t in range(T_frames):
+            start = t * hop_length - (win_length // 2 if center else 0)
+            end = min(start + win_length, L)
+            start = max(start, 0)
+            if end > start:
+                out[b, t] = float(mask_time[b, start:end].min() == 1)
+    return out
