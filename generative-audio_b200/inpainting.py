@@ -62,10 +62,15 @@ class _DoubleConv(nn.Module):
             self._fold, self._fold_key = out, key
         return self._fold
 
+    mc_dropout = False   # MC-dropout inference (utils.enable_dropout, utils.py:334-338): Dropout layers stay active in eval
+
     def forward(self, x):
         (w0, b0), (w1, b1) = self._folded()
         x = F.leaky_relu(F.conv2d(x, w0, b0, padding=1), 0.2, inplace=True)
-        return F.leaky_relu(F.conv2d(x, w1, b1, padding=1), 0.2, inplace=True)
+        x = F.leaky_relu(F.conv2d(x, w1, b1, padding=1), 0.2, inplace=True)
+        if self.mc_dropout and len(self.conv) > 6:
+            x = F.dropout(x, self.conv[6].p, training=True)
+        return x
 
 
 class _InConv(nn.Module):
@@ -253,3 +258,61 @@ class InpaintingNPPCStep:
         log = dict(w_mat=w_mat, err_norm=st["err_norm"], err_proj=st["err_proj"], w_norms=st["w_norms"],
                    reconst_err=st["reconst_err"], second_moment_mse=st["second_moment_mse"], objective=objective)
         return st["reconst_err"], objective, log
+
+
+# ---- row N4 (second half): the MC-dropout + PCA baseline of the inpainting evaluation, batched on the GPU ----------------
+def enable_dropout(model: nn.Module, on: bool = True):
+    """utils.enable_dropout (utils.py:334-338): keep the Dropout layers of the UNet active at inference time."""
+    for m in model.modules():
+        if isinstance(m, _DoubleConv):
+            m.mc_dropout = on
+
+
+def pca_batch(outputs: torch.Tensor, n_components: int = 5):
+    """utils.compute_pca_sklearn_batch (utils.py:392-470) without leaving the GPU: outputs [K,B,D] -> unit principal
+    components [B,n,D], PCs scaled by their singular values [B,n,D], importance weights S / sum(S) [B,n], mean [B,D],
+    singular values [B,n].  One batched thin SVD of the centred [B,K,D] stack instead of a per-item sklearn PCA on the CPU
+    (exact SVD; sklearn's auto solver is the randomised one for these shapes), with sklearn's sign convention
+    (svd_flip, v-based: the largest-magnitude entry of every component is positive)."""
+    K, B, D = outputs.shape
+    n = min(n_components, K)
+    X = outputs.permute(1, 0, 2).float()
+    mean = X.mean(dim=1)
+    U, S, Vh = torch.linalg.svd(X - mean[:, None, :], full_matrices=False)
+    Vh, S = Vh[:, :n], S[:, :n]
+    idx = Vh.abs().argmax(dim=2, keepdim=True)
+    Vh = Vh * torch.sign(torch.gather(Vh, 2, idx))
+    return Vh, Vh * S[:, :, None], S / S.sum(dim=1, keepdim=True), mean, S
+
+
+@torch.no_grad()
+def calculate_unet_baseline(model: RestorationWrapper, masked_spec: torch.Tensor, mask: torch.Tensor, n_mc_samples: int = 50,
+                            n_components: int = 5, chunk: int = 64):
+    """utils.calculate_unet_baseline (utils.py:545-648): n_mc_samples stochastic passes of the restoration UNet with dropout
+    active, PCA of the predictions inside the gap, results scattered back to full [B,*,F,T] spectrograms (zero outside the
+    gap).  The K passes run as batches of `chunk` samples through one UNet call each; PCA is one batched SVD on the GPU.
+    Every item must mask the same number of bins (as in the reference)."""
+    B, _, Fq, T = masked_spec.shape
+    enable_dropout(model, True)
+    try:
+        reps = masked_spec.repeat(n_mc_samples, 1, 1, 1)   # sample-major: [K*B,1,F,T]
+        mreps = mask.repeat(n_mc_samples, 1, 1, 1)
+        preds = torch.cat([model(reps[i:i + chunk], mreps[i:i + chunk]) for i in range(0, reps.shape[0], chunk)])
+    finally:
+        enable_dropout(model, False)
+    gap = mask.reshape(B, -1) == 0
+    n_gap = int(gap[0].sum())
+    if not bool((gap.sum(dim=1) == n_gap).all()):
+        raise ValueError("every batch item must mask the same number of bins")
+    flat = preds.reshape(n_mc_samples, B, Fq * T)
+    vals = flat[:, gap].reshape(n_mc_samples, B, n_gap)
+    pcs, scaled, weights, mean, svals = pca_batch(vals, n_components)
+
+    def scatter(v):   # [B,n,n_gap] or [B,n_gap] -> full spectrograms, zero in the known region
+        lead = v.shape[1:-1]
+        full = torch.zeros(B, *lead, Fq * T, device=v.device, dtype=v.dtype)
+        full[gap[:, None, :].expand(B, *lead, Fq * T) if lead else gap] = v.reshape(-1)
+        return full.reshape(B, *lead, Fq, T)
+
+    return {"mean_prediction": scatter(mean).unsqueeze(1), "principal_components": scatter(pcs),
+            "scaled_principal_components": scatter(scaled), "importance_weights": weights, "singular_vals": svals}

@@ -39,3 +39,12 @@ def build_model(n_dirs=5, groups=1, impl="f32", seed=0, norm_type="offline_lapla
     m.eval()
     _MODELS[key] = (m, sd)
     return m, sd
+
+
+def pca_samples(seed=0, K=50, B=3, D=2304):
+    """Seeded MC-dropout-like samples [K,B,D] with a decaying spectrum (shared by oracle/make_golden_pca.py and the test)."""
+    rng = np.random.default_rng(seed)
+    basis = rng.standard_normal((B, 6, D))
+    coef = rng.standard_normal((K, B, 6)) * np.array([30, 18, 10, 6, 3, 1.5])
+    x = np.einsum("kbj,bjd->kbd", coef, basis) + 0.05 * rng.standard_normal((K, B, D)) + rng.standard_normal((1, B, D))
+    return torch.from_numpy(x.astype(np.float32))

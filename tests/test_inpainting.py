@@ -116,3 +116,41 @@ def test_inpainting_kernels_vs_oracle():
     c, mm, mean, std = g.ops.logmag_normalize(spec_c.cuda(), spec_m.cuda())
     co, _, mo = O.inpaint_preprocess(spec_c, spec_m, torch.ones(B, T))
     assert rel_err(c.cpu(), co) < 1e-5 and rel_err(mm.cpu(), mo) < 1e-5
+
+
+def test_pca_batch_vs_reference_sklearn():
+    """Row N4 (second half): the batched SVD replacement of the reference's per-item sklearn PCA, on the fixture's seeded samples
+    (CPU tensors: torch.linalg.svd runs on either device; the product path calls it on CUDA tensors)."""
+    import generative_audio_b200 as g
+    from helpers import pca_samples
+    x = pca_samples()
+    gd = load_golden("fn_pca_batch")
+    pcs, scaled, weights, mean, svals = g.inpainting.pca_batch(x, 5)
+    assert rel_err(svals, gd["svals"]) < 1e-4 and rel_err(weights, gd["weights"]) < 1e-4 and rel_err(mean, gd["mean"]) < 1e-5
+    assert rel_err(pcs, gd["pcs"]) < 1e-3 and rel_err(scaled, gd["scaled"]) < 1e-3
+
+
+@pytest.mark.gpu
+def test_mc_dropout_baseline():
+    import generative_audio_b200 as g
+    I = g.inpainting
+    gd = load_golden("inpaint_model_b2")
+    net = I.UNet(I.UNetConfig(in_channels=1, out_channels=1, dropout=0.2))
+    net.load_state_dict(weights.synth_unet_state_dict(_shapes(net), 0, "rest."))
+    model = I.RestorationWrapper(net.cuda().eval())
+    clean_n, m4, masked_n = I.preprocess_data(gd["clean_spec"].cuda(), gd["masked_spec"].cuda(), gd["mask"].cuda())
+    det = model(masked_n, m4)
+    assert rel_err(det.cpu(), gd["pred"]) < 1e-4          # dropout layers exist but are off: same as the p = 0 reference run
+    out = I.calculate_unet_baseline(model, masked_n, m4, n_mc_samples=24, n_components=4)
+    B, _, Fq, T = masked_n.shape
+    pcs = out["principal_components"]
+    assert pcs.shape == (B, 4, Fq, T) and out["mean_prediction"].shape == (B, 1, Fq, T)
+    gap = (m4 == 0)
+    assert torch.all(pcs[~gap.expand_as(pcs)] == 0) and torch.all(out["mean_prediction"][~gap] == 0)
+    gram = torch.einsum("bif,bjf->bij", pcs.flatten(2), pcs.flatten(2))
+    assert rel_err(gram.cpu(), torch.eye(4).expand(B, 4, 4)) < 1e-4                  # orthonormal directions
+    assert torch.all(out["singular_vals"][:, :-1] >= out["singular_vals"][:, 1:]) and torch.all(out["singular_vals"] > 0)
+    assert rel_err(out["importance_weights"].sum(dim=1).cpu(), torch.ones(B)) < 1e-5
+    # the MC mean stays close to the deterministic restoration inside the gap, and dropout is switched off again afterwards
+    assert rel_err(out["mean_prediction"].cpu(), (det * gap).cpu()) < 0.5
+    assert torch.equal(model(masked_n, m4), det)
