@@ -63,9 +63,17 @@ class _DoubleConv(nn.Module):
         return self._fold
 
     mc_dropout = False   # MC-dropout inference (utils.enable_dropout, utils.py:334-338): Dropout layers stay active in eval
+    compute_dtype = None  # None = fp32 (parity path); torch.float16 / bfloat16 = 16-bit tensor-core convolutions (set_compute_dtype)
 
     def forward(self, x):
         (w0, b0), (w1, b1) = self._folded()
+        if self.compute_dtype is not None:
+            dt = self.compute_dtype
+            if getattr(self, "_fold16_key", None) != (self._fold_key, dt):
+                self._fold16 = [(w.to(dt).contiguous(memory_format=torch.channels_last), b.to(dt)) for w, b in self._fold]
+                self._fold16_key = (self._fold_key, dt)
+            (w0, b0), (w1, b1) = self._fold16
+            x = x.to(dt).contiguous(memory_format=torch.channels_last)
         x = F.leaky_relu(F.conv2d(x, w0, b0, padding=1), 0.2, inplace=True)
         x = F.leaky_relu(F.conv2d(x, w1, b1, padding=1), 0.2, inplace=True)
         if self.mc_dropout and len(self.conv) > 6:
@@ -147,7 +155,7 @@ class UNet(nn.Module):
         x = self.up2(x, x3)
         x = self.up3(x, x2)
         x = self.up4(x, x1)
-        return self.outc(x)
+        return self.outc(x.float().contiguous())
 
 
 class RestorationWrapper(nn.Module):
@@ -261,6 +269,15 @@ class InpaintingNPPCStep:
 
 
 # ---- row N4 (second half): the MC-dropout + PCA baseline of the inpainting evaluation, batched on the GPU ----------------
+def set_compute_dtype(model: nn.Module, dtype=None):
+    """Throughput option: run the UNet's 3x3 convolutions in fp16 / bf16 (channels-last, tensor cores, fp32 accumulate inside
+    the library kernels); None restores the fp32 parity path.  The 1x1 output convolution and everything outside the UNet
+    stay fp32."""
+    for m in model.modules():
+        if isinstance(m, _DoubleConv):
+            m.compute_dtype = dtype
+
+
 def enable_dropout(model: nn.Module, on: bool = True):
     """utils.enable_dropout (utils.py:334-338): keep the Dropout layers of the UNet active at inference time."""
     for m in model.modules():

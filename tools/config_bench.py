@@ -84,4 +84,13 @@ with torch.no_grad():
     ms = timeit(lambda: mi(masked_n, m4), reps=3, warm=2)
     out["config4_inpainting_b128_ndirs10"] = {"ms_per_step": ms, "audio_s_per_s": B * 4.0 / (ms * 1e-3),
                                               "note": "UNet convolutions on cuDNN (row N4), glue + real Gram-Schmidt on the kernels"}
+    I.set_compute_dtype(mi, torch.float16)
+    w32 = None
+    ms = timeit(lambda: mi(masked_n, m4), reps=3, warm=2)
+    out["config4_inpainting_b128_ndirs10_fp16convs"] = {"ms_per_step": ms, "audio_s_per_s": B * 4.0 / (ms * 1e-3),
+                                                        "note": "same with the UNet convolutions in fp16 channels-last (cuDNN tensor cores)"}
+    w16 = mi(masked_n[:8], m4[:8])
+    I.set_compute_dtype(mi, None)
+    w32 = mi(masked_n[:8], m4[:8])
+    out["config4_inpainting_b128_ndirs10_fp16convs"]["w_mat_rel_err_vs_fp32"] = ((w16 - w32).abs().max() / w32.abs().max()).item()
 print(json.dumps(out, indent=1))
