@@ -95,11 +95,9 @@ __global__ void __launch_bounds__(TPB) spec_mask_kernel(const float* __restrict_
     start = start < 0 ? 0 : start;
     end = end > L ? L : end;
     float mn = 1.0f;
-    bool any = false;
-    for (int i = start + lane; i < end; i += 32) { mn = fminf(mn, mask_time[(size_t)b * L + i]); any = true; }
+    for (int i = start + lane; i < end; i += 32) mn = fminf(mn, mask_time[(size_t)b * L + i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    (void)any;
     if (lane == 0) out[wid] = (end > start && mn == 1.0f) ? 1.0f : 0.0f;
 }
 

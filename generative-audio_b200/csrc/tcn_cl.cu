@@ -216,9 +216,9 @@ extern "C" int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, co
 }
 
 // CTAs per sample: contiguous row chunks, ~4 waves of 8 CTAs/SM over the whole batch, at least 8 rows per CTA
-static int rows_grid(int T, int B) {
+static int rows_grid(int T, int B, int min_rows = 8) {
     int per = nppc::cdiv((long long)nppc::sm_count() * 32, B);
-    int cap = nppc::cdiv(T, 8);
+    int cap = nppc::cdiv(T, min_rows);
     if (per > cap) per = cap;
     return per < 1 ? 1 : per;
 }
@@ -244,7 +244,7 @@ extern "C" int nppc_tcn_mid_cl(const void* y1, int B, int T, int H, const float*
     NPPC_CHECK_ARG(B > 0 && T > 0 && dilation > 0 && B <= 65535 && H == HID, "nppc_tcn_mid_cl: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     NPPC_CUDA_OK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * B, s));
-    tcn_mid_cl_kernel<<<dim3(rows_grid(T, B), B), TPB, 0, s>>>((const __half2*)y1, T, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w,
+    tcn_mid_cl_kernel<<<dim3(rows_grid(T, B), B), TPB, 0, s>>>   /* 16 rows per CTA measured no faster (24.6 vs 23.4 us) */((const __half2*)y1, T, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w,
                                                               dw_b, dilation, prelu2_a, (__half2*)z, stats2);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
