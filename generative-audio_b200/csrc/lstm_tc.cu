@@ -108,7 +108,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 const __grid_constant__ CUtensorMap tmap_hst, const __grid_constant__ CUtensorMap tmap_x,
                 const __grid_constant__ CUtensorMap tmap_wx, const __grid_constant__ CUtensorMap tmap_fc,
                 const uint4* __restrict__ zx, const float* __restrict__ bias, int RS, int Tp,
-                const float* __restrict__ fc_b, int O, int R, float* __restrict__ y, int dbg) {
+                const float* __restrict__ fc_b, int O, int R, float* __restrict__ y, int dbg, int xkk) {
     using S = RecSmem<FUSE_X>;
     constexpr int NST = S::NST;
     constexpr int NP = NSLAB / 2;                  // slab pairs per chunk (one ring stage each)
@@ -351,8 +351,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                                 if (is_x) {
                                     const uint64_t da = umma_desc_k128(x_base);
                                     const uint64_t db = umma_desc_k128(w_base + stage * S::WST_BYTES);
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
+                                    for (int kk = 0; kk < xkk; ++kk)   // only the K = 16 steps that hold real input features
                                         umma_f16_pair(tmem_base + as * 128, da + 2 * kk, db + 2 * kk, idesc, kk != 0);
                                 } else {
 #pragma unroll
@@ -693,13 +692,14 @@ struct FcArgs {
 
 template <bool FUSE_X, bool FUSE_FC>
 int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& thst, const CUtensorMap& tx,
-               const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc, cudaStream_t s) {
+               const CUtensorMap& twx, const void* zx, const float* bias, int RS, int Tp, const FcArgs& fc, cudaStream_t s,
+               int xkk = 4) {
     auto kern = lstm_rec_kernel<FUSE_X, FUSE_FC>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<FUSE_X>::TOTAL));
     const int tiles = RS / ROWS;
     static const int dbg = getenv("NPPC_LSTM_DBG") ? atoi(getenv("NPPC_LSTM_DBG")) : 0;   // timing ablations only (wrong results)
     kern<<<nppc::cdiv(tiles, 2) * 2, NTHREADS, RecSmem<FUSE_X>::TOTAL, s>>>(tw, th, thst, tx, twx, *fc.tfc, (const uint4*)zx, bias,
-                                                                            RS, Tp, fc.fc_b, fc.O, fc.R, fc.y, dbg);
+                                                                            RS, Tp, fc.fc_b, fc.O, fc.R, fc.y, dbg, xkk);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -780,7 +780,7 @@ int lstm_forward_tc(const nppc_lstm_plan* p, const void* xs, int R, int RS, int 
     const bool fc_in_rec = fuse_fc && p->O <= 16;   // fc fused into the last layer's recurrent kernel (mini-chunk per step)
     const FcArgs fc{&tfc, p->fc_b, p->O, R, y};
     if (fuse_x && KP == 64) {
-        rc = launch_rec<true, false>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, fc, s);
+        rc = launch_rec<true, false>(tw[0], th, thst, tx, twx, nullptr, p->bias_p[0], RS, Tp, fc, s, (p->I + 15) / 16);
     } else {
         rc = gemm_16bit_tn(xs, p->wp_ih[0], p->bias_p[0], zx, M, H4, KP, 2, s);
         if (rc) return rc;
