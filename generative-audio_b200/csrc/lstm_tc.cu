@@ -435,6 +435,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             const uint32_t as = j & 1, use = (uint32_t)t * (NCHUNK / 2) + (j >> 1);
             mbar_wait(&acc_full[as], use & 1);
             if (threadIdx.x == 128) TRACE(5);
+            if (threadIdx.x == 256) TRACE(10);
             tcgen05_fence_after();
             const uint32_t t_acc = t_lane + as * 128 + half * 64;
             tmem_ld16(t_acc, g0);
@@ -467,6 +468,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(ae0 + as * 8);   // the stage is in registers: its next MMAs may start
                 if (threadIdx.x == 128) TRACE(6);
+                if (threadIdx.x == 256) TRACE(11);
                 int jn = j + 1, tn = t;
                 if (jn == NCHUNK) { jn = 0; tn = t + 1; }
                 const uint4* zn = zx_ptr(tn < Tp ? tn : t, chunk_of(jn));   // Zx of the next position (clamped at the very end)
@@ -527,6 +529,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 block(g3, 3);
                 tmem_st8(t_lane + S::C_COL + jc * 16 + half * 8, cp);
                 if (threadIdx.x == 128) TRACE(7);
+                if (threadIdx.x == 256) TRACE(12);
                 if (j == NCHUNK - 1) {
                     // acc_full of position 11 was seen: no MMA of this step reads the A operand any more -> positions 10, 11
                     // (the late slab) go straight into it (the store warp fences and publishes them)
@@ -539,6 +542,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     if (lane == 0) mbar_arrive(late_written);
                 }
                 stage_out(hp, t, j);
+                if (threadIdx.x == 128) TRACE(15);
                 if (j == NCHUNK - 1) {
                     tmem_wait_st();   // c of this step is in TMEM before any load of the next step
                     if (FUSE_FC && half == 0) fc_out(t + 1);
@@ -549,6 +553,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     issue_loads(t, j + 1);
                 }
                 if (threadIdx.x == 128) TRACE(8);
+                if (threadIdx.x == 256) TRACE(13);
             }
         }
     }

@@ -29,7 +29,7 @@ lib.nppc_debug_rec_trace.argtypes = [C.c_void_p]
 assert lib.nppc_debug_rec_trace(buf) == 0
 a = np.array(buf, dtype=np.int64).reshape(4, 12, 16)
 t0 = a[0, 0, 0]
-print("MMA: 0 acc_empty ok | 1 w_full[0] ok | 2 w_full[3] ok | 3 w_full[last] ok | 4 commit issued || epi warp4: 5 acc_full seen | 6 arrived acc_empty | 7 math+STTM done | 8 h staged+TMA issued || W producer: 9 w_empty ok (k=0) | 14 w_empty ok (k=last) || 12 staged prev | 10 token | 11 math done | warp8: 13 token | 15 math done")
+print("MMA: 0 acc_empty ok | 1 w_full[0] ok | 3 w_full[last] ok | 4 commit issued || epi warp 4 (half 0): 5 acc_full seen (loads issued next) | 6 wait::ld done, acc_empty arrived | 7 math+STTM done | 15 h staged | 8 next loads issued || W producer: 9 w_empty ok (k=0) | 14 (k=last) || epi warp 8 (half 1, same scheduler): 10 acc_full seen | 11 wait::ld done | 12 math done | 13 next loads issued")
 for t in range(3):
     for j in range(12):
         r = a[t, j] - t0
