@@ -1,7 +1,7 @@
 // Row N2: the full-band TCN stack with its 1x1 convolutions on the tcgen05 GEMM (gemm_tc.cu) instead of the library.
 // A 1x1 Conv1d over [B, C, T'] is a TN GEMM once the activations are CHANNEL-LAST:  Y[b*T'+t, co] = sum_ci X[b*T'+t, ci] W[co, ci]
 // (both operands K-major), so inside the stack everything lives as [M = B*T' rows][channels]:
-//   x32 [M][C]   fp32  residual stream (exact accumulation across the 8 blocks)
+//   x32 [M][Kp]  fp32  residual stream (exact accumulation across the 8 blocks), rows padded like xh (16-byte vectors)
 //   xh  [M][Kp]  fp16  the same values as GEMM A operand, C zero-padded to Kp (multiple of 64)
 //   y1  [M][512] fp16  conv1x1 output WITHOUT bias (bias is applied where y1 is read)
 //   z   [M][512] fp16  PReLU2(depthwise(GroupNorm1(PReLU1(y1 + b1))))                       (causal_conv.py:100-104)
@@ -21,7 +21,17 @@ constexpr int HID = 512;   // TCNBlock hidden width (causal_conv.py:67 default; 
 
 __device__ __forceinline__ float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
 
-// channel-first fp32 [B][C][T] -> x32 [B*T][C] fp32 and xh [B*T][Kp] fp16 (columns >= C are pre-zeroed and never written).
+// GroupNorm(1, 512) moments of a sample from its fp64 (sum, sum of squares): the cancellation-prone part (E[x^2] - mean^2)
+// stays in fp64, the division is a multiplication by the host-computed 1 / (512 T) and the reciprocal square root is the
+// fp32 MUFU one (2 ulp) -- a dozen instructions per thread instead of the ~150 of fp64 division + sqrt.
+__device__ __forceinline__ void moments(const double* __restrict__ st, double inv_n, float& mu, float& rstd) {
+    const double mu_d = st[0] * inv_n;
+    const double var_d = fma(st[1], inv_n, -mu_d * mu_d);
+    mu = (float)mu_d;
+    rstd = rsqrtf(fmaxf((float)var_d, 0.f) + 1e-8f);
+}
+
+// channel-first fp32 [B][C][T] -> x32 [B*T][Kp] fp32 and xh [B*T][Kp] fp16 (columns >= C are pre-zeroed and never written).
 // 32x32 shared-memory transpose tiles; grid (ceil(T/32), ceil(C/32), B), block (32, 8).
 __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp, const float* __restrict__ inv_scale,
                                float* __restrict__ x32, __half* __restrict__ xh) {
@@ -37,7 +47,7 @@ __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp
         if (t < T && c < C) {
             const float v = tile[threadIdx.x][i];
             const size_t row = (size_t)b * T + t;
-            x32[row * C + c] = v;
+            x32[row * Kp + c] = v;
             xh[row * Kp + c] = __float2half_rn(v * inv_scale[b]);
         }
     }
@@ -106,13 +116,11 @@ __global__ void __launch_bounds__(TPB) tcn_mid_cl_kernel(const __half2* __restri
                                                         const float* __restrict__ g1, const float* __restrict__ be1,
                                                         const float* __restrict__ dw_w, const float* __restrict__ dw_b, int dil,
                                                         const float* __restrict__ a2_ptr, __half2* __restrict__ z,
-                                                        double* __restrict__ stats2) {
+                                                        double* __restrict__ stats2, double inv_n) {
     __shared__ double red[32];
     const int b = blockIdx.y, c2 = threadIdx.x;
-    const double n = (double)HID * T;
-    const double mu_d = stats1[2 * b] / n;
-    const double var_d = stats1[2 * b + 1] / n - mu_d * mu_d;
-    const float mu = (float)mu_d, rstd = (float)(1.0 / sqrt(fmax(var_d, 0.0) + 1e-8));
+    float mu, rstd;
+    moments(stats1 + 2 * b, inv_n, mu, rstd);
     const float a1 = *a1_ptr, a2 = *a2_ptr, sb = scale[b];
     float sc[2], sh[2], k0[2], k1[2], k2[2], kb[2], bb[2];
 #pragma unroll
@@ -156,44 +164,59 @@ __global__ void __launch_bounds__(TPB) tcn_mid_cl_kernel(const __half2* __restri
 }
 
 // x32 <- x32 + o * rstd + (vb - mean * rstd * u); xh <- fp16(x32 / scale) or fp16(relu(x32) / scale) (last block: the stack's
-// trailing ReLU).  thread = channel (per-channel constant hoisted, accesses coalesced along c), each CTA owns a contiguous
-// run of rows with 4 independent rows in flight; grid (row chunks, B).
-constexpr int OUT_TPB = 288;   // 9 warps: one pass covers C = 257, two passes C = 514
+// trailing ReLU).  thread = (row lane, 4 consecutive channels): x32 rows are padded to Kp floats, so every access is a 16-byte
+// (fp32) or 8-byte (fp16) vector; the per-channel constants of the quad stay in registers while the thread walks down its rows.
+// grid (row chunks, B).  Channels >= C of the last quad: xh stays zero (GEMM K padding), x32 padding is never read as data.
+constexpr int OUT_TPB = 288;
 __global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __restrict__ o, float* __restrict__ x32, int T, int C, int Np,
                                                             int Kp, const double* __restrict__ stats2, const float* __restrict__ u,
                                                             const float* __restrict__ vb, const float* __restrict__ inv_scale,
-                                                            __half* __restrict__ xh, int relu_h) {
+                                                            __half* __restrict__ xh, int relu_h, double inv_n) {
     const int b = blockIdx.y;
+    const int CQ = (C + 3) >> 2;                 // channel quads per row
+    const int RL = OUT_TPB / CQ;                 // rows worked on side by side (host checks RL >= 1)
+    const int cq = threadIdx.x % CQ, rl = threadIdx.x / CQ;
+    if (rl >= RL) return;
     const float is = inv_scale[b];
-    const double n = (double)HID * T;
-    const double mu_d = stats2[2 * b] / n;
-    const double var_d = stats2[2 * b + 1] / n - mu_d * mu_d;
-    const float rstd = (float)(1.0 / sqrt(fmax(var_d, 0.0) + 1e-8));
-    const float mr = (float)mu_d * rstd;
+    float mu, rstd;
+    moments(stats2 + 2 * b, inv_n, mu, rstd);
+    const float mr = mu * rstd;
+    const float lo = relu_h ? 0.f : -3.0e38f;    // trailing ReLU of the stack (last block) as a lower clamp
     const int rows = (T + gridDim.x - 1) / gridDim.x, tb = blockIdx.x * rows, te = min(T, tb + rows);
-    for (int c = threadIdx.x; c < C; c += OUT_TPB) {
-        const float kc = vb[c] - mr * u[c];
-        for (int t = tb; t < te; t += 4) {
-            float xv[4];
-            __half ov[4];
+    const int c0 = cq * 4;
+    float kc[4];
+    bool ok[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (t + q < te) {
-                    const size_t row = (size_t)b * T + t + q;
-                    xv[q] = x32[row * C + c];
-                    ov[q] = o[row * Np + c];
-                }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (t + q < te) {
-                    const size_t row = (size_t)b * T + t + q;
-                    const float v = xv[q] + __half2float(ov[q]) * rstd + kc;
-                    x32[row * C + c] = v;
-                    const float h = relu_h ? fmaxf(v, 0.f) : v;
-                    xh[row * Kp + c] = __float2half_rn(fminf(fmaxf(h * is, -65504.f), 65504.f));
-                }
-        }
+    for (int e = 0; e < 4; ++e) {
+        ok[e] = c0 + e < C;
+        kc[e] = ok[e] ? vb[c0 + e] - mr * u[c0 + e] : 0.f;
     }
+    const size_t r0 = (size_t)b * T + tb + rl;
+    float4* xp = reinterpret_cast<float4*>(x32 + r0 * Kp + c0);
+    const uint2* op = reinterpret_cast<const uint2*>(o + r0 * Np + c0);
+    uint2* hp = reinterpret_cast<uint2*>(xh + r0 * Kp + c0);
+    const int sx = RL * Kp / 4, so = RL * Np / 4;   // strides between this thread's consecutive rows, in vectors
+    auto finish = [&](float4 xv, uint2 ov, float4* xd, uint2* hd) {
+        const float2 o01 = __half22float2(*reinterpret_cast<const __half2*>(&ov.x));
+        const float2 o23 = __half22float2(*reinterpret_cast<const __half2*>(&ov.y));
+        float v[4] = {fmaf(o01.x, rstd, xv.x) + kc[0], fmaf(o01.y, rstd, xv.y) + kc[1], fmaf(o23.x, rstd, xv.z) + kc[2],
+                      fmaf(o23.y, rstd, xv.w) + kc[3]};
+        float h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = ok[e] ? fminf(fmaxf(fmaxf(v[e], lo) * is, -65504.f), 65504.f) : 0.f;
+        *xd = make_float4(v[0], v[1], v[2], v[3]);
+        const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
+        *hd = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    };
+    int nr = (te - tb - rl + RL - 1) / RL;   // rows of this chunk that fall on this row lane
+    for (; nr >= 2; nr -= 2) {               // two independent rows in flight
+        const float4 xa = xp[0], xb = xp[sx];
+        const uint2 oa = __ldg(op), ob = __ldg(op + so);
+        finish(xa, oa, xp, hp);
+        finish(xb, ob, xp + sx, hp + sx);   // x32 (float4) and xh (4 halves) rows have the same stride in vectors: Kp / 4
+        xp += 2 * sx; op += 2 * so; hp += 2 * sx;
+    }
+    if (nr > 0) finish(xp[0], __ldg(op), xp, hp);
 }
 }  // namespace
 
@@ -244,8 +267,10 @@ extern "C" int nppc_tcn_mid_cl(const void* y1, int B, int T, int H, const float*
     NPPC_CHECK_ARG(B > 0 && T > 0 && dilation > 0 && B <= 65535 && H == HID, "nppc_tcn_mid_cl: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     NPPC_CUDA_OK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * B, s));
-    tcn_mid_cl_kernel<<<dim3(rows_grid(T, B), B), TPB, 0, s>>>   /* 16 rows per CTA measured no faster (24.6 vs 23.4 us) */((const __half2*)y1, T, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w,
-                                                              dw_b, dilation, prelu2_a, (__half2*)z, stats2);
+    // measured and rejected: 16 rows per CTA; computing n(t) once per row into a shared-memory window (dil 9 gets slower,
+    // net -6 %); 4 channels per thread; per-warp REDs instead of the block reduction.  The CTA's fixed costs dominate.
+    tcn_mid_cl_kernel<<<dim3(rows_grid(T, B), B), TPB, 0, s>>>((const __half2*)y1, T, scale, bias1, prelu1_a, stats1, gamma1, beta1, dw_w,
+                                                              dw_b, dilation, prelu2_a, (__half2*)z, stats2, 1.0 / ((double)HID * T));
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -255,7 +280,9 @@ extern "C" int nppc_tcn_out_cl(const void* o, float* x32, int B, int T, int C, i
                                const float* u, const float* vb, const float* inv_scale, void* xh, int relu_h, void* stream) {
     NPPC_CHECK_ARG(o && x32 && stats2 && u && vb && inv_scale && xh && B > 0 && T > 0 && C > 0 && Np >= C && Kp >= C && B <= 65535 && H == HID,
                    "nppc_tcn_out_cl: bad arguments");
-    tcn_out_cl_kernel<<<dim3(rows_grid(T, B), B), OUT_TPB, 0, (cudaStream_t)stream>>>((const __half*)o, x32, T, C, Np, Kp, stats2, u, vb, inv_scale, (__half*)xh, relu_h);
+    NPPC_CHECK_ARG(Kp % 4 == 0 && Np % 4 == 0 && (C + 3) / 4 <= OUT_TPB, "nppc_tcn_out_cl: Kp, Np must be multiples of 4 and C <= %d", 4 * OUT_TPB);
+    tcn_out_cl_kernel<<<dim3(rows_grid(T, B), B), OUT_TPB, 0, (cudaStream_t)stream>>>((const __half*)o, x32, T, C, Np, Kp, stats2, u, vb, inv_scale, (__half*)xh, relu_h,
+                                                                                          1.0 / ((double)HID * T));
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

@@ -156,7 +156,7 @@ class SequenceModel(nn.Module):
         B, C, T = x.shape
         M = B * T
         dev = x.device
-        x32 = torch.empty(M, C, device=dev, dtype=torch.float32)
+        x32 = torch.empty(M, pl["Kp"], device=dev, dtype=torch.float32)   # residual stream, rows padded like xh
         xh = torch.zeros(M, pl["Kp"], device=dev, dtype=torch.float16)
         # per-sample fp16 scale: the real / imag streams are normalised by a cancelling mean and can be huge (see tcn_cl.cu)
         scale = x.abs().amax(dim=(1, 2)).clamp_min(1e-30).float().contiguous()

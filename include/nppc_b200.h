@@ -215,7 +215,7 @@ int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, l
  * (audio_zen/model/module/causal_conv.py:96-108, sequence_model.py:47-58,106-112).  M = B*T' rows, row = b*T' + t.
  * fp16 range: xh holds x / scale[b] (scale[b] = max|x| of the sample on entry, inv_scale = 1/scale); y1 and the final Linear
  * are multiplied back by scale[b] in fp32 where they are read.
- * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,C] f32 (residual stream) and xh [M,Kp] fp16 (GEMM operand; columns >= C
+ * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,Kp] f32 (residual stream, rows padded like xh) and xh [M,Kp] fp16 (GEMM operand; columns >= C
  *                      must be zero on entry and stay zero).
  * nppc_prelu_stats_cl: stats[b] = (sum, sum^2) of PReLU(y1 + bias[c]) over the sample, y1 [M,512] fp16.
  * nppc_tcn_mid_cl:     z [M,512] fp16 = PReLU2(depthwise_dilated(GroupNorm1(PReLU1(y1 + bias1)))), stats2 = moments of z.
