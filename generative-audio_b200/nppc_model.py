@@ -55,6 +55,31 @@ class NPPCModel(nn.Module):
         return ops.gram_schmidt_complex(head)
 
     @torch.no_grad()
+    def forward_host(self, noisy_host: torch.Tensor, out_host: torch.Tensor = None) -> torch.Tensor:
+        """Serving loop entry: PINNED host waveform [B, L] -> PINNED host w_mat [B, n_dirs, 2, F', T].
+        The upload and the kernels run on the current stream; the download of w_mat (165 MB at B = 64) is queued on a side
+        stream behind them, so it overlaps the NEXT call's compute instead of stalling it.  Returns out_host immediately;
+        its contents are valid after `self.host_copy_done()` (or any device synchronise)."""
+        dev = next(self.parameters()).device
+        if not (noisy_host.is_pinned() and (out_host is None or out_host.is_pinned())):
+            raise ValueError("forward_host needs pinned host tensors (torch.Tensor.pin_memory())")
+        w = self.forward(noisy_host.to(dev, non_blocking=True))
+        if out_host is None:
+            out_host = torch.empty(w.shape, dtype=w.dtype).pin_memory()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._copy_stream):
+            out_host.copy_(w, non_blocking=True)
+        w.record_stream(self._copy_stream)
+        return out_host
+
+    def host_copy_done(self):
+        """Block the host until every download queued by forward_host has landed."""
+        if getattr(self, "_copy_stream", None) is not None:
+            self._copy_stream.synchronize()
+
+    @torch.no_grad()
     def get_pred_crm(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
         """compressed cRM of the frozen backbone, [B,2,F,T] (nppc_model.py:117-132)."""
         mag, real, imag = self._stft(noisy_waveform)

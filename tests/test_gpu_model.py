@@ -152,3 +152,16 @@ def test_ragged_lengths_and_batches(B, L, seed):
         assert rel_err(w.cpu(), ref) < tol_w, impl
         enh_ref = O.enhance(O._sub(sd, "pretrained_restoration_model."), x)
         assert rel_err(m.enhance(x.cuda()).cpu(), enh_ref) < tol_e, impl
+
+
+def test_forward_host_pipelined_download_matches_forward():
+    """Serving entry point: pinned host in, pinned host out, the download on a side stream.  Two back-to-back calls into
+    different output buffers (the second call's kernels overlap the first download) must both equal NPPCModel.forward."""
+    m, _ = build_model(5, 1, "f32")
+    xa, xb = wave(2, 16000, 3).pin_memory(), wave(2, 16000, 4).pin_memory()
+    oa = m.forward_host(xa)
+    ob = m.forward_host(xb)
+    m.host_copy_done()
+    assert oa.is_pinned() and torch.equal(oa, m(xa.cuda()).cpu()) and torch.equal(ob, m(xb.cuda()).cpu())
+    with pytest.raises(ValueError):
+        m.forward_host(wave(2, 16000, 3))   # pageable host memory: refused, no silent synchronous copy
