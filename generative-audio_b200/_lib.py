@@ -54,6 +54,7 @@ PROTOTYPES = {
     "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "nppc_gemm_f16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
+    "nppc_tcn_cl_scale": (_i, [_p, _i, _ll, _p, _p, _p]),
     "nppc_tcn_cl_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_tcn_cl_unpack": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p]),
     "nppc_prelu_stats_cl": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -31,7 +31,7 @@ __device__ __forceinline__ void moments(const double* __restrict__ st, double in
     rstd = rsqrtf(fmaxf((float)var_d, 0.f) + 1e-8f);
 }
 
-// channel-first fp32 [B][C][T] -> x32 [B*T][Kp] fp32 and xh [B*T][Kp] fp16 (columns >= C are pre-zeroed and never written).
+// channel-first fp32 [B][C][T] -> x32 [B*T][Kp] fp32 and xh [B*T][Kp] fp16 (columns [C, Kp) of xh are written as zeros).
 // 32x32 shared-memory transpose tiles; grid (ceil(T/32), ceil(C/32), B), block (32, 8).
 __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp, const float* __restrict__ inv_scale,
                                float* __restrict__ x32, __half* __restrict__ xh) {
@@ -44,12 +44,48 @@ __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int t = t0 + i, c = c0 + threadIdx.x;
-        if (t < T && c < C) {
+        if (t < T && c < Kp) {   // columns [C, Kp) of xh are the GEMM's K padding: written as zeros here (no separate fill)
             const float v = tile[threadIdx.x][i];
             const size_t row = (size_t)b * T + t;
-            x32[row * Kp + c] = v;
+            if (c < C) x32[row * Kp + c] = v;
             xh[row * Kp + c] = __float2half_rn(v * inv_scale[b]);
         }
+    }
+}
+
+// per-sample fp16 range scale: scale[b] = max(max |x[b]|, 1e-30), inv_scale[b] = 1 / scale[b].  grid (chunks, B): every CTA folds
+// its slice into the sample's maximum with one atomicMax on the float's bit pattern (non-negative floats order like unsigned
+// integers; the slot is zeroed first), a B-thread kernel then clamps and inverts.
+__global__ void __launch_bounds__(TPB) absmax_cl_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ bits) {
+    __shared__ float red[TPB / 32];
+    const float* xb = x + (size_t)blockIdx.y * n;
+    const long long per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    long long i = i0 + threadIdx.x;
+    for (; i + 3 * TPB < i1; i += 4 * TPB) {   // four independent loads in flight
+        m0 = fmaxf(m0, fabsf(xb[i]));
+        m1 = fmaxf(m1, fabsf(xb[i + TPB]));
+        m2 = fmaxf(m2, fabsf(xb[i + 2 * TPB]));
+        m3 = fmaxf(m3, fabsf(xb[i + 3 * TPB]));
+    }
+    for (; i < i1; i += TPB) m0 = fmaxf(m0, fabsf(xb[i]));
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < TPB / 32; ++w) m = fmaxf(m, red[w]);
+        atomicMax(bits + blockIdx.y, __float_as_uint(m));
+    }
+}
+__global__ void scale_finish_kernel(int B, float* __restrict__ scale, float* __restrict__ inv_scale) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        float sc = fmaxf(scale[b], 1e-30f);   // (fmaxf drops NaNs: a NaN input still poisons the output through the GEMMs)
+        scale[b] = sc;
+        inv_scale[b] = 1.0f / sc;
     }
 }
 
@@ -220,10 +256,26 @@ __global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __res
 }
 }  // namespace
 
+extern "C" int nppc_tcn_cl_scale(const float* x, int B, long long n_per_sample, float* scale, float* inv_scale, void* stream) {
+    NPPC_CHECK_ARG(x && scale && inv_scale && B > 0 && n_per_sample > 0, "nppc_tcn_cl_scale: bad arguments");
+    NPPC_CHECK_ARG(B <= 65535, "nppc_tcn_cl_scale: B too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    NPPC_CUDA_OK(cudaMemsetAsync(scale, 0, sizeof(float) * B, s));
+    int chunks = nppc::cdiv((long long)nppc::sm_count() * 4, B);
+    const int cap = (int)((n_per_sample + 4 * TPB - 1) / (4 * TPB));   // at least one full 4-load round per CTA
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    absmax_cl_kernel<<<dim3(chunks, B), TPB, 0, s>>>(x, n_per_sample, reinterpret_cast<unsigned int*>(scale));
+    scale_finish_kernel<<<nppc::cdiv(B, 128), 128, 0, s>>>(B, scale, inv_scale);
+    NPPC_COUNT_LAUNCH(2);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
 extern "C" int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh,
                                 void* stream) {
     NPPC_CHECK_ARG(x && inv_scale && x32 && xh && B > 0 && C > 0 && T > 0 && Kp >= C && B <= 65535, "nppc_tcn_cl_pack: bad arguments");
-    pack_cl_kernel<<<dim3(nppc::cdiv(T, 32), nppc::cdiv(C, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, C, T, Kp, inv_scale, x32, (__half*)xh);
+    pack_cl_kernel<<<dim3(nppc::cdiv(T, 32), nppc::cdiv(Kp, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, C, T, Kp, inv_scale, x32, (__half*)xh);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

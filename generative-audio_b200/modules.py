@@ -157,11 +157,11 @@ class SequenceModel(nn.Module):
         M = B * T
         dev = x.device
         x32 = torch.empty(M, pl["Kp"], device=dev, dtype=torch.float32)   # residual stream, rows padded like xh
-        xh = torch.zeros(M, pl["Kp"], device=dev, dtype=torch.float16)
+        xh = torch.empty(M, pl["Kp"], device=dev, dtype=torch.float16)   # K padding columns are zeroed by the pack kernel
         # per-sample fp16 scale: the real / imag streams are normalised by a cancelling mean and can be huge (see tcn_cl.cu)
-        scale = x.abs().amax(dim=(1, 2)).clamp_min(1e-30).float().contiguous()
-        inv_scale = (1.0 / scale).contiguous()
-        ops.tcn_cl_pack(x.contiguous(), pl["Kp"], inv_scale, x32, xh)
+        x = x.contiguous()
+        scale, inv_scale = ops.tcn_cl_scale(x)
+        ops.tcn_cl_pack(x, pl["Kp"], inv_scale, x32, xh)
         blocks = [m for m in self.sequence_model if isinstance(m, TCNBlock)]
         for i, (blk, (w1, w2, u, vb)) in enumerate(zip(blocks, pl["blocks"])):
             y1 = ops.gemm_f16_tn(xh, w1)

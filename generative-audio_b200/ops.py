@@ -494,6 +494,17 @@ def gemm_f16_tn(a: torch.Tensor, w: torch.Tensor, bias=None):
     return c
 
 
+def tcn_cl_scale(x: torch.Tensor):
+    """per-sample fp16 range scale of x [B, ...] f32: (scale [B], inv_scale [B]) with scale = max(max|x[b]|, 1e-30)."""
+    _chk(x)
+    B = x.shape[0]
+    scale = torch.empty(B, device=x.device, dtype=torch.float32)
+    inv = torch.empty_like(scale)
+    _lib.check(_lib.load().nppc_tcn_cl_scale(x.data_ptr(), B, x[0].numel(), scale.data_ptr(), inv.data_ptr(), _stream()),
+               "nppc_tcn_cl_scale")
+    return scale, inv
+
+
 def tcn_cl_pack(x: torch.Tensor, Kp: int, inv_scale: torch.Tensor, x32: torch.Tensor, xh: torch.Tensor):
     _chk(x, inv_scale, x32, xh)
     B, C, T = x.shape

@@ -222,6 +222,8 @@ int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, l
  * nppc_tcn_out_cl:     x32 += o*rstd2 + vb - mean2*rstd2*u (o [M,Np] fp16 = z*(W2 diag(gamma2))^T); xh = fp16(x32), or
  *                      fp16(relu(x32)) when relu_h (the stack's trailing ReLU before fc_output_layer).
  * nppc_tcn_cl_unpack:  o [M,Np] fp16 (+bias, optional ReLU) -> [B,C,T'] f32. */
+/* per-sample fp16 range scale of a [B, n_per_sample] f32 tensor: scale[b] = max(max|x[b]|, 1e-30), inv_scale[b] = 1/scale[b] */
+int nppc_tcn_cl_scale(const float* x, int B, long long n_per_sample, float* scale, float* inv_scale, void* stream);
 int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh, void* stream);
 int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, const float* scale /* [B] or NULL */, const float* bias,
                        int relu, float* out, void* stream);
