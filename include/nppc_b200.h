@@ -215,14 +215,14 @@ int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, l
  * (audio_zen/model/module/causal_conv.py:96-108, sequence_model.py:47-58,106-112).  M = B*T' rows, row = b*T' + t.
  * fp16 range: xh holds x / scale[b] (scale[b] = max|x| of the sample on entry, inv_scale = 1/scale); y1 and the final Linear
  * are multiplied back by scale[b] in fp32 where they are read.
- * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,Kp] f32 (residual stream, rows padded like xh) and xh [M,Kp] fp16 (GEMM operand; columns >= C
- *                      must be zero on entry and stay zero).
+ * nppc_tcn_cl_scale:   scale[b] = max(max|x[b]|, 1e-30), inv_scale[b] = 1/scale[b] of a [B, n_per_sample] f32 tensor (two launches).
+ * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,Kp] f32 (residual stream, rows padded like xh; padding never read) and xh [M,Kp]
+ *                      fp16 (GEMM operand; the K-padding columns [C,Kp) are written as zeros here and stay zero).
  * nppc_prelu_stats_cl: stats[b] = (sum, sum^2) of PReLU(y1 + bias[c]) over the sample, y1 [M,512] fp16.
  * nppc_tcn_mid_cl:     z [M,512] fp16 = PReLU2(depthwise_dilated(GroupNorm1(PReLU1(y1 + bias1)))), stats2 = moments of z.
  * nppc_tcn_out_cl:     x32 += o*rstd2 + vb - mean2*rstd2*u (o [M,Np] fp16 = z*(W2 diag(gamma2))^T); xh = fp16(x32), or
  *                      fp16(relu(x32)) when relu_h (the stack's trailing ReLU before fc_output_layer).
  * nppc_tcn_cl_unpack:  o [M,Np] fp16 (+bias, optional ReLU) -> [B,C,T'] f32. */
-/* per-sample fp16 range scale of a [B, n_per_sample] f32 tensor: scale[b] = max(max|x[b]|, 1e-30), inv_scale[b] = 1/scale[b] */
 int nppc_tcn_cl_scale(const float* x, int B, long long n_per_sample, float* scale, float* inv_scale, void* stream);
 int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh, void* stream);
 int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, const float* scale /* [B] or NULL */, const float* bias,
