@@ -96,6 +96,41 @@ def cpu_reference_run(steps, warmup, batch_cpu):
                 sample=f"{steps} x NPPCModel.forward on {batch_cpu} synthetic 4 s utterances, fp32, torch CPU, {cores} threads")
 
 
+def gpu_eager_run(batch, steps=3, warmup=2):
+    """SURVEY.md §0.1 / §8(d) bar: the reference's own Blackwell path = the same torch-eager code on `cuda` (fp32, cuDNN LSTM,
+    cuFFT STFT, library conv/GEMM), here the oracle port with its tensors on the device (fast=True -> nn.LSTM-equivalent
+    aten::lstm -> cuDNN).  Same workload (B x 4 s, n_dirs = 5), CUDA-event timed, inputs resident."""
+    import torch
+
+    import nppc_oracle as O
+    import weights
+    from helpers import wave
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prev_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False   # the reference never enables TF32: plain fp32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            sd = {k: v.to(dev) for k, v in weights.synth_state_dict(N_DIRS, 0).items()}
+            x = wave(batch, L, 1000).to(dev)
+            for _ in range(warmup):
+                O.nppc_forward(sd, x, n_dirs=N_DIRS, fast=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                O.nppc_forward(sd, x, n_dirs=N_DIRS, fast=True)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev_tf32
+        torch.cuda.empty_cache()
+    return {"value": batch * L / SR / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+            "warmup": warmup, "what": "reference's torch-eager path on the same B200 (oracle port on cuda: fp32, TF32 off, "
+                                      "cuDNN LSTM, cuFFT, library convolutions), device-resident input"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -106,6 +141,7 @@ def main():
     ap.add_argument("--lstm-impl", default=os.environ.get("NPPC_LSTM_IMPL", "tc"), choices=["tc", "f32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline leg (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,13 +155,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-        r = cpu_reference_run(steps, warmup, args.cpu_batch)
+        # EXACTLY K timed + W warm-up steps like our arm; each step is a bounded SAMPLE of the workload: --cpu-batch of the
+        # 64 utterances a step holds (audio-s/s is per audio-second, so the sample's throughput is the workload's; B = 64
+        # on these host cores would be ~25 s per step).  `config` is our arm's; what actually ran is in `sample` below.
+        r = cpu_reference_run(args.steps, args.warmup, args.cpu_batch)
         line = {"metric": METRIC, "value": r["value"], "unit": "audio-s/s", "impl": "reference", "n_gpus": args.gpus,
-                "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, reference_arm="reference CPU path via the oracle port (reference is Python; "
-                                                      "/root/reference does not travel to the GPU box)"),
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "sample": {"batch_per_step": args.cpu_batch, "of_batch": args.batch,
+                           "note": f"each reference step runs {args.cpu_batch} of the {args.batch} utterances of a step (bounded sample); "
+                                   "reference CPU path via the oracle port, fast=True -> ATen fused CPU LSTM (the reference is Python "
+                                   "and /root/reference does not travel to the GPU box)"},
                 "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port",
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,6 +269,17 @@ def main():
     _, ms_step = aggregate_throughput(B * L / SR, ms_total / args.steps)
     _, ms_e2e_step = aggregate_throughput(B * L / SR, ms_e2e / args.steps)
     audio_s = B * world * L / SR
+    per_rank = None
+    if world > 1:   # which GPU is the slow one, and at what clock (the line's ms_per_step is the MAX over ranks)
+        mine = torch.tensor([ms_total / args.steps, ms_e2e / args.steps, float(sampler.summary()["sm_mhz"] or 0)],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu()
+        ms_r = sorted(allr[:, 0].tolist())
+        per_rank = {"ms_per_step": [round(v, 3) for v in allr[:, 0].tolist()], "ms_per_step_e2e": [round(v, 3) for v in allr[:, 1].tolist()],
+                    "sm_mhz": [int(v) for v in allr[:, 2].tolist()], "ms_min": ms_r[0], "ms_median": ms_r[len(ms_r) // 2],
+                    "ms_max": ms_r[-1]}
     lstm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in lstm_events) / max(len(lstm_events), 1)
     R, Tp = (lstm_events[0][2], lstm_events[0][3]) if lstm_events else (B * F, TP)
     flops = LSTM_FLOP_PER_SEQ_STEP * R * Tp
@@ -254,8 +305,15 @@ def main():
             "e2e": {"value": audio_s / (ms_e2e_step * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_step,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary()}
+    if per_rank is not None:
+        line["per_rank"] = per_rank
+    if not args.no_gpu_eager and world == 1:
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_run(B)
+        except Exception as e:   # reported, never fatal: it is a side-by-side bar, not the product
+            line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(2, 1, args.cpu_batch)
+        r = cpu_reference_run(3, 1, args.cpu_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
     if world > 1:

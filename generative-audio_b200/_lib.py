@@ -73,12 +73,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("_nppc_build", os.path.join(HERE, "build.py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        mod.build()
+    # Always go through build.build(): it is a sha256 stamp compare of csrc/ + the header + the flags when the library is
+    # current, and a rebuild when any source changed (a stale .so from an older commit must never be called with new
+    # argument lists).  Without nvcc (a deployment box that received a prebuilt .so) the stamp is still checked.
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_nppc_build", os.path.join(HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if os.path.exists(mod.NVCC):
+        mod.build(force=False, verbose=False)
+    elif not mod.is_current():
+        raise NppcError(f"{LIB_PATH} does not match the sources under csrc/ (stale build) and nvcc is not available to rebuild it")
     if not os.path.exists(LIB_PATH):
         raise NppcError(f"{LIB_PATH} is missing and could not be built; the CUDA path has no fallback")
     lib = C.CDLL(LIB_PATH)

@@ -18,7 +18,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnppc_b200.so")
 CUTLASS_INC = "/opt/prime-rl/.venv/lib/python3.12/site-packages/flashinfer/data/cutlass/include"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DNPPC_REC_TRACE"] if os.environ.get("NPPC_REC_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+FLAGS = (["-DNPPC_REC_TRACE"] if os.environ.get("NPPC_REC_TRACE") else []) + \
+        (["-DNPPC_LSTM_ABLATE"] if os.environ.get("NPPC_LSTM_ABLATE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
@@ -34,6 +35,11 @@ def _digest():
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
+
+
+def is_current() -> bool:
+    stamp = os.path.join(OBJ, "stamp")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == _digest()
 
 
 def build(force: bool = False, verbose: bool = True) -> str:

@@ -1,7 +1,7 @@
 """Pydantic configs with the reference's field names and defaults, so reference yaml/dicts construct them
 unchanged: FullSubNetPlusConfig (fullsubnet_plus.py:18-42), MultiDirectionConfig (networks.py:9-14),
 AudioPCWrapperConfig (pc_wrapper.py:46-51), StftConfig (utils.py:14-17), NPPCModelConfig (nppc_model.py:13-22).
-Extra knob (not in the reference): `lstm_impl` selects the LSTM kernel ("tc" = bf16 tcgen05, "f32" = fp32 SIMT)."""
+Extra knob (not in the reference): `lstm_impl` selects the LSTM kernel ("tc" = fp16-operand / fp32-accumulate tcgen05 kernels for the LSTM and the TCN 1x1 convolutions, "f32" = fp32 SIMT LSTM + fp32 TCN)."""
 from typing import List, Literal
 
 import pydantic

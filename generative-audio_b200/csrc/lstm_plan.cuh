@@ -11,7 +11,7 @@ struct nppc_lstm_plan {
     float* bias[2];    // [4H] = b_ih + b_hh
     float* fc_w;       // [O][H]
     float* fc_b;       // [O]
-    // impl 1 (bf16 tcgen05): gate-interleaved, K-padded bf16 weights (see lstm_tc.cu)
+    // impl 1 (fp16 tcgen05): gate-interleaved, K-padded fp16 weights (see lstm_tc.cu; 16-bit buffers are typed __nv_bfloat16* for size only)
     int KP0;                   // padded input width of layer 0 (multiple of 64)
     __nv_bfloat16* wp_ih[2];   // [4H][KP] permuted rows
     __nv_bfloat16* wp_hh[2];   // [4H][H]  permuted rows

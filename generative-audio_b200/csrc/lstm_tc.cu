@@ -25,11 +25,17 @@ constexpr int ROWS = 128;           // sequences per CTA
 constexpr int CH = 32;              // hidden units per chunk
 constexpr int NCHUNK = H / CH;      // 12
 constexpr int NSLAB = H / 64;       // 6 K-slabs of 64
-constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have the same shape: 128 x 64 bf16)
+constexpr int SLAB_BYTES = ROWS * 64 * 2;   // 16 KB (A slab and W stage have the same shape: 128 x 64 fp16)
 constexpr int NTHREADS = 384;       // warps 0-3: TMA-W, MMA, TMEM alloc, TMA-A ; warps 4-11: epilogue
 constexpr int OPMAX = 24;
 
 constexpr int HST_BYTES = ROWS * CH * 2;   // one chunk of h_t for the CTA's rows: [128][32] fp16 = 8 KB
+
+#ifdef NPPC_LSTM_ABLATE
+#define NPPC_DBG(dbg, bit) ((dbg) & (bit))
+#else
+#define NPPC_DBG(dbg, bit) false
+#endif
 
 #ifdef NPPC_REC_TRACE
 __device__ long long g_trace[4 * 12 * 16];
@@ -210,7 +216,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         if (k == NK - 1) TRACE(14);
                         unsigned char* dst = smem + S::W_OFF + stage * S::WST_BYTES;
                         const int wrow = chunk_of(j) * 128 + (int)crank * 64;
-                        if (dbg & 2) {
+                        if (NPPC_DBG(dbg, 2)) {
                             mbar_arrive_cluster(wf0 + stage * 8);
                         } else if (FUSE_X && k == 0) {
                             mbar_arrive_expect_tx_cluster(wf0 + stage * 8, HALF_SLAB);
@@ -245,7 +251,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     const int k = pair_of(kk >> 1) * 2 + (kk & 1);
                     if (k == late_slab) continue;
                     mbar_wait(&h_stored[k], (t - 1) & 1);
-                    if (dbg & 8) { mbar_arrive_cluster(af0 + k * 8); continue; }
+                    if (NPPC_DBG(dbg, 8)) { mbar_arrive_cluster(af0 + k * 8); continue; }
                     mbar_arrive_expect_tx_cluster(af0 + k * 8, SLAB_BYTES);
                     tma_load_2d_pair(smem + S::A_OFF + k * SLAB_BYTES, &tmap_h, af0 + k * 8, k * 64, (t - 1) * RS + row0);
                 }
@@ -347,7 +353,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         if (k == NK - 1) TRACE(3);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            if (!(dbg & 4)) {
+                            if (!NPPC_DBG(dbg, 4)) {
                                 if (is_x) {
                                     const uint64_t da = umma_desc_k128(x_base);
                                     const uint64_t db = umma_desc_k128(w_base + stage * S::WST_BYTES);
@@ -569,7 +575,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
 }
 
-// fp32 [4H][K] (nn.LSTM row order) -> bf16 [4H][KP] with permuted rows, zero-padded K
+// fp32 [4H][K] (nn.LSTM row order) -> fp16 [4H][KP] with permuted rows, zero-padded K
 // packed gate column p = chunk*128 + half*64 + blk*16 + gate*4 + uu  ->  nn.LSTM row gate*H + chunk*32 + half*16 + blk*4 + uu
 __device__ __forceinline__ int packed_to_lstm_row(int p) {
     const int chunk = p >> 7, half = (p >> 6) & 1, blk = (p >> 4) & 3, gate = (p >> 2) & 3, uu = p & 3;
@@ -702,7 +708,11 @@ int launch_rec(const CUtensorMap& tw, const CUtensorMap& th, const CUtensorMap& 
     auto kern = lstm_rec_kernel<FUSE_X, FUSE_FC>;
     NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<FUSE_X>::TOTAL));
     const int tiles = RS / ROWS;
-    static const int dbg = getenv("NPPC_LSTM_DBG") ? atoi(getenv("NPPC_LSTM_DBG")) : 0;   // timing ablations only (wrong results)
+#ifdef NPPC_LSTM_ABLATE   // compile-time only (build.py adds -DNPPC_LSTM_ABLATE when NPPC_LSTM_ABLATE is set at BUILD time)
+    static const int dbg = getenv("NPPC_LSTM_DBG") ? atoi(getenv("NPPC_LSTM_DBG")) : 0;   // timing ablations: wrong results
+#else
+    constexpr int dbg = 0;   // the shipped library has no run-time switch that changes results
+#endif
     kern<<<nppc::cdiv(tiles, 2) * 2, NTHREADS, RecSmem<FUSE_X>::TOTAL, s>>>(tw, th, thst, tx, twx, *fc.tfc, (const uint4*)zx, bias,
                                                                             RS, Tp, fc.fc_b, fc.O, fc.R, fc.y, dbg, xkk);
     NPPC_COUNT_LAUNCH(1);

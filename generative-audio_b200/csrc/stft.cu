@@ -6,6 +6,8 @@
 // with one conflict-free (17-padded) shared-memory transpose in between — two frames per warp at a time, 3 warp
 // syncs per transform instead of the 8 shared-memory radix-2 stages this replaced.  Twiddles and the periodic hann
 // window are staged in shared memory once per CTA.
+#include <mutex>
+#include <math.h>
 #include "common.cuh"
 
 namespace {
@@ -89,27 +91,28 @@ struct __align__(16) SmemTables {
     float win[NFFT];  // periodic hann
 };
 
-__device__ SmemTables g_tables;   // filled once per process by init_tables_kernel
-__global__ void init_tables_kernel() {
-    for (int k = threadIdx.x; k < M; k += blockDim.x) {
-        float s, c;
-        sincospif(-(float)k / 256.0f, &s, &c);
-        g_tables.tw[k] = make_float2(c, s);
-    }
-    for (int n = threadIdx.x; n < NFFT; n += blockDim.x) g_tables.win[n] = 0.5f - 0.5f * cospif((float)n / 256.0f);
-}
+__device__ SmemTables g_tables;   // per device; filled once per device by ensure_tables (host-computed, blocking upload)
 __device__ __forceinline__ void fill_tables(SmemTables* tb) {
     const float4* src = reinterpret_cast<const float4*>(&g_tables);
     float4* dst = reinterpret_cast<float4*>(tb);
     for (int i = threadIdx.x; i < (int)(sizeof(SmemTables) / 16); i += blockDim.x) dst[i] = src[i];
 }
-int ensure_tables(cudaStream_t s) {
-    static bool done = false;
-    if (!done) {
-        init_tables_kernel<<<1, 256, 0, s>>>();
-        if (cudaGetLastError() != cudaSuccess) return -1;
-        done = true;
-    }
+// Twiddles and window are computed on the host in double precision and uploaded with a BLOCKING cudaMemcpyToSymbol the first
+// time each device is used (per-device flag under a mutex): the copy has completed before this returns, so kernels launched
+// afterwards on ANY stream of that device, from any thread, see the tables.
+int ensure_tables(cudaStream_t) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return 0;
+    static SmemTables host;
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < M; ++k) host.tw[k] = make_float2((float)cos(-pi * k / 256.0), (float)sin(-pi * k / 256.0));
+    for (int n = 0; n < NFFT; ++n) host.win[n] = (float)(0.5 - 0.5 * cos(pi * n / 256.0));
+    if (cudaMemcpyToSymbol(g_tables, &host, sizeof(SmemTables)) != cudaSuccess) return -1;
+    done[dev] = true;
     return 0;
 }
 

@@ -1,9 +1,10 @@
 """Full-band modules of FullSubNet+ (TSSE attention a3, TCN sequence model a4) and the parameter container of
 the sub-band LSTM (a7), with the reference's parameter names so state_dicts are interchangeable.
 
-Round-1 status: a3/a4 run on stock torch CUDA ops (cuDNN/cuBLAS library calls — the reference's own GPU path,
-≈2-3 % of the FLOPs; SURVEY.md §7 step 6, §8f row N2 "next").  The LSTM is never run through nn.LSTM: its
-weights feed the hand-written kernels via ops.LstmPlan."""
+a3 (TSSE) runs on three fused kernels; a4 (TCN) has two paths: lstm_impl="tc" runs the whole stack channel-last with every
+1x1 convolution and the output Linear on the in-house tcgen05 GEMM (forward_tc), lstm_impl="f32" keeps fp32 activations with
+the 1x1 convolutions on the library and everything between them on three fused kernels.  The LSTM is never run through
+nn.LSTM on the inference path: its weights feed the hand-written kernels via ops.LstmPlan."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

@@ -12,7 +12,9 @@ under tests/golden/.  tests/test_oracle_vs_golden.py re-checks that pin on every
 
 Every function is written from the reference's *behaviour* (no code copied) and cites the reference
 file:line it follows (paths relative to /root/reference).  It is dtype-generic: pass float64 params and
-inputs to get the fp64 yardstick used to adjudicate tolerances.
+inputs to get the fp64 yardstick used to adjudicate tolerances, and device-generic: with its tensors on `cuda` it IS the
+reference's torch-eager GPU path (cuDNN LSTM via fast=True, cuFFT, library convolutions) that bench.py times as
+`gpu_eager_baseline`.
 
 Parameters are passed as a flat `dict[str, Tensor]` with the reference's state_dict keys.
 """
@@ -45,7 +47,7 @@ def stft_mri(wave: torch.Tensor, n_fft: int = 512, hop: int = 256, win: int = 51
     if wave.dim() == 1:
         wave = wave[None]
     assert win == n_fft, "reference configs always use win_length == n_fft"
-    w = hann_periodic(win, wave.dtype)
+    w = hann_periodic(win, wave.dtype).to(wave.device)
     xp = F.pad(wave[:, None, :], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
     frames = xp.unfold(-1, n_fft, hop)  # [B, T, n_fft]
     spec = torch.fft.rfft(frames * w, dim=-1)  # [B, T, F]
@@ -62,11 +64,11 @@ def istft(real: torch.Tensor, imag: torch.Tensor, length: int, n_fft: int = 512,
     real/imag: [B, F, T] -> [B, length]
     """
     B, Fq, T = real.shape
-    w = hann_periodic(n_fft, real.dtype)
+    w = hann_periodic(n_fft, real.dtype).to(real.device)
     frames = torch.fft.irfft(torch.complex(real, imag).transpose(1, 2), n=n_fft, dim=-1) * w  # [B,T,n_fft]
     total = n_fft + hop * (T - 1)
-    out = torch.zeros(B, total, dtype=real.dtype)
-    env = torch.zeros(total, dtype=real.dtype)
+    out = torch.zeros(B, total, dtype=real.dtype, device=real.device)
+    env = torch.zeros(total, dtype=real.dtype, device=real.device)
     for t in range(T):
         out[:, t * hop:t * hop + n_fft] += frames[:, t]
         env[t * hop:t * hop + n_fft] += w * w
@@ -92,7 +94,7 @@ def cumulative_laplace_norm(x: torch.Tensor) -> torch.Tensor:
     B, C, Fq, T = x.shape
     z = x.reshape(B * C, Fq, T)
     cs = torch.cumsum(z.sum(dim=1), dim=-1)
-    cnt = (torch.arange(1, T + 1, dtype=x.dtype) * Fq)[None]
+    cnt = (torch.arange(1, T + 1, dtype=x.dtype, device=x.device) * Fq)[None]
     return (z / ((cs / cnt)[:, None, :] + EPSILON)).reshape(B, C, Fq, T)
 
 
@@ -162,7 +164,7 @@ def unfold(x: torch.Tensor, n: int) -> torch.Tensor:
     B, C, Fq, T = x.shape
     if n < 1:
         return x.permute(0, 2, 1, 3).reshape(B, Fq, C, 1, T)
-    idx = torch.arange(Fq)[:, None] + torch.arange(2 * n + 1)[None, :] - n
+    idx = torch.arange(Fq, device=x.device)[:, None] + torch.arange(2 * n + 1, device=x.device)[None, :] - n
     idx = torch.where(idx < 0, -idx, idx)
     idx = torch.where(idx > Fq - 1, 2 * (Fq - 1) - idx, idx)
     out = x[:, :, idx, :]  # [B,C,F,K,T]
@@ -195,7 +197,7 @@ def lstm_fc(x: torch.Tensor, p: Params, pre: str, fast: bool = False) -> torch.T
         N = seq.shape[0]
         H = p[f"{lp}.weight_hh_l0"].shape[1]
         flat = [p[f"{lp}.{k}_l{l}"] for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-        z = torch.zeros(2, N, H, dtype=seq.dtype)
+        z = torch.zeros(2, N, H, dtype=seq.dtype, device=seq.device)
         seq = torch.lstm(seq.contiguous(), (z, z), flat, True, 2, 0.0, False, False, True)[0]
     else:
         for layer in (0, 1):
@@ -204,8 +206,8 @@ def lstm_fc(x: torch.Tensor, p: Params, pre: str, fast: bool = False) -> torch.T
             N, T, _ = seq.shape
             H = w_hh.shape[1]
             zx = seq @ w_ih.T + b  # [N,T,4H]
-            h = torch.zeros(N, H, dtype=seq.dtype)
-            c = torch.zeros(N, H, dtype=seq.dtype)
+            h = torch.zeros(N, H, dtype=seq.dtype, device=seq.device)
+            c = torch.zeros(N, H, dtype=seq.dtype, device=seq.device)
             outs = []
             for t in range(T):
                 z = zx[:, t] + h @ w_hh.T
