@@ -51,15 +51,20 @@ PROTOTYPES = {
     "nppc_lstm_plan_destroy": (None, [_p]),
     "nppc_lstm_workspace_bytes": (_sz, [_p, _i, _i, _i]),
     "nppc_lstm_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "nppc_lstm_step_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nppc_lstm_step_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "nppc_lstm_step_backward": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p, _p, _p, _p]),
+    "nppc_gemm_f16_atb": (_i, [_p, _p, _ll, _i, _i, _i, _p, _p, _p]),
     "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "nppc_gemm_f16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "nppc_tcn_cl_scale": (_i, [_p, _i, _ll, _p, _p, _p]),
-    "nppc_tcn_cl_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "nppc_tcn_cl_unpack": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p]),
+    "nppc_gemm_f16_tn_ex": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _p]),
+    "nppc_tcn_cl_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "nppc_tcn_cl_unpack": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p]),
     "nppc_prelu_stats_cl": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "nppc_tcn_mid_cl": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
-    "nppc_tcn_out_cl": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "nppc_tcn_out_cl": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p]),
 }
 
 _lib = None

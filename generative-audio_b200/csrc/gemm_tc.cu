@@ -29,10 +29,14 @@ struct GemmSmem {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int BN, bool F16, bool ZX>
+// a_wrap: the A operand has only a_wrap K-blocks; K-block kb of the product reads A block kb % a_wrap (split-precision
+//         products [hi | lo | hi] x [Whi | Whi | Wlo] without storing hi twice); a_wrap = K / 64 for a plain GEMM.
+// OUT32 : C is fp32 [M][N] row-major, written straight from the accumulator registers (no 16-bit rounding of the result).
+template <int BN, bool F16, bool ZX, bool OUT32>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, long long M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, long long M, int N, int K,
+                    int a_wrap, float* __restrict__ c32) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     using S = GemmSmem<BN>;
@@ -72,7 +76,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     unsigned char* sa = smem + stage * S::STAGE_BYTES;
                     unsigned char* sb = sa + S::A_BYTES;
                     mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sa, &tmap_a, &full[stage], (kb % a_wrap) * BK, m_blk * BM);
                     tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -112,6 +116,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int rloc = ew * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
             unsigned char* cs = smem + S::C_OFFSET;
+            if (OUT32) {
+                const long long grow = (long long)m_blk * BM + rloc;
+                float* crow = c32 + (size_t)grow * N + (size_t)n_blk * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c * 32, v);
+                    tmem_wait_ld();
+                    if (grow < M) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                            if (bias) {
+                                const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n_blk * BN + c * 32) + q);
+                                o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+                            }
+                            reinterpret_cast<float4*>(crow + c * 32)[q] = o;
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&tempty[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                continue;
+            }
             // the previous tile's TMA stores must have finished reading the staging buffer
             if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -193,22 +223,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
-template <int BN, bool F16, bool ZX>
-int launch_gemm(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s) {
+template <int BN, bool F16, bool ZX, bool OUT32 = false>
+int launch_gemm(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, cudaStream_t s, int KA = 0) {
+    if (KA <= 0) KA = K;
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, BM, BK);
+    int rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)KA, (uint64_t)KA * 2, BM, BK);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, BK);
     if (rc) return rc;
     CUtensorMap tcm;
-    if (ZX) rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)(M / 128) * (N / 128) * 256, 64, 128, 256, 64, 0);
+    if (OUT32) tcm = tb;   // unused by the fp32 epilogue
+    else if (ZX) rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)(M / 128) * (N / 128) * 256, 64, 128, 256, 64, 0);
     else rc = make_tmap_bf16_2d(&tcm, C, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, BM, 64);
     if (rc) return rc;
     using S = GemmSmem<BN>;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, F16, ZX>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, F16, ZX, OUT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     long long tiles = ((M + BM - 1) / BM) * (N / BN);
     int grid = (int)(tiles < nppc::sm_count() ? tiles : nppc::sm_count());
-    gemm_bf16_tn_kernel<BN, F16, ZX><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K);
+    gemm_bf16_tn_kernel<BN, F16, ZX, OUT32><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, bias, M, N, K, KA / BK, OUT32 ? (float*)C : nullptr);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -238,6 +270,21 @@ int gemm_16bit_tn(const void* A, const void* W, const float* bias, void* C, long
 extern "C" int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K,
                                  void* stream) {
     return nppc::gemm_16bit_tn(A, W, bias, C, M, N, K, 0, (cudaStream_t)stream);
+}
+
+// fp16 operands with a wrapped A operand (A is [M][KA], K-block kb reads A block kb % (KA/64)) and optional fp32 output:
+// the split-precision products of the TCN path (tcn_cl.cu): A = [hi | lo], W = [Whi | Whi | Wlo], K = 3 Kp, KA = 2 Kp.
+extern "C" int nppc_gemm_f16_tn_ex(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, int KA,
+                                   int out_f32, void* stream) {
+    NPPC_CHECK_ARG(A && W && C, "nppc_gemm_f16_tn_ex: null pointer");
+    NPPC_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % BK == 0 && N % 128 == 0 && KA > 0 && KA % BK == 0 && KA <= K,
+                   "nppc_gemm_f16_tn_ex: need K %% 64 == 0, KA %% 64 == 0, KA <= K, N %% 128 == 0 (M=%lld N=%d K=%d KA=%d)", M, N, K, KA);
+    NPPC_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                   "nppc_gemm_f16_tn_ex: pointers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out_f32) return N % 256 == 0 ? launch_gemm<256, true, false, true>(A, W, bias, C, M, N, K, s, KA)
+                                     : launch_gemm<128, true, false, true>(A, W, bias, C, M, N, K, s, KA);
+    return N % 256 == 0 ? launch_gemm<256, true, false>(A, W, bias, C, M, N, K, s, KA) : launch_gemm<128, true, false>(A, W, bias, C, M, N, K, s, KA);
 }
 
 // same with IEEE fp16 operands / output (the TCN 1x1 convolutions, tcn_cl.cu)

@@ -10,6 +10,12 @@
 // fp16 RANGE: the real / imag streams are normalised by a cancelling mean (base_model.py:219-222) and can reach 1e4 and more,
 // so xh holds x / scale[b] with scale[b] = max|x_0| of the sample (<= 1 on entry, huge head-room for the residual growth);
 // the consumers of y1 (and of the final Linear) multiply the per-sample scale back in fp32: y1 = scale[b] * (W1 xh) + b1.
+// fp16 MANTISSA: the frozen backbone's output feeds the PC head's cancelling-mean normalisers (mean(enhanced_real) etc.), which
+// amplify any backbone error by the cancellation depth (measured 200x on speech, tests/golden/speech12.npz).  Error model
+// (tools/tcn_fp16_error_model.py): of all fp16 rounding points only three matter — the residual stream as GEMM A operand, the
+// conv1x1 / fc weights, and the fc output.  With `split` the A operand is written as hi + lo fp16 halves ([M][2 Kp]: hi | lo)
+// and the weights as [Whi | Whi | Wlo] ([N][3 Kp]): the GEMM computes hi*Whi + lo*Whi + hi*Wlo (~22 mantissa bits, fp32
+// accumulate) by wrapping its A K-blocks (gemm_tc.cu a_wrap), and the fc GEMM writes fp32.
 // All kernels here are HBM-bound streaming passes over fp16 tensors (half the bytes of the channel-first fp32 versions
 // in tcn.cu); per-sample GroupNorm moments are fp64 block reductions + fp64 atomics as before.
 #include <cuda_fp16.h>
@@ -33,8 +39,14 @@ __device__ __forceinline__ void moments(const double* __restrict__ st, double in
 
 // channel-first fp32 [B][C][T] -> x32 [B*T][Kp] fp32 and xh [B*T][Kp] fp16 (columns [C, Kp) of xh are written as zeros).
 // 32x32 shared-memory transpose tiles; grid (ceil(T/32), ceil(C/32), B), block (32, 8).
+// hi / lo split of a scaled value: hi = fp16(v), lo = fp16(v - hi) (exact subtraction in fp32)
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
 __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp, const float* __restrict__ inv_scale,
-                               float* __restrict__ x32, __half* __restrict__ xh) {
+                               float* __restrict__ x32, __half* __restrict__ xh, int split) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -48,7 +60,14 @@ __global__ void pack_cl_kernel(const float* __restrict__ x, int C, int T, int Kp
             const float v = tile[threadIdx.x][i];
             const size_t row = (size_t)b * T + t;
             if (c < C) x32[row * Kp + c] = v;
-            xh[row * Kp + c] = __float2half_rn(v * inv_scale[b]);
+            if (split) {
+                __half hi, lo;
+                split_h(v * inv_scale[b], hi, lo);
+                xh[row * (2 * Kp) + c] = hi;
+                xh[row * (2 * Kp) + Kp + c] = lo;
+            } else {
+                xh[row * Kp + c] = __float2half_rn(v * inv_scale[b]);
+            }
         }
     }
 }
@@ -83,14 +102,18 @@ __global__ void __launch_bounds__(TPB) absmax_cl_kernel(const float* __restrict_
 __global__ void scale_finish_kernel(int B, float* __restrict__ scale, float* __restrict__ inv_scale) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
-        float sc = fmaxf(scale[b], 1e-30f);   // (fmaxf drops NaNs: a NaN input still poisons the output through the GEMMs)
+        // floor 1: the residual stream grows by O(1) per block whatever the input level (GroupNorm'd branch), so a quiet or
+        // silent sample (max|x| -> 0) must not get a tiny scale — x32 / scale would overflow fp16 after the first block
+        // (measured on the digitally silent utterance of tests/golden/speech12.npz: pred_crm 0.76 off before this floor).
+        float sc = fmaxf(scale[b], 1.0f);   // (fmaxf drops NaNs: a NaN input still poisons the output through the GEMMs)
         scale[b] = sc;
         inv_scale[b] = 1.0f / sc;
     }
 }
 
 // o [B*T][Np] fp16 (+ bias[c], optional ReLU) -> channel-first fp32 [B][C][T]
-__global__ void unpack_cl_kernel(const __half* __restrict__ o, int C, int T, int Np, const float* __restrict__ scale,
+template <typename TO>
+__global__ void unpack_cl_kernel(const TO* __restrict__ o, int C, int T, int Np, const float* __restrict__ scale,
                                  const float* __restrict__ bias, int relu, float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -98,7 +121,7 @@ __global__ void unpack_cl_kernel(const __half* __restrict__ o, int C, int T, int
         const int t = t0 + i, c = c0 + threadIdx.x;
         float v = 0.f;
         if (t < T && c < C) {
-            v = __half2float(o[((size_t)b * T + t) * Np + c]) * (scale ? scale[b] : 1.f) + (bias ? bias[c] : 0.f);
+            v = (float)o[((size_t)b * T + t) * Np + c] * (scale ? scale[b] : 1.f) + (bias ? bias[c] : 0.f);
             if (relu) v = fmaxf(v, 0.f);
         }
         tile[i][threadIdx.x] = v;
@@ -207,7 +230,7 @@ constexpr int OUT_TPB = 288;
 __global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __restrict__ o, float* __restrict__ x32, int T, int C, int Np,
                                                             int Kp, const double* __restrict__ stats2, const float* __restrict__ u,
                                                             const float* __restrict__ vb, const float* __restrict__ inv_scale,
-                                                            __half* __restrict__ xh, int relu_h, double inv_n) {
+                                                            __half* __restrict__ xh, int relu_h, double inv_n, int split) {
     const int b = blockIdx.y;
     const int CQ = (C + 3) >> 2;                 // channel quads per row
     const int RL = OUT_TPB / CQ;                 // rows worked on side by side (host checks RL >= 1)
@@ -230,8 +253,10 @@ __global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __res
     const size_t r0 = (size_t)b * T + tb + rl;
     float4* xp = reinterpret_cast<float4*>(x32 + r0 * Kp + c0);
     const uint2* op = reinterpret_cast<const uint2*>(o + r0 * Np + c0);
-    uint2* hp = reinterpret_cast<uint2*>(xh + r0 * Kp + c0);
+    const int XS = split ? 2 * Kp : Kp;             // xh row stride (hi | lo halves when split)
+    uint2* hp = reinterpret_cast<uint2*>(xh + r0 * XS + c0);
     const int sx = RL * Kp / 4, so = RL * Np / 4;   // strides between this thread's consecutive rows, in vectors
+    const int sh = RL * XS / 4;
     auto finish = [&](float4 xv, uint2 ov, float4* xd, uint2* hd) {
         const float2 o01 = __half22float2(*reinterpret_cast<const __half2*>(&ov.x));
         const float2 o23 = __half22float2(*reinterpret_cast<const __half2*>(&ov.y));
@@ -243,14 +268,19 @@ __global__ void __launch_bounds__(OUT_TPB) tcn_out_cl_kernel(const __half* __res
         *xd = make_float4(v[0], v[1], v[2], v[3]);
         const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
         *hd = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        if (split) {   // lo half: the fp16 rounding residual of the scaled value (zero in the K padding)
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(h[0] - f01.x, h[1] - f01.y), l23 = __floats2half2_rn(h[2] - f23.x, h[3] - f23.y);
+            hd[Kp / 4] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        }
     };
     int nr = (te - tb - rl + RL - 1) / RL;   // rows of this chunk that fall on this row lane
     for (; nr >= 2; nr -= 2) {               // two independent rows in flight
         const float4 xa = xp[0], xb = xp[sx];
         const uint2 oa = __ldg(op), ob = __ldg(op + so);
         finish(xa, oa, xp, hp);
-        finish(xb, ob, xp + sx, hp + sx);   // x32 (float4) and xh (4 halves) rows have the same stride in vectors: Kp / 4
-        xp += 2 * sx; op += 2 * so; hp += 2 * sx;
+        finish(xb, ob, xp + sx, hp + sh);
+        xp += 2 * sx; op += 2 * so; hp += 2 * sh;
     }
     if (nr > 0) finish(xp[0], __ldg(op), xp, hp);
 }
@@ -273,18 +303,20 @@ extern "C" int nppc_tcn_cl_scale(const float* x, int B, long long n_per_sample, 
 }
 
 extern "C" int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh,
-                                void* stream) {
+                                int split, void* stream) {
     NPPC_CHECK_ARG(x && inv_scale && x32 && xh && B > 0 && C > 0 && T > 0 && Kp >= C && B <= 65535, "nppc_tcn_cl_pack: bad arguments");
-    pack_cl_kernel<<<dim3(nppc::cdiv(T, 32), nppc::cdiv(Kp, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, C, T, Kp, inv_scale, x32, (__half*)xh);
+    pack_cl_kernel<<<dim3(nppc::cdiv(T, 32), nppc::cdiv(Kp, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, C, T, Kp, inv_scale, x32, (__half*)xh, split);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
 }
 
-extern "C" int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, const float* scale, const float* bias, int relu,
-                                  float* out, void* stream) {
+extern "C" int nppc_tcn_cl_unpack(const void* o, int o_f32, int B, int C, int T, int Np, const float* scale, const float* bias,
+                                  int relu, float* out, void* stream) {
     NPPC_CHECK_ARG(o && out && B > 0 && C > 0 && T > 0 && Np >= C && B <= 65535, "nppc_tcn_cl_unpack: bad arguments");
-    unpack_cl_kernel<<<dim3(nppc::cdiv(T, 32), nppc::cdiv(C, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>((const __half*)o, C, T, Np, scale, bias, relu, out);
+    const dim3 grid(nppc::cdiv(T, 32), nppc::cdiv(C, 32), B), block(32, 8);
+    if (o_f32) unpack_cl_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)o, C, T, Np, scale, bias, relu, out);
+    else unpack_cl_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)o, C, T, Np, scale, bias, relu, out);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -329,12 +361,13 @@ extern "C" int nppc_tcn_mid_cl(const void* y1, int B, int T, int H, const float*
 }
 
 extern "C" int nppc_tcn_out_cl(const void* o, float* x32, int B, int T, int C, int Np, int Kp, int H, const double* stats2,
-                               const float* u, const float* vb, const float* inv_scale, void* xh, int relu_h, void* stream) {
+                               const float* u, const float* vb, const float* inv_scale, void* xh, int relu_h, int split,
+                               void* stream) {
     NPPC_CHECK_ARG(o && x32 && stats2 && u && vb && inv_scale && xh && B > 0 && T > 0 && C > 0 && Np >= C && Kp >= C && B <= 65535 && H == HID,
                    "nppc_tcn_out_cl: bad arguments");
     NPPC_CHECK_ARG(Kp % 4 == 0 && Np % 4 == 0 && (C + 3) / 4 <= OUT_TPB, "nppc_tcn_out_cl: Kp, Np must be multiples of 4 and C <= %d", 4 * OUT_TPB);
     tcn_out_cl_kernel<<<dim3(rows_grid(T, B), B), OUT_TPB, 0, (cudaStream_t)stream>>>((const __half*)o, x32, T, C, Np, Kp, stats2, u, vb, inv_scale, (__half*)xh, relu_h,
-                                                                                          1.0 / ((double)HID * T));
+                                                                                          1.0 / ((double)HID * T), split);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

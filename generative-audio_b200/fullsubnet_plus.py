@@ -63,6 +63,7 @@ class FullSubNet_Plus(nn.Module):
         tc = self.lstm_impl == "tc" and os.environ.get("NPPC_TCN_TC", "1") != "0"   # 1x1 convs on the tcgen05 GEMM (row N2)
         for m in (self.fb_model, self.fb_model_real, self.fb_model_imag):
             m.use_tc_convs = tc
+            m.tc_split = os.environ.get("NPPC_TCN_SPLIT", "1") != "0"
 
     # -- helpers --------------------------------------------------------------------------------------
     def _pad_norm(self, x):

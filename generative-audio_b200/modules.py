@@ -14,6 +14,18 @@ from . import ops
 TCN_DILATIONS = (1, 2, 5, 9, 1, 2, 5, 9)  # sequence_model.py:48-57
 
 
+def _conv1x1_f32(w, x):
+    """1x1 Conv1d of the fp32 path as a TRUE fp32 GEMM: w [O,C,1], x [B,C,T] -> [B,O,T].  F.conv1d goes through cuDNN, whose
+    default (torch.backends.cudnn.allow_tf32 = True) is a TF32 tensor-core GEMM with a 10-bit mantissa — measured 4e-3 on
+    w_mat for speech input, 40x the fp32 budget; matmul with TF32 forced off is the library's fp32 SGEMM."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return torch.matmul(w[:, :, 0], x)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 class _ConvPoolRelu(nn.Sequential):
     """Keeps the reference's `smallConv1d.0.weight` key layout (attention_model.py:57-71)."""
 
@@ -77,13 +89,13 @@ class TCNBlock(nn.Module):
         """x [B,C,T'] -> x + sconv(norm2(prelu2(dwconv(norm1(prelu1(conv1x1(x)))))))  (causal_conv.py:96-108).
         1x1 convolutions: library GEMM; everything between them: 3 fused kernels (prelu_stats, tcn_mid, tcn_out)."""
         x = x.contiguous()
-        y1 = F.conv1d(x, self.conv1x1.weight)   # bias folded into the two kernels that read y1
+        y1 = _conv1x1_f32(self.conv1x1.weight, x)   # bias folded into the two kernels that read y1
         stats1 = ops.prelu_stats(y1, self.prelu1.weight, self.conv1x1.bias)
         z, stats2 = ops.tcn_mid(y1, self.prelu1.weight, stats1, self.norm1.weight, self.norm1.bias,
                                 self.depthwise_conv.weight, self.depthwise_conv.bias, self.dilation, self.prelu2.weight,
                                 self.conv1x1.bias)
         w2f, u, vb = self._folded()
-        o = F.conv1d(z, w2f)
+        o = _conv1x1_f32(w2f, z)
         return ops.tcn_out(o, x, z.shape[1], stats2, u, vb)
 
 
@@ -123,29 +135,54 @@ class SequenceModel(nn.Module):
     # ---- TCN path ----
     use_tc_convs = False   # set by the owning model when lstm_impl == "tc": 1x1 convolutions on the tcgen05 GEMM (row N2)
 
+    # split-precision 1x1 convolutions (tcn_cl.cu): hi + lo fp16 halves of the residual stream and of the conv1x1 / fc weights,
+    # fp32 fc output.  NPPC_TCN_SPLIT=0 selects the plain fp16 operands (~1 ms faster per step at B = 64, 3-10x larger error on
+    # cancelling inputs; profiles/r02_parity_report.md).
+    tc_split = True
+
+    @staticmethod
+    def _split_w(w32, rows, Kp, dev):
+        """fp32 [n, C] -> fp16 [rows, 3 Kp] = [Whi | Whi | Wlo] (zero padded)."""
+        n, C = w32.shape
+        w32 = w32.clamp(-65504, 65504)
+        hi = w32.half()
+        lo = (w32 - hi.float()).half()
+        out = torch.zeros(rows, 3 * Kp, device=dev, dtype=torch.float16)
+        out[:n, :C] = hi
+        out[:n, Kp:Kp + C] = hi
+        out[:n, 2 * Kp:2 * Kp + C] = lo
+        return out
+
     def _tcn_plan(self):
         """fp16 / padded copies of the 1x1-conv weights for the channel-last tcgen05 path (derived cache, never serialised)."""
         blocks = [m for m in self.sequence_model if isinstance(m, TCNBlock)]
         ps = [p for blk in blocks for p in (blk.conv1x1.weight, blk.sconv.weight, blk.sconv.bias, blk.norm2.weight, blk.norm2.bias)]
         ps += [self.fc_output_layer.weight, self.fc_output_layer.bias]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (self.tc_split,)
         if getattr(self, "_tplan", None) is None or key != self._tplan_key:
             C = blocks[0].conv1x1.weight.shape[1]
             Kp, Np = -(-C // 64) * 64, -(-C // 128) * 128
             dev = blocks[0].conv1x1.weight.device
+            split = self.tc_split
             with torch.no_grad():
-                plan = dict(C=C, Kp=Kp, Np=Np, blocks=[])
+                plan = dict(C=C, Kp=Kp, Np=Np, blocks=[], split=split)
                 for blk in blocks:
-                    w1 = torch.zeros(512, Kp, device=dev, dtype=torch.float16)
-                    w1[:, :C] = blk.conv1x1.weight[:, :, 0].clamp(-65504, 65504).half()
+                    if split:
+                        w1 = self._split_w(blk.conv1x1.weight[:, :, 0], 512, Kp, dev)
+                    else:
+                        w1 = torch.zeros(512, Kp, device=dev, dtype=torch.float16)
+                        w1[:, :C] = blk.conv1x1.weight[:, :, 0].clamp(-65504, 65504).half()
                     w2f, u, vb = blk._folded()
                     w2 = torch.zeros(Np, 512, device=dev, dtype=torch.float16)
                     w2[:C] = w2f[:, :, 0].clamp(-65504, 65504).half()
                     plan["blocks"].append((w1, w2, u, vb))
                 O = self.fc_output_layer.weight.shape[0]
                 Op = -(-O // 128) * 128
-                wfc = torch.zeros(Op, Kp, device=dev, dtype=torch.float16)
-                wfc[:O, :C] = self.fc_output_layer.weight.clamp(-65504, 65504).half()
+                if split:
+                    wfc = self._split_w(self.fc_output_layer.weight, Op, Kp, dev)
+                else:
+                    wfc = torch.zeros(Op, Kp, device=dev, dtype=torch.float16)
+                    wfc[:O, :C] = self.fc_output_layer.weight.clamp(-65504, 65504).half()
                 plan.update(O=O, Op=Op, wfc=wfc)
             self._tplan, self._tplan_key = plan, key
         return self._tplan
@@ -157,21 +194,22 @@ class SequenceModel(nn.Module):
         B, C, T = x.shape
         M = B * T
         dev = x.device
+        split = pl["split"]
         x32 = torch.empty(M, pl["Kp"], device=dev, dtype=torch.float32)   # residual stream, rows padded like xh
-        xh = torch.empty(M, pl["Kp"], device=dev, dtype=torch.float16)   # K padding columns are zeroed by the pack kernel
+        xh = torch.empty(M, pl["Kp"] * (2 if split else 1), device=dev, dtype=torch.float16)   # K padding zeroed by the pack kernel
         # per-sample fp16 scale: the real / imag streams are normalised by a cancelling mean and can be huge (see tcn_cl.cu)
         x = x.contiguous()
         scale, inv_scale = ops.tcn_cl_scale(x)
-        ops.tcn_cl_pack(x, pl["Kp"], inv_scale, x32, xh)
+        ops.tcn_cl_pack(x, pl["Kp"], inv_scale, x32, xh, split)
         blocks = [m for m in self.sequence_model if isinstance(m, TCNBlock)]
         for i, (blk, (w1, w2, u, vb)) in enumerate(zip(blocks, pl["blocks"])):
-            y1 = ops.gemm_f16_tn(xh, w1)
+            y1 = ops.gemm_f16_tn_ex(xh, w1)
             stats1 = ops.prelu_stats_cl(y1, B, T, scale, blk.conv1x1.bias, blk.prelu1.weight)
             z, stats2 = ops.tcn_mid_cl(y1, B, T, scale, blk.conv1x1.bias, blk.prelu1.weight, stats1, blk.norm1.weight, blk.norm1.bias,
                                        blk.depthwise_conv.weight, blk.depthwise_conv.bias, blk.dilation, blk.prelu2.weight)
             o = ops.gemm_f16_tn(z, w2)
-            ops.tcn_out_cl(o, x32, B, T, C, pl["Np"], pl["Kp"], stats2, u, vb, inv_scale, xh, relu_h=(i == len(blocks) - 1))
-        o = ops.gemm_f16_tn(xh, pl["wfc"])
+            ops.tcn_out_cl(o, x32, B, T, C, pl["Np"], pl["Kp"], stats2, u, vb, inv_scale, xh, relu_h=(i == len(blocks) - 1), split=split)
+        o = ops.gemm_f16_tn_ex(xh, pl["wfc"], out_f32=split)
         relu = {"ReLU": 1, None: 0, "": 0, False: 0}.get(self.output_activate_function, None)
         if relu is None:
             raise NotImplementedError("tcgen05 TCN path: only ReLU / no output activation (every reference config)")

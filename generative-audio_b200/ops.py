@@ -431,6 +431,93 @@ class LstmPlan:
         return y
 
 
+# ---- a7 implementation 2: stepwise tensor-core LSTM (generic I / H, saved state, BPTT) -----------------------------------
+def _lstm_structs():
+    import ctypes as C
+
+    class W(C.Structure):
+        _fields_ = [("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2),
+                    ("fc_w", C.c_void_p), ("fc_b", C.c_void_p), ("I", C.c_int), ("H", C.c_int), ("O", C.c_int)]
+
+    class G(C.Structure):
+        _fields_ = [("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2),
+                    ("fc_w", C.c_void_p), ("fc_b", C.c_void_p)]
+    return W, G
+
+
+def _lstm_wstruct(params):
+    """params: (w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, fc_w, fc_b) fp32 CUDA tensors (nn.LSTM layout)."""
+    import ctypes as C
+    W, _ = _lstm_structs()
+    ts = [_f32(t.detach()) for t in params]
+    _chk(*ts)
+    w = W()
+    w.w_ih = (C.c_void_p * 2)(ts[0].data_ptr(), ts[4].data_ptr())
+    w.w_hh = (C.c_void_p * 2)(ts[1].data_ptr(), ts[5].data_ptr())
+    w.b_ih = (C.c_void_p * 2)(ts[2].data_ptr(), ts[6].data_ptr())
+    w.b_hh = (C.c_void_p * 2)(ts[3].data_ptr(), ts[7].data_ptr())
+    w.fc_w, w.fc_b = ts[8].data_ptr(), ts[9].data_ptr()
+    w.I, w.H, w.O = ts[0].shape[1], ts[1].shape[1], ts[8].shape[0]
+    assert ts[0].shape[0] == 4 * w.H and ts[4].shape == (4 * w.H, w.H) and ts[8].shape[1] == w.H
+    return w, ts
+
+
+def lstm_step_forward(params, xs: torch.Tensor, R: int = None, train: bool = False, precise: bool = False):
+    """Stepwise tensor-core LSTM + fc: xs [T', R_stride, KP] (fp16; fp32 when precise) -> (y [R, O, T'] f32, workspace).
+    train=True keeps gates / c / h of every step in the returned workspace for lstm_step_backward."""
+    import ctypes as C
+    _chk(xs)
+    Tp, RS, KP = xs.shape
+    R = RS if R is None else R
+    if xs.dtype != (torch.float32 if precise else _F16):
+        raise RuntimeError("lstm_step_forward: xs must be fp16 (fast mode) or fp32 (precise mode)")
+    w, keep = _lstm_wstruct(params)
+    lib = _lib.load()
+    nbytes = lib.nppc_lstm_step_workspace_bytes(w.I, w.H, w.O, RS, Tp, KP, int(train), int(precise))
+    ws = torch.empty(nbytes, device=xs.device, dtype=torch.uint8)
+    y = torch.empty(R, w.O, Tp, device=xs.device, dtype=torch.float32)
+    _lib.check(lib.nppc_lstm_step_forward(C.byref(w), xs.data_ptr(), int(precise), R, RS, Tp, KP, int(train), int(precise),
+                                          ws.data_ptr(), nbytes, y.data_ptr(), _stream()), "nppc_lstm_step_forward")
+    return y, ws
+
+
+def lstm_step_backward(params, xs: torch.Tensor, R: int, ws: torch.Tensor, dy: torch.Tensor, want_dxs: bool = True):
+    """BPTT of lstm_step_forward(train=True): dy [R, O, T'] -> (list of 10 parameter gradients in `params` order, dxs or None)."""
+    import ctypes as C
+    dy = _f32(dy)
+    _chk(xs, ws, dy)
+    Tp, RS, KP = xs.shape
+    w, keep = _lstm_wstruct(params)
+    _, G = _lstm_structs()
+    gs = [torch.empty_like(t) for t in keep]
+    g = G()
+    g.w_ih = (C.c_void_p * 2)(gs[0].data_ptr(), gs[4].data_ptr())
+    g.w_hh = (C.c_void_p * 2)(gs[1].data_ptr(), gs[5].data_ptr())
+    g.b_ih = (C.c_void_p * 2)(gs[2].data_ptr(), gs[6].data_ptr())
+    g.b_hh = (C.c_void_p * 2)(gs[3].data_ptr(), gs[7].data_ptr())
+    g.fc_w, g.fc_b = gs[8].data_ptr(), gs[9].data_ptr()
+    dxs = torch.empty(Tp, RS, KP, device=xs.device, dtype=torch.float32) if want_dxs else None
+    _lib.check(_lib.load().nppc_lstm_step_backward(C.byref(w), xs.data_ptr(), R, RS, Tp, KP, ws.data_ptr(), ws.numel(), dy.data_ptr(),
+                                                   C.byref(g), _ptr(dxs), _stream()), "nppc_lstm_step_backward")
+    return gs, dxs
+
+
+def gemm_f16_atb(a: torch.Tensor, b: torch.Tensor, splits: int = None):
+    """C [Mo, No] f32 = A^T B, A [rows, Mo], B [rows, No] fp16 row-major (tcgen05 MN-major operands, deterministic split-K)."""
+    _chk(a, b)
+    assert a.dtype == _F16 and b.dtype == _F16 and a.shape[0] == b.shape[0]
+    rows, Mo = a.shape
+    No = b.shape[1]
+    if splits is None:
+        tiles = (Mo // 128) * (No // 64)
+        splits = max(1, min(64, 148 // max(tiles, 1), rows // 64))
+    part = torch.empty(splits, Mo, No, device=a.device, dtype=torch.float32)
+    c = torch.empty(Mo, No, device=a.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_gemm_f16_atb(a.data_ptr(), b.data_ptr(), rows, Mo, No, splits, part.data_ptr(), c.data_ptr(), _stream()),
+               "nppc_gemm_f16_atb")
+    return c
+
+
 def tsse(x: torch.Tensor, kersize, conv_w, conv_b, fcat_w, fcat_b, fc1_w, fc1_b, fc2_w, fc2_b):
     """ChannelTimeSenseSELayer.forward (attention_model.py:78-98): x [B,C,T] -> x * gate."""
     import ctypes as C
@@ -494,8 +581,21 @@ def gemm_f16_tn(a: torch.Tensor, w: torch.Tensor, bias=None):
     return c
 
 
+def gemm_f16_tn_ex(a: torch.Tensor, w: torch.Tensor, bias=None, out_f32: bool = False):
+    """C[M,N] = sum over the K-blocks kb of W[N,K]: A[M, KA] block (kb % (KA/64)) x W block kb (fp16 operands, fp32
+    accumulate); out fp16 or fp32.  KA = a.shape[1] <= K = w.shape[1]."""
+    _chk(a, w, bias)
+    assert a.dtype == torch.float16 and w.dtype == torch.float16
+    M, KA = a.shape
+    N, K = w.shape
+    c = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_f32 else torch.float16)
+    _lib.check(_lib.load().nppc_gemm_f16_tn_ex(a.data_ptr(), w.data_ptr(), _ptr(bias), c.data_ptr(), M, N, K, KA, int(out_f32),
+                                               _stream()), "nppc_gemm_f16_tn_ex")
+    return c
+
+
 def tcn_cl_scale(x: torch.Tensor):
-    """per-sample fp16 range scale of x [B, ...] f32: (scale [B], inv_scale [B]) with scale = max(max|x[b]|, 1e-30)."""
+    """per-sample fp16 range scale of x [B, ...] f32: (scale [B], inv_scale [B]) with scale = max(max|x[b]|, 1)."""
     _chk(x)
     B = x.shape[0]
     scale = torch.empty(B, device=x.device, dtype=torch.float32)
@@ -505,18 +605,20 @@ def tcn_cl_scale(x: torch.Tensor):
     return scale, inv
 
 
-def tcn_cl_pack(x: torch.Tensor, Kp: int, inv_scale: torch.Tensor, x32: torch.Tensor, xh: torch.Tensor):
+def tcn_cl_pack(x: torch.Tensor, Kp: int, inv_scale: torch.Tensor, x32: torch.Tensor, xh: torch.Tensor, split: bool = False):
     _chk(x, inv_scale, x32, xh)
     B, C, T = x.shape
-    _lib.check(_lib.load().nppc_tcn_cl_pack(x.data_ptr(), B, C, T, Kp, inv_scale.data_ptr(), x32.data_ptr(), xh.data_ptr(), _stream()),
-               "nppc_tcn_cl_pack")
+    assert xh.shape[1] == (2 * Kp if split else Kp)
+    _lib.check(_lib.load().nppc_tcn_cl_pack(x.data_ptr(), B, C, T, Kp, inv_scale.data_ptr(), x32.data_ptr(), xh.data_ptr(), int(split),
+                                            _stream()), "nppc_tcn_cl_pack")
 
 
 def tcn_cl_unpack(o: torch.Tensor, B: int, C: int, T: int, Np: int, scale, bias, relu: int):
     _chk(o, scale, bias)
+    assert o.dtype in (torch.float16, torch.float32)
     out = torch.empty(B, C, T, device=o.device, dtype=torch.float32)
-    _lib.check(_lib.load().nppc_tcn_cl_unpack(o.data_ptr(), B, C, T, Np, _ptr(scale), _ptr(bias), int(relu), out.data_ptr(), _stream()),
-               "nppc_tcn_cl_unpack")
+    _lib.check(_lib.load().nppc_tcn_cl_unpack(o.data_ptr(), int(o.dtype == torch.float32), B, C, T, Np, _ptr(scale), _ptr(bias),
+                                              int(relu), out.data_ptr(), _stream()), "nppc_tcn_cl_unpack")
     return out
 
 
@@ -538,10 +640,12 @@ def tcn_mid_cl(y1, B: int, T: int, scale, bias1, prelu1_a, stats1, gamma1, beta1
     return z, stats2
 
 
-def tcn_out_cl(o, x32, B: int, T: int, C: int, Np: int, Kp: int, stats2, u, vb, inv_scale, xh, relu_h: bool):
+def tcn_out_cl(o, x32, B: int, T: int, C: int, Np: int, Kp: int, stats2, u, vb, inv_scale, xh, relu_h: bool, split: bool = False):
     _chk(o, x32, stats2, u, vb, inv_scale, xh)
+    assert xh.shape[1] == (2 * Kp if split else Kp)
     _lib.check(_lib.load().nppc_tcn_out_cl(o.data_ptr(), x32.data_ptr(), B, T, C, Np, Kp, 512, stats2.data_ptr(), u.data_ptr(),
-                                           vb.data_ptr(), inv_scale.data_ptr(), xh.data_ptr(), int(relu_h), _stream()), "nppc_tcn_out_cl")
+                                           vb.data_ptr(), inv_scale.data_ptr(), xh.data_ptr(), int(relu_h), int(split), _stream()),
+               "nppc_tcn_out_cl")
 
 
 def assemble_mask(y: torch.Tensor, B: int, Fp: int, look_ahead: int):

@@ -198,6 +198,46 @@ size_t nppc_lstm_workspace_bytes(const nppc_lstm_plan* plan, int R, int Tp, int 
 int nppc_lstm_forward(const nppc_lstm_plan* plan, const void* xs, int R, int R_stride, int Tp, int KP, int impl,
                       void* workspace, size_t workspace_bytes, float* y, void* stream);
 
+/* ---- a7, implementation 2: stepwise tensor-core LSTM for generic (I, H), with saved state and BPTT ------------------------
+ * One tcgen05 GEMM launch per (layer, time step) whose epilogue is the LSTM cell (csrc/lstm_step.cu).  Replaces, for the
+ * TRAINED PC head, nn.LSTM forward + backward (sequence_model.py:113-123 under trainer.py:100-106) and serves shapes the
+ * persistent kernel is not built for (FullSubNet's full-band LSTM 257 -> 512, fullsubnet.py:39-47).  fp32 master weights in
+ * the nn.LSTM layout are passed directly (repacked on the device every call).
+ *   xs          packed time-major input [Tp, R_stride, KP]: fp16 (fast mode) or fp32 (precise mode), features >= I zero
+ *   train != 0  gates / c / h of every step stay in the workspace for nppc_lstm_step_backward (same workspace, untouched)
+ *   precise!=0  split-precision operands (hi + lo fp16 halves of x, h and the weights: ~22 mantissa bits), exact tanh / exp:
+ *               fp32-class accuracy on the tensor cores, for utterances whose normaliser means cancel
+ *   y           [R, O, Tp] fp32 (the layout SequenceModel.forward returns)
+ * backward: dy [R, O, Tp] -> gradients of the ten parameters (nn.LSTM layout, overwritten) and, if dxs != NULL, of the packed
+ * input ([Tp, R_stride, KP] fp32).  Gradient tensors are fp16 with a power-of-two loss scale chosen on the device. */
+typedef struct {
+    const float* w_ih[2];   /* [4H, I] / [4H, H] */
+    const float* w_hh[2];   /* [4H, H] */
+    const float* b_ih[2];
+    const float* b_hh[2];
+    const float* fc_w;      /* [O, H] */
+    const float* fc_b;      /* [O] */
+    int I, H, O;
+} nppc_lstm_weights;
+typedef struct {
+    float* w_ih[2];
+    float* w_hh[2];
+    float* b_ih[2];
+    float* b_hh[2];
+    float* fc_w;
+    float* fc_b;
+} nppc_lstm_grads;
+size_t nppc_lstm_step_workspace_bytes(int I, int H, int O, int R_stride, int Tp, int KP, int train, int precise);
+int nppc_lstm_step_forward(const nppc_lstm_weights* w, const void* xs, int xs_is_f32, int R, int R_stride, int Tp, int KP,
+                           int train, int precise, void* workspace, size_t workspace_bytes, float* y, void* stream);
+int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* xs, int R, int R_stride, int Tp, int KP, void* workspace,
+                            size_t workspace_bytes, const float* dy, const nppc_lstm_grads* grads, float* dxs, void* stream);
+/* C[Mo, No] fp32 = A^T B with A [rows, Mo], B [rows, No] fp16 row-major (both consumed MN-major by tcgen05; split-K over
+ * `splits` CTAs per tile into `partials` [splits, Mo, No], summed in a fixed order).  The weight-gradient GEMM of the LSTM and
+ * of the TCN's 1x1 convolutions (dW = dY^T X).  rows % 64 == 0, Mo % 128 == 0, No % 64 == 0. */
+int nppc_gemm_f16_atb(const void* A, const void* B, long long rows, int Mo, int No, int splits, float* partials, float* C,
+                      void* stream);
+
 /* ---- a8/a11 output assembly -----------------------------------------------------------------------
  * y [B*F', O, T'] -> out [B, O, F', T'-la] dropping the first `look_ahead` frames
  * (fullsubnet_plus.py:227-229; networks.py:156-161 is the same memory layout with O = 2*n_dirs). */
@@ -210,12 +250,19 @@ int nppc_gemm_bf16_tn(const void* A, const void* W, const float* bias, void* C, 
                       void* stream);
 /* same with IEEE fp16 operands and output */
 int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, void* stream);
+/* fp16 operands with a WRAPPED A operand and optional fp32 output: A is [M, KA] and K-block kb of the product reads A block
+ * kb % (KA / 64), W is [N, K].  Used for the split-precision 1x1 convolutions of the TCN path (A = [hi | lo], W = [Whi | Whi |
+ * Wlo], K = 3 Kp, KA = 2 Kp): same arithmetic as the reference's fp32 Conv1d to ~22 mantissa bits
+ * (causal_conv.py:71,80; sequence_model.py:79).  out_f32 != 0: C is fp32 [M, N]. */
+int nppc_gemm_f16_tn_ex(const void* A, const void* W, const float* bias, void* C, long long M, int N, int K, int KA, int out_f32,
+                        void* stream);
 
 /* ---- N2: TCN stack in channel-last layout with its 1x1 convolutions on the tcgen05 GEMM ------------------------
  * (audio_zen/model/module/causal_conv.py:96-108, sequence_model.py:47-58,106-112).  M = B*T' rows, row = b*T' + t.
  * fp16 range: xh holds x / scale[b] (scale[b] = max|x| of the sample on entry, inv_scale = 1/scale); y1 and the final Linear
  * are multiplied back by scale[b] in fp32 where they are read.
- * nppc_tcn_cl_scale:   scale[b] = max(max|x[b]|, 1e-30), inv_scale[b] = 1/scale[b] of a [B, n_per_sample] f32 tensor (two launches).
+ * split != 0 (nppc_tcn_cl_pack / nppc_tcn_out_cl): xh is [M, 2 Kp] = [hi | lo] fp16 halves of x / scale[b] (see nppc_gemm_f16_tn_ex).
+ * nppc_tcn_cl_scale:   scale[b] = max(max|x[b]|, 1), inv_scale[b] = 1/scale[b] of a [B, n_per_sample] f32 tensor (two launches).
  * nppc_tcn_cl_pack:    x [B,C,T'] f32 -> x32 [M,Kp] f32 (residual stream, rows padded like xh; padding never read) and xh [M,Kp]
  *                      fp16 (GEMM operand; the K-padding columns [C,Kp) are written as zeros here and stay zero).
  * nppc_prelu_stats_cl: stats[b] = (sum, sum^2) of PReLU(y1 + bias[c]) over the sample, y1 [M,512] fp16.
@@ -224,16 +271,17 @@ int nppc_gemm_f16_tn(const void* A, const void* W, const float* bias, void* C, l
  *                      fp16(relu(x32)) when relu_h (the stack's trailing ReLU before fc_output_layer).
  * nppc_tcn_cl_unpack:  o [M,Np] fp16 (+bias, optional ReLU) -> [B,C,T'] f32. */
 int nppc_tcn_cl_scale(const float* x, int B, long long n_per_sample, float* scale, float* inv_scale, void* stream);
-int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh, void* stream);
-int nppc_tcn_cl_unpack(const void* o, int B, int C, int T, int Np, const float* scale /* [B] or NULL */, const float* bias,
-                       int relu, float* out, void* stream);
+int nppc_tcn_cl_pack(const float* x, int B, int C, int T, int Kp, const float* inv_scale, float* x32, void* xh, int split,
+                     void* stream);
+int nppc_tcn_cl_unpack(const void* o, int o_f32 /* o is fp32 instead of fp16 */, int B, int C, int T, int Np,
+                       const float* scale /* [B] or NULL */, const float* bias, int relu, float* out, void* stream);
 int nppc_prelu_stats_cl(const void* y1, int B, int T, int H, const float* scale, const float* bias, const float* prelu_a,
                         double* stats, void* stream);
 int nppc_tcn_mid_cl(const void* y1, int B, int T, int H, const float* scale, const float* bias1, const float* prelu1_a,
                     const double* stats1, const float* gamma1, const float* beta1, const float* dw_w, const float* dw_b,
                     int dilation, const float* prelu2_a, void* z, double* stats2, void* stream);
 int nppc_tcn_out_cl(const void* o, float* x32, int B, int T, int C, int Np, int Kp, int H, const double* stats2, const float* u,
-                    const float* vb, const float* inv_scale, void* xh, int relu_h, void* stream);
+                    const float* vb, const float* inv_scale, void* xh, int relu_h, int split, void* stream);
 
 
 #ifdef __cplusplus

@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 def load_golden(name):
     import torch
     z = np.load(os.path.join(GOLD, name + ".npz"))
-    return {k: torch.from_numpy(z[k]) for k in z.files}
+    return {k: torch.from_numpy(z[k]) for k in z.files if z[k].dtype.kind in "fiub"}   # (string arrays: names only)
 
 
 def rel_err(a, b):
