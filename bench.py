@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
-    ap.add_argument("--lstm-impl", default=os.environ.get("NPPC_LSTM_IMPL", "tc"), choices=["tc", "f32"])
+    ap.add_argument("--lstm-impl", default=os.environ.get("NPPC_LSTM_IMPL", "tc"), choices=["tc", "f32", "tcp"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline leg (N = 1 only)")
@@ -284,7 +284,7 @@ def main():
     R, Tp = (lstm_events[0][2], lstm_events[0][3]) if lstm_events else (B * F, TP)
     flops = LSTM_FLOP_PER_SEQ_STEP * R * Tp
     pk = peaks()
-    achieved = flops / (lstm_ms * 1e-3) / 1e12
+    achieved = flops / (max(lstm_ms, 1e-9) * 1e-3) / 1e12 if lstm_events else 0.0
     roofline = {"bound": "tensor", "kernel": f"sub-band LSTM (2 layers + fc), impl={args.lstm_impl}, per nppc_lstm_forward call",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 # DRAM bytes of one nppc_lstm_forward call (rec layer 0 + Zx GEMM + rec layer 1) from the ncu --set full capture

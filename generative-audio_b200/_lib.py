@@ -24,6 +24,7 @@ PROTOTYPES = {
     "nppc_build_cirm": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "nppc_offline_laplace_norm": (_i, [_p, _i, _ll, _p, _p, _p]),
     "nppc_pad_offline_laplace_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "nppc_cancel_depth": (_i, [_p, _i, _ll, C.c_double, _p, _p, _p]),
     "nppc_cumulative_laplace_norm": (_i, [_p, _i, _i, _i, _p, _p]),
     "nppc_unfold": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_drop_band": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),

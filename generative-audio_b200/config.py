@@ -1,7 +1,8 @@
 """Pydantic configs with the reference's field names and defaults, so reference yaml/dicts construct them
 unchanged: FullSubNetPlusConfig (fullsubnet_plus.py:18-42), MultiDirectionConfig (networks.py:9-14),
 AudioPCWrapperConfig (pc_wrapper.py:46-51), StftConfig (utils.py:14-17), NPPCModelConfig (nppc_model.py:13-22).
-Extra knob (not in the reference): `lstm_impl` selects the LSTM kernel ("tc" = fp16-operand / fp32-accumulate tcgen05 kernels for the LSTM and the TCN 1x1 convolutions, "f32" = fp32 SIMT LSTM + fp32 TCN)."""
+Extra knob (not in the reference): `lstm_impl` selects the LSTM kernel ("tc" = fp16-operand / fp32-accumulate tcgen05 kernels for the LSTM and the TCN 1x1 convolutions, "f32" = fp32 SIMT LSTM + fp32 TCN, "tcp" = split-precision tensor-core path (hi + lo fp16 operands: fp32-class accuracy on tcgen05), "auto" = "tc" with the
+utterances whose normaliser means cancel re-run through "tcp" (NPPCModel.forward, DESIGN.md "Conditioning"))."""
 from typing import List, Literal
 
 import pydantic
@@ -57,4 +58,4 @@ class NPPCModelConfig(pydantic.BaseModel):
     audio_pc_wrapper_configuration: AudioPCWrapperConfig
     stft_configuration: StftConfig
     device: Literal["cpu", "cuda"] = "cuda"
-    lstm_impl: Literal["tc", "f32"] = "tc"
+    lstm_impl: Literal["tc", "f32", "tcp", "auto"] = "tc"

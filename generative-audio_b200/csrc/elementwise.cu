@@ -144,6 +144,33 @@ __global__ void __launch_bounds__(TPB) sample_sum_kernel(const float* __restrict
     if (threadIdx.x == 0) atomicAdd(&sums[b], acc);
 }
 
+// per-sample (sum x, sum |x|) in fp64 -> cancellation depth of the offline normaliser's divisor, see nppc_cancel_depth
+__global__ void __launch_bounds__(TPB) sample_sum_abs_kernel(const float* __restrict__ x, long long n, double* __restrict__ sums) {
+    __shared__ double red[32];
+    const int b = blockIdx.y;
+    const float* xb = x + (size_t)b * n;
+    double acc = 0.0, aab = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = (double)xb[i];
+        acc += v;
+        aab += fabs(v);
+    }
+    acc = nppc::block_sum(acc, red);
+    aab = nppc::block_sum(aab, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&sums[2 * b], acc);
+        atomicAdd(&sums[2 * b + 1], aab);
+    }
+}
+__global__ void cancel_depth_finish_kernel(const double* __restrict__ sums, int B, double count, float* __restrict__ depth) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double mean = sums[2 * b] / count, mabs = sums[2 * b + 1] / count;
+    const float d = (float)(mabs / (fabs(mean) + 1e-5) / sqrt(count));
+    depth[b] = fmaxf(depth[b], d);
+}
+
 __global__ void __launch_bounds__(TPB) offline_norm_kernel(const float* __restrict__ x, long long n,
                                                           const double* __restrict__ sums, double count,
                                                           float* __restrict__ y) {
@@ -463,6 +490,20 @@ extern "C" int nppc_offline_laplace_norm(const float* x, int B, long long n, dou
     int gx = per_sample_grid(n, B);
     sample_sum_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, n, sums);
     offline_norm_kernel<<<dim3(gx, B), TPB, 0, s>>>(x, n, sums, (double)n, y);
+    NPPC_COUNT_LAUNCH(2);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+// depth[b] = max(depth[b], (mean|x_b| / (|mean x_b| + 1e-5)) / sqrt(count)): how much deeper the divisor of
+// offline_laplace_norm (base_model.py:219-222, a signed mean for the real / imag streams) cancels than a random-sign sum of
+// `count` terms would (depth ~ 1).  Errors of relative size eps in x come out of the normaliser amplified by ~ eps * depth.
+extern "C" int nppc_cancel_depth(const float* x, int B, long long n, double count, double* sums, float* depth, void* stream) {
+    NPPC_CHECK_ARG(x && sums && depth && B > 0 && n > 0 && count > 0, "nppc_cancel_depth: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    NPPC_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, s));
+    sample_sum_abs_kernel<<<dim3(per_sample_grid(n, B), B), TPB, 0, s>>>(x, n, sums);
+    cancel_depth_finish_kernel<<<nppc::cdiv(B, 128), 128, 0, s>>>(sums, B, count, depth);
     NPPC_COUNT_LAUNCH(2);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

@@ -15,7 +15,7 @@ from .config import FullSubNetPlusConfig
 from .modules import ChannelTimeSenseSELayer, SequenceModel
 
 KP = 64  # padded feature width of the packed LSTM input (34 real features)
-_IMPL = {"f32": 0, "tc": 1}
+_IMPL = {"f32": 0, "tc": 1, "tcp": 2}   # tcp: split-precision tensor-core path (fp32-class accuracy)
 
 
 class FullSubNet_Plus(nn.Module):
@@ -60,7 +60,11 @@ class FullSubNet_Plus(nn.Module):
         self.fb_model_real = SequenceModel(**kw)
         self.fb_model_imag = SequenceModel(**kw)
         import os
-        tc = self.lstm_impl == "tc" and os.environ.get("NPPC_TCN_TC", "1") != "0"   # 1x1 convs on the tcgen05 GEMM (row N2)
+        # 1x1 convs on the tcgen05 GEMM (row N2) for "tc"; the accuracy-first "tcp" path keeps the fp32 TCN (fp32 SGEMM + the
+        # fused kernels): on a digitally silent utterance the residual stream IS the sum of the block outputs, so the fp16
+        # y1 / z / o intermediates of the channel-last path show up at 1.6e-3 in pred_crm (tests/golden/speech12.npz, #3),
+        # and next to the split-precision LSTM the fp32 TCN costs < 10 % of the step
+        tc = self.lstm_impl == "tc" and os.environ.get("NPPC_TCN_TC", "1") != "0"
         for m in (self.fb_model, self.fb_model_real, self.fb_model_imag):
             m.use_tc_convs = tc
             m.tc_split = os.environ.get("NPPC_TCN_SPLIT", "1") != "0"
@@ -80,7 +84,7 @@ class FullSubNet_Plus(nn.Module):
         dt = torch.float16 if impl == 1 else torch.float32
         G = self.num_groups_in_drop_band
         if self.norm_type == "offline_laplace_norm":
-            xs, R = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt)
+            xs, R = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt, pad_rows=(impl == 2))
             Fp = R // B
         else:
             # explicit route through the standalone kernels (cumulative norm is not fused into the packer)
@@ -93,7 +97,7 @@ class FullSubNet_Plus(nn.Module):
             Fp = sb.shape[1]
             S = sb.shape[2]
             R = B * Fp
-            xs = torch.zeros(Tp, ops.padded_rows(R, dt), KP, device=fb.device, dtype=dt)
+            xs = torch.zeros(Tp, ops.padded_rows(R, torch.float16 if impl == 2 else dt), KP, device=fb.device, dtype=dt)
             xs[:, :R, :S] = sb.reshape(R, S, Tp).permute(2, 0, 1).to(dt)
         return self.sb_model.lstm_forward(xs, impl, R), Fp
 

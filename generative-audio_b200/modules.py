@@ -236,8 +236,21 @@ class SequenceModel(nn.Module):
             self._plan_key = key
         return self._plan
 
+    def lstm_params(self):
+        """The ten tensors of the 2-layer LSTM + fc in the order the stepwise kernels take them."""
+        m = self.sequence_model
+        return [getattr(m, f"{k}_l{l}") for l in (0, 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")] + \
+            [self.fc_output_layer.weight, self.fc_output_layer.bias]
+
     def lstm_forward(self, xs, impl: int, R: int = None):
-        """xs [T', R_stride, KP] -> [R, O, T'] (the layout SequenceModel.forward returns, sequence_model.py:122)."""
+        """xs [T', R_stride, KP] -> [R, O, T'] (the layout SequenceModel.forward returns, sequence_model.py:122).
+        impl 0: fp32 SIMT; 1: fp16 tensor cores (persistent CTA-pair kernel for H = 384, the stepwise kernel for every other
+        hidden size, e.g. FullSubNet's 257 -> 512 full-band LSTM); 2: split-precision stepwise tensor-core kernel (fp32 xs)."""
         if self.output_activate_function:
             raise NotImplementedError("sb_output_activate_function is False in every reference config")
+        H = self.sequence_model.hidden_size
+        if impl == 2:
+            return ops.lstm_step_forward(self.lstm_params(), xs, R, precise=True)[0]
+        if impl == 1 and H != 384:
+            return ops.lstm_step_forward(self.lstm_params(), xs, R)[0]
         return self._lstm_plan().forward(xs, impl, R)

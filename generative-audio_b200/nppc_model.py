@@ -1,5 +1,6 @@
 """NPPCModel (a13): drop-in for nppc_audio/nppc_model.py:25-132 — same constructor config, forward /
 get_pred_crm signatures, sub-module attribute names and state_dict keys; CUDA only (no CPU fallback)."""
+import os
 from pathlib import Path
 
 import torch
@@ -28,31 +29,80 @@ class NPPCModel(nn.Module):
         if config.device != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("generative-audio_b200.NPPCModel runs on CUDA (sm_100a) only: there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device())
+        impl0 = "tc" if config.lstm_impl == "auto" else config.lstm_impl
         self.pretrained_restoration_model = load_pretrained_model(
-            config.pretrained_restoration_model_path, config.pretrained_restoration_model_configuration, config.lstm_impl)
+            config.pretrained_restoration_model_path, config.pretrained_restoration_model_configuration, impl0)
         self.pretrained_restoration_model.to(self.device).eval()
-        self.audio_pc_wrapper = AudioPCWrapper(config.audio_pc_wrapper_configuration, lstm_impl=config.lstm_impl)
+        self.audio_pc_wrapper = AudioPCWrapper(config.audio_pc_wrapper_configuration, lstm_impl=impl0)
         self.audio_pc_wrapper.to(self.device)
+        # lstm_impl="auto": utterances whose enhanced real / imag normaliser means cancel deeper than this (x the depth of a
+        # random-sign sum) are re-run through the split-precision path; expected fp16-path error ~ 7e-4 * depth * O(1..6)
+        self.auto_depth_threshold = float(os.environ.get("NPPC_AUTO_DEPTH", "2.5"))
+        self.last_auto = None
+
+    def _set_impl(self, impl: str):
+        """Switch both networks between the fp16 tensor-core path ("tc"), the split-precision one ("tcp") and fp32 SIMT."""
+        tc_convs = impl == "tc" and os.environ.get("NPPC_TCN_TC", "1") != "0"
+        for net in (self.pretrained_restoration_model, self.audio_pc_wrapper.net):
+            net.lstm_impl = impl
+            for m in (net.fb_model, net.fb_model_real, net.fb_model_imag):
+                m.use_tc_convs = tc_convs
 
     def _stft(self, wave):
         c = self.config.stft_configuration
         return ops.stft_mri(wave.to(self.device, non_blocking=True), c.nfft, c.hop_length, c.win_length)
 
     @torch.no_grad()
-    def forward_stages(self, noisy_waveform: torch.Tensor):
+    def forward_stages(self, noisy_waveform: torch.Tensor, taps: dict = None):
         """STFT -> frozen backbone -> decompress + conj(M)*N (utils.py:241-249 quirk) -> PC head (pre-Gram-Schmidt).
-        Returns (head [B,n,2,F',T], pred_crm [B,2,F,T])."""
+        Returns (head [B,n,2,F',T], pred_crm [B,2,F,T]); `taps` (optional dict) receives the noisy / enhanced spectra."""
         mag, real, imag = self._stft(noisy_waveform)
         pred_crm = self.pretrained_restoration_model(mag, real, imag)
         emag, ereal, eimag = ops.crm_decompress_apply(pred_crm, real, imag, conj=True)
         head = self.audio_pc_wrapper.head(mag, real, imag, emag[:, None], ereal[:, None], eimag[:, None])
+        if taps is not None:
+            taps.update(mag=mag, real=real, imag=imag, emag=emag, ereal=ereal, eimag=eimag)
         return head, pred_crm
+
+    @torch.no_grad()
+    def conditioning(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
+        """Per-utterance cancellation depth [B] of the PC head's enhanced real / imag normalisers (the amplifier of the fp16
+        path's backbone error, DESIGN.md "Conditioning"), from one pass of the current path."""
+        taps = {}
+        self.forward_stages(noisy_waveform, taps)
+        return self._depth(taps)
+
+    def _depth(self, taps):
+        la = self.audio_pc_wrapper.net.look_ahead
+        Fq, T = taps["ereal"].shape[-2:]
+        count = Fq * (T + la)     # the reference's mean runs over the zero-padded look-ahead frames too
+        d = ops.cancel_depth(taps["ereal"], count)
+        return ops.cancel_depth(taps["eimag"], count, d)
 
     @torch.no_grad()
     def forward(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
         """noisy_waveform [B, L] -> w_mat [B, n_dirs, 2, F', T]."""
-        head, _ = self.forward_stages(noisy_waveform)
-        return ops.gram_schmidt_complex(head)
+        if self.config.lstm_impl != "auto":
+            head, _ = self.forward_stages(noisy_waveform)
+            return ops.gram_schmidt_complex(head)
+        # auto: fp16 tensor-core pass for everybody, split-precision re-run for the utterances whose normalisers cancel
+        if self.audio_pc_wrapper.net.num_groups_in_drop_band > 1 and noisy_waveform.shape[0] > 1:
+            raise NotImplementedError('lstm_impl="auto" needs num_groups_in_drop_band == 1 (drop_band interleaves the batch)')
+        taps = {}
+        self._set_impl("tc")
+        head, _ = self.forward_stages(noisy_waveform, taps)
+        w = ops.gram_schmidt_complex(head)
+        depth = self._depth(taps)
+        idx = torch.nonzero(depth > self.auto_depth_threshold).flatten()      # host sync: the price of the routing decision
+        if idx.numel():
+            self._set_impl("tcp")
+            try:
+                hp, _ = self.forward_stages(noisy_waveform.to(self.device)[idx].contiguous())
+                w[idx] = ops.gram_schmidt_complex(hp)
+            finally:
+                self._set_impl("tc")
+        self.last_auto = dict(depth=depth, rerouted=idx)
+        return w
 
     @torch.no_grad()
     def forward_host(self, noisy_host: torch.Tensor, out_host: torch.Tensor = None) -> torch.Tensor:

@@ -124,6 +124,19 @@ def pad_offline_laplace_norm(x: torch.Tensor, look_ahead: int):
     return y
 
 
+def cancel_depth(x: torch.Tensor, count: float, depth: torch.Tensor = None):
+    """depth[b] = max(depth[b], cancellation depth of the offline normaliser's mean over x[b]) (see nppc_cancel_depth)."""
+    x = _f32(x)
+    _chk(x, depth)
+    B = x.shape[0]
+    if depth is None:
+        depth = torch.zeros(B, device=x.device, dtype=torch.float32)
+    sums = torch.empty(2 * B, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().nppc_cancel_depth(x.data_ptr(), B, x[0].numel(), float(count), sums.data_ptr(), depth.data_ptr(), _stream()),
+               "nppc_cancel_depth")
+    return depth
+
+
 def cumulative_laplace_norm(x: torch.Tensor):
     """BaseModel.cumulative_laplace_norm (base_model.py:227-257): x [B,C,F,T]."""
     x = _f32(x)
@@ -373,22 +386,24 @@ def padded_rows(R: int, dtype) -> int:
     return -(-R // TC_ROW_TILE) * TC_ROW_TILE if dtype == _F16 else R
 
 
-def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int = 64, dtype=torch.float32):
+def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int = 64, dtype=torch.float32, pad_rows: bool = False,
+                 want_sums: bool = False):
     """Fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> time-major LSTM input [T', R_stride, KP]
-    (R = B*F' real rows; rows R..R_stride-1 are zero padding for the tensor-core path). Returns (xs, R)."""
+    (R = B*F' real rows; rows R..R_stride-1 are zero padding for the tensor-core paths: always for fp16, for fp32 when
+    pad_rows). Returns (xs, R) or (xs, R, sums [B] fp64 = per-sample sum of the un-normalised sub-band tensor)."""
     nbr_src, fb, fbr, fbi = (_f32(v) for v in (nbr_src, fb, fbr, fbi))
     _chk(nbr_src, fb, fbr, fbi)
     B, F, Tp = nbr_src.shape
     G = groups if (groups > 1 and B > 1) else 1
     R = B * (F // G)
-    RS = padded_rows(R, dtype)
+    RS = padded_rows(R, _F16 if pad_rows else dtype)
     xs = torch.empty(Tp, RS, KP, device=fb.device, dtype=dtype)
     sums = torch.empty(B, device=fb.device, dtype=torch.float64)
     _lib.check(_lib.load().nppc_subband_pack(nbr_src.data_ptr(), fb.data_ptr(), fbr.data_ptr(), fbi.data_ptr(), B, F, Tp,
                                              num_neighbor, groups, KP, RS, sums.data_ptr(),
                                              xs.data_ptr() if dtype == torch.float32 else 0,
                                              xs.data_ptr() if dtype == _F16 else 0, _stream()), "nppc_subband_pack")
-    return xs, R
+    return (xs, R, sums) if want_sums else (xs, R)
 
 
 class LstmPlan:

@@ -92,6 +92,12 @@ int nppc_offline_laplace_norm(const float* x, int B, long long n, double* sums, 
 /* Fused F.pad(x,[0,look_ahead]) (fullsubnet_plus.py:158-160) + offline_laplace_norm: x [B,F,T] -> y [B,F,T+la]. */
 int nppc_pad_offline_laplace_norm(const float* x, int B, int F, int T, int look_ahead, double* sums, float* y,
                                   void* stream);
+/* Conditioning diagnostic of the offline normaliser (base_model.py:219-222): depth[b] = max(depth[b], (mean|x_b| /
+ * (|mean x_b| + 1e-5)) / sqrt(count)) for x [B, n]; count = the number of elements the reference's mean runs over (n plus the
+ * zero look-ahead frames).  ~1 for a random-sign sum; errors of relative size eps in x leave the normaliser amplified by
+ * ~eps * depth.  NPPCModel(lstm_impl="auto") re-runs utterances above a threshold through the split-precision path. */
+int nppc_cancel_depth(const float* x, int B, long long n, double count, double* sums /* [2B] scratch */, float* depth /* [B], in/out */,
+                      void* stream);
 /* cumulative_laplace_norm (base_model.py:227-257): x [BC,F,T] -> y; y[f,t] = x[f,t]/(cumsum_t(sum_f x)/(F(t+1)) + eps). */
 int nppc_cumulative_laplace_norm(const float* x, int BC, int F, int T, float* y, void* stream);
 

@@ -26,11 +26,15 @@ def main():
     report = {}
     for name in args.cases.split(","):
         for impl in args.impls.split(","):
-            if name == "model_b64" and impl == "f32":
+            if name == "model_b64" and impl == "f32":   # (tcp, the split-precision tensor-core path, is fast enough)
                 continue   # the fp32 SIMT LSTM at B = 64 is minutes of GPU time; tc is the benchmarked path
             r = P.run_case(name, impl)
+            if "_auto" in r:
+                a = r.pop("_auto")
+                report[f"{name}/auto/routing"] = a
+                print(f"{name:16s} auto: {len(a['rerouted'])} of {len(a['depth'])} utterances re-run through tcp (depth > {a['threshold']}): {a['rerouted']}", flush=True)
             for k, v in r.items():
-                bud = P.budget(impl, v["gap"])
+                bud = P.budget(impl, v["gap"], k)
                 e = np.minimum(v["err32"], v["err64"])
                 report[f"{name}/{impl}/{k}"] = dict(err32=v["err32"].tolist(), err64=v["err64"].tolist(), gap=v["gap"].tolist(),
                                                     budget=bud.tolist(), within=bool((e <= bud).all()))
