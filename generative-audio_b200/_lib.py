@@ -28,6 +28,7 @@ PROTOTYPES = {
     "nppc_cumulative_laplace_norm": (_i, [_p, _i, _i, _i, _p, _p]),
     "nppc_unfold": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_drop_band": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_complex_lincomb": (_i, [_p, _p, _p, _i, _i, _ll, _p, _p, _p]),
     "nppc_gs_scratch_bytes": (_sz, [_i, _i]),
     "nppc_gram_schmidt_complex": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
     "nppc_gram_schmidt_real": (_i, [_p, _i, _i, _ll, _p, _p, _p]),

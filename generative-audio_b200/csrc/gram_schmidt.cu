@@ -412,6 +412,50 @@ int run(const float* x, const float* gt, const float* pred, int B, int n, long l
 
 }  // namespace
 
+// out_i = sum_{k<n} C[i][k] x_k + C[i][n] (gt - pred), complex coefficients: the one streaming pass of the Gram-Schmidt + loss
+// BACKWARD (gs_backward.py: the gradient w.r.t. every head output lies in the span of the n directions and the error vector).
+// grid (chunks, B); coefficients [B][n][n+1][2] fp32 staged in shared memory.
+__global__ void __launch_bounds__(TPB) complex_lincomb_kernel(const float* __restrict__ x, const float* __restrict__ gt,
+                                                             const float* __restrict__ pred, int n, long long P,
+                                                             const float* __restrict__ coef, float* __restrict__ out) {
+    __shared__ float2 C[12 * 13];
+    const int b = blockIdx.y, n1 = n + 1;
+    for (int i = threadIdx.x; i < n * n1; i += blockDim.x)
+        C[i] = make_float2(coef[((size_t)b * n * n1 + i) * 2], coef[((size_t)b * n * n1 + i) * 2 + 1]);
+    __syncthreads();
+    const float* xb = x + (size_t)b * n * 2 * P;
+    float* ob = out + (size_t)b * n * 2 * P;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        float vr[13], vi[13];
+        for (int k = 0; k < n; ++k) { vr[k] = xb[(size_t)k * 2 * P + p]; vi[k] = xb[(size_t)k * 2 * P + P + p]; }
+        load_vec<true>(x, gt, pred, b, n, n, P, p, vr[n], vi[n]);
+        for (int i = 0; i < n; ++i) {
+            float wr = 0.f, wi = 0.f;
+            for (int k = 0; k < n1; ++k) {
+                const float2 c = C[i * n1 + k];
+                wr += c.x * vr[k] - c.y * vi[k];
+                wi += c.x * vi[k] + c.y * vr[k];
+            }
+            ob[(size_t)i * 2 * P + p] = wr;
+            ob[(size_t)i * 2 * P + P + p] = wi;
+        }
+    }
+}
+
+extern "C" int nppc_complex_lincomb(const float* x, const float* gt, const float* pred, int B, int n, long long P,
+                                    const float* coef, float* out, void* stream) {
+    NPPC_CHECK_ARG(x && gt && pred && coef && out && B > 0 && P > 0 && n >= 1 && n <= 12, "nppc_complex_lincomb: bad arguments");
+    NPPC_CHECK_ARG(B <= 65535, "nppc_complex_lincomb: B too large");
+    int chunks = nppc::cdiv((long long)nppc::sm_count() * 8, B);
+    const int cap = nppc::cdiv(P, TPB);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    complex_lincomb_kernel<<<dim3(chunks, B), TPB, 0, (cudaStream_t)stream>>>(x, gt, pred, n, P, coef, out);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
 extern "C" size_t nppc_gs_scratch_bytes(int B, int n) {
     (void)n;
     return sizeof(SampleScratch) * (size_t)(B > 0 ? B : 0);

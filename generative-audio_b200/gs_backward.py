@@ -1,0 +1,51 @@
+"""Backward of Gram-Schmidt (pc_wrapper.py:8-44, with its conjugated coefficient and the detach() of the normaliser at :37) +
+the NPPC projection / second-moment objective (trainer.py:259-298,337-342, with the detach() at :295), in COEFFICIENT SPACE.
+
+Every vector involved — the directions w_i, the error e = gt - pred and therefore the gradients — lies in the span of the
+n + 1 vectors {x_0 .. x_{n-1}, e} the forward pass already took the Gram matrix of, so the whole backward is O(n^3) complex
+arithmetic per utterance on (n+1)-vectors plus ONE streaming pass that forms d objective / d x_i = sum_k C_ik x_k + C_in e
+(ops.complex_lincomb).  Pure tensor arithmetic on tiny tensors: runs on whatever device G lives on (CPU in the unit test
+against torch.autograd, CUDA in the training step).
+
+Derivation (delta = 1e-8, <u, v>_R = Re u^H v):  with nu_k = |w_k|, eps = |e|, q_k = w_k^H e,
+    pi_k^2 = |q_k|^2 / ((nu_k + delta)^2 (eps + delta)^2),   nu'_k = nu_k / (eps + delta)
+    objective = mean_b (1 - sum_k pi_k^2) + lambda mean_{b,k} (nu'_k^2 - sg(pi_k^2))^2
+    d objective / d w_k = alpha_k e + beta_k w_k
+        alpha_k = -(1/B) 2 conj(q_k) / ((nu_k + delta)^2 (eps + delta)^2)
+        beta_k  =  (1/B) 2 |q_k|^2 / ((nu_k + delta)^3 nu_k (eps + delta)^2) + (lambda / (B n)) 4 (nu'_k^2 - pi_k^2) / (eps + delta)^2
+Gram-Schmidt with constant (detached) a_j = w_j / |w_j|:  w_i = M_{i-1} .. M_0 x_i,  M_j v = v - a_j conj(a_j^H v).  M_j is
+symmetric for <.,.>_R, so d/dx_i = M_0 M_1 .. M_{i-1} (d/dw_i)."""
+import torch
+
+
+def gs_loss_grad_coeffs(G: torch.Tensor, A: torch.Tensor, lam: float, grad_scale=1.0) -> torch.Tensor:
+    """G [B, n+1, n+1] complex (G[j,k] = v_j^H v_k over the vectors x_0..x_{n-1}, e);  A [B, n, n] complex (w_i = sum_k A_ik x_k)
+    -> C [B, n, n+1] complex with d objective / d x_i = sum_k C[i,k] v_k  (times grad_scale, the incoming d/d objective)."""
+    B, n1, _ = G.shape
+    n = n1 - 1
+    cd = G.dtype
+    Wc = torch.zeros(B, n, n1, dtype=cd, device=G.device)
+    Wc[:, :, :n] = A.to(cd)
+    GW = torch.einsum("bmk,bjk->bjm", G, Wc)                  # (G w_j)[m]
+    nu2 = torch.einsum("bjm,bjm->bj", Wc.conj(), GW).real.clamp_min(0)
+    nu = nu2.sqrt()
+    eps = G[:, n, n].real.clamp_min(0).sqrt()
+    q = GW[:, :, n].conj()                                    # conj(e^H w_k)... = w_k^H e
+    q = torch.einsum("bjm,bm->bj", Wc.conj(), G[:, :, n])     # w_k^H e, explicit
+    d = 1e-8
+    e2 = (eps + d) ** 2
+    pi2 = (q.abs() ** 2) / ((nu + d) ** 2 * e2[:, None])
+    nup2 = nu2 / e2[:, None]
+    alpha = -(1.0 / B) * 2 * q.conj() / ((nu + d) ** 2 * e2[:, None])
+    beta = (1.0 / B) * 2 * (q.abs() ** 2) / ((nu + d) ** 3 * nu * e2[:, None]) + (lam / (B * n)) * 4 * (nup2 - pi2) / e2[:, None]
+    a = Wc / nu[:, :, None].to(cd)                            # detached normalised directions (no epsilon, pc_wrapper.py:37)
+    Ga = torch.einsum("bmk,bjk->bjm", G, a)                   # (G a_j)[m];  a_j^H v = sum_m conj((G a_j)[m]) ... see below
+    out = torch.zeros(B, n, n1, dtype=cd, device=G.device)
+    for i in range(n):
+        v = beta[:, i, None].to(cd) * Wc[:, i]
+        v[:, n] = v[:, n] + alpha[:, i]
+        for j in range(i - 1, -1, -1):
+            s = torch.einsum("bm,bm->b", Ga[:, j].conj(), v)  # a_j^H v = sum_k conj(a_j[m]) G[m,k] v[k] = (G a_j)^H v  (G Hermitian)
+            v = v - a[:, j] * s.conj()[:, None]
+        out[:, i] = v
+    return out * grad_scale

@@ -225,6 +225,45 @@ def gs_loss_fused(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
                    second_moment_mse=sm)
 
 
+GS_SCRATCH_BYTES = 13 * 13 * 2 * 8 + 12 * 12 * 2 * 4   # SampleScratch of gram_schmidt.cu
+
+
+def gs_loss_fused_with_gram(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """gs_loss_fused that also returns what the backward needs from the forward's scratch: the Hermitian Gram matrix
+    G [B, n+1, n+1] complex128 of (x_0 .. x_{n-1}, gt - pred) and the coefficient matrix A [B, n, n] complex64 (w = A x)."""
+    head, gt, pred = _f32(head), _f32(gt), _f32(pred)
+    _chk(head, gt, pred)
+    B, n = head.shape[:2]
+    P = head[0, 0, 0].numel()
+    w = torch.empty_like(head)
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs(B, n, head.device)
+    scr = _gs_scratch(B, n, head.device)
+    assert scr.numel() == B * GS_SCRATCH_BYTES
+    _lib.check(_lib.load().nppc_gs_loss_fused(head.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, scr.data_ptr(),
+                                              w.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(), w_norms.data_ptr(),
+                                              reconst.data_ptr(), sm.data_ptr(), _stream()), "nppc_gs_loss_fused")
+    scr = scr.reshape(B, GS_SCRATCH_BYTES)
+    Gu = torch.view_as_complex(scr[:, :13 * 13 * 16].contiguous().view(torch.float64).reshape(B, 13, 13, 2))[:, :n + 1, :n + 1]
+    up = torch.triu(Gu, diagonal=1)
+    G = torch.diag_embed(torch.diagonal(Gu, dim1=1, dim2=2).real.to(Gu.dtype)) + up + up.conj().transpose(1, 2)
+    A = torch.view_as_complex(scr[:, 13 * 13 * 16:].contiguous().view(torch.float32).reshape(B, 12, 12, 2))[:, :n, :n]
+    st = dict(err_norm=err_norm, err_proj=torch.view_as_complex(err_proj), w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm)
+    return w, st, G, A
+
+
+def complex_lincomb(x: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor, coef: torch.Tensor):
+    """out[b,i] = sum_k coef[b,i,k] x[b,k] + coef[b,i,n] (gt - pred)[b]; x [B,n,2,...], coef [B,n,n+1] complex."""
+    x, gt, pred = _f32(x), _f32(gt), _f32(pred)
+    c = torch.view_as_real(coef.to(torch.complex64).contiguous()).contiguous()
+    _chk(x, gt, pred, c)
+    B, n = x.shape[:2]
+    P = x[0, 0, 0].numel()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().nppc_complex_lincomb(x.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, c.data_ptr(), out.data_ptr(),
+                                                _stream()), "nppc_complex_lincomb")
+    return out
+
+
 def projection_loss(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
     """Loss statistics of NPPCAudioTrainer.base_step (trainer.py:259-298) for an explicit w_mat."""
     w_mat, gt, pred = _f32(w_mat), _f32(gt), _f32(pred)

@@ -3,8 +3,10 @@
 
 `base_step(batch)` (no grad): everything on the B200 kernels; the frozen backbone and the noisy STFT run ONCE (the reference
 runs the backbone twice and the noisy STFT three times); Gram-Schmidt + loss are two HBM passes in total.
-`base_step(batch, requires_grad=True)` / `train_step`: same statistics with an autograd graph through the PC head — the
-frozen half still runs on the hand-written kernels, the head's forward/backward on torch autograd (see training.py)."""
+`base_step(batch, requires_grad=True)` / `train_step`: same statistics with an autograd graph through the PC head whose heavy
+nodes are hand-written (training.py): stepwise tcgen05 LSTM forward + BPTT, tcgen05 GEMMs for every 1x1 convolution (forward,
+dX and dW), a coefficient-space Gram-Schmidt + objective backward; no nn.LSTM / F.conv1d launches.  Data parallel: gradients
+are all-reduced bucket by bucket while the backward is still running (training.GradBucketReducer)."""
 import torch
 
 from . import ops, training
@@ -21,8 +23,9 @@ class NPPCAudioStep:
     def __init__(self, nppc_model: NPPCModel, second_moment_loss_grace: float = 500, second_moment_loss_lambda: float = 1.0,
                  amp_dtype=None):
         self.nppc_model = nppc_model
-        self.amp_dtype = amp_dtype   # e.g. torch.bfloat16: autocast for the head's GEMM-shaped ops (BASELINE config 3)
+        self.amp_dtype = amp_dtype   # kept for API compatibility: the GEMM-shaped ops always run fp16-operand / fp32-accumulate
         self.step = 0
+        self._reducer = None
         self.second_moment_loss_grace = second_moment_loss_grace
         self.second_moment_loss_lambda = second_moment_loss_lambda
 
@@ -53,22 +56,23 @@ class NPPCAudioStep:
         feats, gt, pred = self._frozen_half(noisy, clean)
         lam = second_moment_lambda(self.step, self.second_moment_loss_grace, self.second_moment_loss_lambda)
         with torch.enable_grad():
-            head = training.head_forward_autograd(model.audio_pc_wrapper.net, *feats, amp_dtype=self.amp_dtype)
-            w_mat = training.gram_schmidt_autograd(head)
-            st = training.nppc_loss_autograd(w_mat, gt, pred, lam)
-        log = {"noisy_complex": noisy, "clean_complex": clean, "pred_crm": pred, "w_mat": w_mat.detach(),
-               "err_norm": st["err_norm"].detach(), "err_proj": st["err_proj"].detach(),
-               "err_proj_mag": st["err_proj_mag"].detach(), "w_norms": st["w_norms"].detach(),
-               "reconst_err": st["reconst_err"].detach(), "second_moment_mse": st["second_moment_mse"].detach(),
-               "objective": st["objective"].detach()}
-        return st["reconst_err"], st["objective"], log
+            head = training.head_forward_train(model.audio_pc_wrapper.net, *feats)
+            objective, w_mat, err_norm, err_proj, w_norms, reconst_err, second_moment = training.GsLossFn.apply(head, gt, pred, lam)
+        err_proj = torch.view_as_complex(err_proj)
+        log = {"noisy_complex": noisy, "clean_complex": clean, "pred_crm": pred, "w_mat": w_mat, "err_norm": err_norm,
+               "err_proj": err_proj, "err_proj_mag": err_proj.abs(), "w_norms": w_norms, "reconst_err": reconst_err,
+               "second_moment_mse": second_moment, "objective": objective.detach()}
+        return reconst_err, objective, log
 
     def train_step(self, batch, optimizer):
-        """zero_grad / backward / DP gradient all-reduce / optimizer.step (trainer.py:100-106) -> (objective, log)."""
+        """zero_grad / backward (+ overlapped DP gradient all-reduce) / optimizer.step (trainer.py:100-106) -> (objective, log)."""
+        if self._reducer is None:
+            self._reducer = training.GradBucketReducer(self.nppc_model.audio_pc_wrapper.parameters())
         optimizer.zero_grad(set_to_none=True)
+        self._reducer.reset()
         _, objective, log = self.base_step(batch, requires_grad=True)
         objective.backward()
-        training.allreduce_gradients(self.nppc_model.audio_pc_wrapper.parameters())
+        self._reducer.finish()
         optimizer.step()
         self.step += 1
         return objective.detach(), log

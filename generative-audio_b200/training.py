@@ -1,141 +1,332 @@
-"""Training step of the PC head (BASELINE config 3; reference: NPPCAudioTrainer.base_step, nppc_audio/trainer.py:234-317).
+"""Training step of the PC head (BASELINE config 3; reference: NPPCAudioTrainer.base_step + backward, nppc_audio/trainer.py:100-106,
+234-317) with a HAND-WRITTEN backward.  What runs where:
 
-What runs where in round 1:
-  * frozen FullSubNet+ backbone, all STFTs, cIRM build, cRM decompress/apply, drop_band  -> hand-written kernels (no grads
-    needed there: the reference wraps the backbone in no_grad, nppc_model.py:94);
-  * PC head forward + backward (TSSE, TCN, sub-band LSTM, Gram-Schmidt, projection loss)  -> torch autograd on the SAME
-    nn.Module parameters (cuDNN LSTM BPTT etc.).  The hand-written backward of the head is round-2 work; this keeps
-    `base_step(...)[1].backward()` + optimizer usable as a drop-in today.  The frozen backbone and the noisy STFT run
-    ONCE per step (the reference runs the backbone twice and the noisy STFT three times).
-  * data parallelism: one process per GPU, flat-bucket NCCL all-reduce (mean) of the head gradients after backward.
+  * frozen FullSubNet+ backbone, all STFTs, cIRM build, cRM decompress/apply, drop_band, the six input normalisers -> the
+    inference kernels (no gradient flows there: the reference wraps the backbone in no_grad, nppc_model.py:94);
+  * sub-band LSTM (2 layers + fc), forward AND backward -> the stepwise tcgen05 kernels of csrc/lstm_step.cu (SubbandLstmFn:
+    fused pack -> LSTM forward with saved gates; BPTT; weight gradients as MN-major tcgen05 GEMMs; gradient of the packed
+    input scattered back through drop_band / offline norm deterministically);
+  * Gram-Schmidt + objective, forward -> nppc_gs_loss_fused; backward -> coefficient-space solve (gs_backward.py) + ONE
+    streaming kernel (nppc_complex_lincomb), honouring both detach()s (pc_wrapper.py:37, trainer.py:295);
+  * TCN stacks: channel-last; every 1x1 convolution and the output Linear, forward AND both backward GEMMs (dX = dY W,
+    dW = dY^T X), on the in-house tcgen05 GEMMs (Conv1x1TCFn); PReLU / GroupNorm(1, C) / the dilated depthwise 3-tap
+    convolution between them are elementwise torch ops (shifted adds — no F.conv1d, no cuDNN);
+  * TSSE attention: windowed sums via cumsum + the tiny excitation MLP, elementwise torch ops.
+  No nn.LSTM / cuDNN RNN / F.conv1d launches in the step.  fp16 gradient operands carry a power-of-two loss scale.
+  * data parallelism: one process per GPU; gradients are all-reduced per bucket as soon as the bucket's last gradient has been
+    accumulated (GradBucketReducer: NCCL all-reduce overlapped with the rest of the backward; mean of per-rank objectives).
 """
-from typing import Iterable, Optional
+import math
+from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
-from .modules import TCN_DILATIONS
+from .gs_backward import gs_loss_grad_coeffs
+from .modules import TCN_DILATIONS, TCNBlock
 
 
-# ---- differentiable torch mirror of the PC head (same parameters as the kernels use) ---------------------------------
-def _offline_norm(x):
-    mu = x.reshape(x.shape[0], -1).mean(dim=1).reshape(-1, *([1] * (x.dim() - 1)))
-    return x / (mu + 1e-5)
+def _pow2_scale(t: torch.Tensor, target_log2: int) -> torch.Tensor:
+    """device scalar 2^k with max|t| * 2^k in [2^(target-1), 2^target) (1 when t == 0): no host synchronisation."""
+    m = t.detach().abs().max().clamp_min(1e-30)
+    return torch.exp2(torch.floor(target_log2 - torch.log2(m)) ).clamp(2.0 ** -60, 2.0 ** 60)
 
 
-def _tsse(m, x):
-    feats = [torch.relu(c[0](x).mean(dim=-1)) for c in (m.smallConv1d, m.middleConv1d, m.largeConv1d)]
+# ---- 1x1 convolution / Linear on the in-house tcgen05 GEMMs, forward + backward --------------------------------------
+def _split16(t):
+    """fp32 -> (hi, lo) fp16 halves with hi + lo = t to ~22 mantissa bits."""
+    hi = t.half()
+    return hi, (t - hi.float()).half()
+
+
+class Conv1x1TCFn(torch.autograd.Function):
+    """y [M, Np] = x [M, Kp] W^T (bias is added by the caller).  x: rows padded to a multiple of 128, columns to a multiple of
+    128 (zeros); W [N, K] fp32 master weight.  All three GEMMs (Y = X W^T, dX = dY W, dW = dY^T X) run on the in-house tcgen05
+    kernels with SPLIT-PRECISION fp16 operands (hi*hi + lo*hi + hi*lo, fp32 accumulate; power-of-two range scales): the
+    residual stream of the real / imag branches spans 5 decades and scalar gradients (PReLU slopes, the 3-tap attention mix)
+    are heavily cancelling sums — plain fp16 operands measured 5e-2 on them against the reference's fp32 autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        M, Kp = x.shape
+        N, K = w.shape
+        Np = -(-N // 128) * 128
+        sx = _pow2_scale(x, 14)
+        xh, xl = _split16(x * sx)
+        wp = torch.zeros(Np, Kp, device=x.device, dtype=torch.float32)
+        wp[:N, :K] = w.detach().clamp(-65504, 65504)
+        wh, wl = _split16(wp)
+        y = ops.gemm_f16_tn_ex(torch.cat([xh, xl], dim=1), torch.cat([wh, wh, wl], dim=1), out_f32=True)
+        y.mul_(1.0 / sx)
+        ctx.save_for_backward(xh, xl, wh, wl, sx)
+        ctx.shape = (N, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, xl, wh, wl, sx = ctx.saved_tensors
+        N, K = ctx.shape
+        sy = _pow2_scale(dy, 10)
+        dh, dl = _split16(dy * sy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wth, wtl = wh.t().contiguous(), wl.t().contiguous()
+            dx = ops.gemm_f16_tn_ex(torch.cat([dh, dl], dim=1), torch.cat([wth, wth, wtl], dim=1), out_f32=True)   # dY W
+            dx.mul_(1.0 / sy)
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_f16_atb(torch.cat([dh, dl, dh], dim=0), torch.cat([xh, xh, xl], dim=0))[:N, :K] * (1.0 / (sy * sx))   # dY^T X
+        return dx, dw
+
+
+def conv1x1_tc(x, w):
+    return Conv1x1TCFn.apply(x, w)
+
+
+# ---- TSSE attention without convolutions -----------------------------------------------------------------------------
+def _tsse_gate(m, x):
+    """ChannelTimeSenseSELayer (attention_model.py:78-98) gate [B, C] for x [B, C, T] (x carries no gradient): the depthwise
+    valid convolution followed by the time average is a weighted sum of windowed sums of x."""
+    B, C, T = x.shape
+    cs = F.pad(torch.cumsum(x.double(), dim=-1), (1, 0))                              # cs[t] = sum_{u < t} x[u]
+    feats = []
+    for conv in (m.smallConv1d[0], m.middleConv1d[0], m.largeConv1d[0]):
+        k = conv.kernel_size[0]
+        L = T - k + 1
+        S = torch.stack([(cs[..., j + L] - cs[..., j]) for j in range(k)], dim=-1).float() / L    # [B, C, k] window means
+        feats.append(torch.relu((S * conv.weight[:, 0, :][None]).sum(-1) + conv.bias[None]))
     s = m.feature_concate_fc(torch.stack(feats, dim=-1))[..., 0]
-    g = torch.sigmoid(m.fc2(torch.relu(m.fc1(s))))
-    return x * g[:, :, None]
+    return torch.sigmoid(m.fc2(torch.relu(m.fc1(s))))
 
 
-def _tcn(seq_model, x):
-    for blk in list(seq_model.sequence_model)[:len(TCN_DILATIONS)]:
-        y = blk.norm1(blk.prelu1(blk.conv1x1(x)))
-        y = blk.norm2(blk.prelu2(blk.depthwise_conv(y)))
-        x = x + blk.sconv(y)
-    o = seq_model.fc_output_layer(torch.relu(x).permute(0, 2, 1))
-    return torch.relu(o).permute(0, 2, 1)
+# ---- TCN stack, channel-last, 1x1 convolutions on the tcgen05 GEMMs -----------------------------------------------------
+def _groupnorm1_cl(y, B, T, gamma, beta, eps=1e-8):
+    """GroupNorm(1, C) on channel-last rows y [B*T, C] (per-sample moments over all (T, C), biased variance)."""
+    v = y.reshape(B, -1)
+    mu = v.mean(dim=1, keepdim=True)
+    var = v.var(dim=1, unbiased=False, keepdim=True)
+    return ((v - mu) * torch.rsqrt(var + eps)).reshape(y.shape) * gamma[None, :] + beta[None, :]
 
 
-def _unfold(x, n):
-    """[B,F,T] -> [B,F,2n+1,T] with reflect padding along F (base_model.py:33-46)."""
-    Fq = x.shape[1]
-    idx = torch.arange(Fq, device=x.device)[:, None] + torch.arange(2 * n + 1, device=x.device)[None, :] - n
-    idx = torch.where(idx < 0, -idx, idx)
-    idx = torch.where(idx > Fq - 1, 2 * (Fq - 1) - idx, idx)
-    return x[:, idx, :]
+def _dwconv3_cl(y, B, T, weight, bias, d):
+    """depthwise Conv1d(k=3, dilation d, zero padding d) along time on channel-last rows y [B*T, C] as three shifted adds."""
+    C = y.shape[1]
+    v = y.reshape(B, T, C)
+    p = F.pad(v, (0, 0, d, d))
+    k = weight[:, 0, :]                                                             # [C, 3]
+    out = p[:, 0:T] * k[None, None, :, 0] + v * k[None, None, :, 1] + p[:, 2 * d:2 * d + T] * k[None, None, :, 2] + bias[None, None, :]
+    return out.reshape(B * T, C)
 
 
-def _drop_band(x, G):
-    B, _, Fq, _ = x.shape
-    assert B > G, f"Batch size = {B}, num_groups = {G}. The batch size should larger than the num_groups."
-    if G <= 1:
-        return x
-    Fq -= Fq % G
-    return torch.cat([x[g::G, :, g:Fq:G, :] for g in range(G)], dim=0)
+def _prelu(v, a):
+    return torch.where(v >= 0, v, a * v)
 
 
-def head_forward_autograd(net, nmag, nreal, nimag, emag, ereal, eimag, amp_dtype=None):
-    """MultiDirectionFullSubNet_Plus.forward (networks.py:63-163) in differentiable torch ops -> [B, n, 2, F', T].
-    amp_dtype (e.g. torch.bfloat16, BASELINE config 3): the GEMM-shaped parts (TCN convolutions, LSTM, fc) run under
-    torch.autocast in that dtype; normalisers, attention, Gram-Schmidt and the loss stay fp32."""
-    amp = lambda: torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None)
+def _pad_rows(v, Mp):
+    return v if v.shape[0] == Mp else F.pad(v, (0, 0, 0, Mp - v.shape[0]))
+
+
+def tcn_forward_train(seq_model, x):
+    """SequenceModel TCN branch (sequence_model.py:47-58,106-112; causal_conv.py:96-108) for x [B, C, T] -> [B, O, T]."""
+    if seq_model.output_activate_function not in ("ReLU",):
+        raise NotImplementedError("training path: the full-band models use output_activate_function='ReLU' (every reference config)")
+    B, C, T = x.shape
+    M = B * T
+    Mp, Cp = -(-M // 128) * 128, -(-C // 128) * 128
+    xr = F.pad(x.permute(0, 2, 1).reshape(M, C), (0, Cp - C))                       # residual stream [M, Cp], zero pad columns
+    blocks = [m for m in seq_model.sequence_model if isinstance(m, TCNBlock)]
+    for blk in blocks:
+        y = conv1x1_tc(_pad_rows(xr, Mp), blk.conv1x1.weight[:, :, 0])[:M, :512] + blk.conv1x1.bias[None, :]
+        y = _groupnorm1_cl(_prelu(y, blk.prelu1.weight), B, T, blk.norm1.weight, blk.norm1.bias)
+        y = _dwconv3_cl(y, B, T, blk.depthwise_conv.weight, blk.depthwise_conv.bias, blk.dilation)
+        y = _groupnorm1_cl(_prelu(y, blk.prelu2.weight), B, T, blk.norm2.weight, blk.norm2.bias)
+        o = conv1x1_tc(_pad_rows(y, Mp), blk.sconv.weight[:, :, 0])[:M, :C] + blk.sconv.bias[None, :]
+        xr = xr + F.pad(o, (0, Cp - C))
+    O = seq_model.fc_output_layer.weight.shape[0]
+    o = conv1x1_tc(_pad_rows(torch.relu(xr), Mp), seq_model.fc_output_layer.weight)[:M, :O] + seq_model.fc_output_layer.bias[None, :]
+    return torch.relu(o).reshape(B, T, O).permute(0, 2, 1).contiguous()
+
+
+# ---- sub-band pack + stepwise LSTM, forward + backward ------------------------------------------------------------------
+def _dropband_maps(B, Fq, G, device):
+    """row -> (sample, frequency) of the packed LSTM input after drop_band (feature.py:254-285): output batches are ordered by
+    group g = sample % G; row = ob * F' + j holds frequency g + G j of sample sb(ob)."""
+    if G <= 1 or B <= 1:
+        sb = torch.arange(B, device=device).repeat_interleave(Fq)
+        f = torch.arange(Fq, device=device).repeat(B)
+        return sb, f, Fq
+    Fg = Fq // G
+    order = torch.cat([torch.arange(g, B, G, device=device) for g in range(G)])   # sample of output batch ob
+    sb = order.repeat_interleave(Fg)
+    f = (order % G).repeat_interleave(Fg) + G * torch.arange(Fg, device=device).repeat(B)
+    return sb, f, Fg
+
+
+class SubbandLstmFn(torch.autograd.Function):
+    """(fb, fbr, fbi [B, F, T'] with gradient; nbr_src [B, F, T'] constant; ten LSTM / fc parameters) -> y [R, O, T'].
+    forward : fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> fp16 time-major input (nppc_subband_pack) ->
+              stepwise tcgen05 LSTM with saved gates (nppc_lstm_step_forward, train = 1)
+    backward: BPTT + weight-gradient GEMMs (nppc_lstm_step_backward) -> gradient of the packed input -> back through
+              drop_band (a permutation: unique indices, no atomics) and the per-sample mean of offline_laplace_norm."""
+
+    @staticmethod
+    def forward(ctx, fb, fbr, fbi, nbr_src, nn_, groups, *params):
+        B, Fq, Tp = fb.shape
+        xs, R, sums = ops.subband_pack(nbr_src, fb, fbr, fbi, nn_, groups, 64, torch.float16, want_sums=True)
+        y, ws = ops.lstm_step_forward(params, xs, R, train=True)
+        ctx.save_for_backward(xs, ws, sums, *params)
+        ctx.meta = (B, Fq, Tp, nn_, groups, R)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, ws, sums, *params = ctx.saved_tensors
+        B, Fq, Tp, nn_, groups, R = ctx.meta
+        need_x = any(ctx.needs_input_grad[:3])
+        grads, dxs = ops.lstm_step_backward(params, xs, R, ws, dy.contiguous(), want_dxs=need_x)
+        dfb = dfbr = dfbi = None
+        if need_x:
+            S = 2 * nn_ + 4
+            G = groups if (groups > 1 and B > 1) else 1
+            sb, f, Fg = _dropband_maps(B, Fq, G, dy.device)
+            N = float(Fq * S * Tp)
+            den = (sums / N).float() + 1e-5                                            # [B], the forward's divisor
+            g = dxs[:, :R, :S]                                                          # [T', R, S]
+            # sum_i g_i y_i per sample (y = the normalised input itself): rows of one output batch are contiguous
+            D_row = (g * xs[:, :R, :S].float()).sum(dim=(0, 2))                         # [R]
+            D_ob = D_row.reshape(-1, Fg).sum(dim=1)                                     # [B'] in output-batch order
+            D = torch.zeros(B, device=dy.device, dtype=torch.float32)
+            D[sb.reshape(-1, Fg)[:, 0]] = D_ob                                          # a permutation of the samples
+            base = (-D / (N * den))[:, None, None]                                      # mean term: every (f, t) of the sample
+            outs = []
+            for k in range(3):
+                d = base.expand(B, Fq, Tp).clone()
+                d[sb, f] = d[sb, f] + g[:, :, S - 3 + k].t() / den[sb][:, None]          # kept (sample, frequency) pairs are unique
+                outs.append(d)
+            dfb, dfbr, dfbi = outs
+        return (dfb, dfbr, dfbi, None, None, None, *grads)
+
+
+# ---- Gram-Schmidt + objective -------------------------------------------------------------------------------------------
+class GsLossFn(torch.autograd.Function):
+    """head [B, n, 2, F', T] -> objective (trainer.py:337-342) with w_mat and the statistics as non-differentiable outputs."""
+
+    @staticmethod
+    def forward(ctx, head, gt, pred, lam):
+        w, st, G, A = ops.gs_loss_fused_with_gram(head, gt, pred)
+        objective = st["reconst_err"].mean() + lam * st["second_moment_mse"].mean()
+        ctx.save_for_backward(head, gt, pred, G, A)
+        ctx.lam = float(lam)
+        outs = (w, st["err_norm"], torch.view_as_real(st["err_proj"]), st["w_norms"], st["reconst_err"], st["second_moment_mse"])
+        ctx.mark_non_differentiable(*outs)
+        return (objective, *outs)
+
+    @staticmethod
+    def backward(ctx, g_obj, *unused):
+        head, gt, pred, G, A = ctx.saved_tensors
+        coef = gs_loss_grad_coeffs(G, A.to(torch.complex128), ctx.lam) * g_obj.double()
+        return ops.complex_lincomb(head, gt, pred, coef), None, None, None
+
+
+# ---- the PC head, training forward ----------------------------------------------------------------------------------------
+def head_forward_train(net, nmag, nreal, nimag, emag, ereal, eimag):
+    """MultiDirectionFullSubNet_Plus.forward (networks.py:63-163) with an autograd graph made of the Functions above ->
+    head [B', n, 2, F', T].  The six inputs [B, 1, F, T] carry no gradient (frozen backbone)."""
+    if net.norm_type != "offline_laplace_norm":
+        raise NotImplementedError("training path: norm_type='offline_laplace_norm' only (the head's shipped configuration); "
+                                  f"got {net.norm_type!r}")
     la = net.look_ahead
-    nmag, nreal, nimag, emag, ereal, eimag = (F.pad(v, [0, la]) for v in (nmag, nreal, nimag, emag, ereal, eimag))
-    B, _, Fq, Tp = nmag.shape
+    B, _, Fq, T = nmag.shape
+    with torch.no_grad():
+        xn = [ops.pad_offline_laplace_norm(v, la) for v in (nmag, nreal, nimag, emag, ereal, eimag)]   # [B, F, T'] each
+        raw = F.pad(nmag[:, 0], [0, la]).contiguous()
 
-    def stream(noisy, enh, att, model):
-        a = _tsse(att, _offline_norm(noisy).reshape(B, Fq, Tp))
-        b = _tsse(att, _offline_norm(enh).reshape(B, Fq, Tp))
-        with amp():
-            return _tcn(model, torch.cat([a, b], dim=1)).float()
+    def stream(a, b, att, model):
+        xa = a * _tsse_gate(att, a)[:, :, None]
+        xb = b * _tsse_gate(att, b)[:, :, None]
+        return tcn_forward_train(model, torch.cat([xa, xb], dim=1))
 
-    fb = stream(nmag, emag, net.channel_attention, net.fb_model)
-    fbr = stream(nreal, ereal, net.channel_attention_real, net.fb_model_real)
-    fbi = stream(nimag, eimag, net.channel_attention_imag, net.fb_model_imag)
-    sb = torch.cat([_unfold(nmag[:, 0], net.sb_num_neighbors), fb[:, :, None], fbr[:, :, None], fbi[:, :, None]], dim=2)
-    sb = _offline_norm(sb)
-    if B > 1:
-        sb = _drop_band(sb.permute(0, 2, 1, 3), net.num_groups_in_drop_band).permute(0, 2, 1, 3)
-    Fp, S = sb.shape[1], sb.shape[2]
-    seq = sb.reshape(B * Fp, S, Tp).permute(0, 2, 1).contiguous()
-    lstm = net.sb_model.sequence_model
-    was_training = lstm.training
-    lstm.train(True)   # cuDNN's RNN backward needs the training-mode forward (no dropout here: identical numerics)
-    try:
-        with amp():
-            o, _ = lstm(seq)
-            y = net.sb_model.fc_output_layer(o).float()
-    finally:
-        lstm.train(was_training)
-    y = y.permute(0, 2, 1)  # [B*F', 2n, T']
+    fb = stream(xn[0], xn[3], net.channel_attention, net.fb_model)
+    fbr = stream(xn[1], xn[4], net.channel_attention_real, net.fb_model_real)
+    fbi = stream(xn[2], xn[5], net.channel_attention_imag, net.fb_model_imag)
+    y = SubbandLstmFn.apply(fb, fbr, fbi, raw, net.sb_num_neighbors, net.num_groups_in_drop_band, *net.sb_model.lstm_params())
+    R, O, Tp = y.shape
+    Fp = R // B
     n = net.n_directions
-    return y.reshape(B, Fp, n, 2, Tp).permute(0, 2, 3, 1, 4)[..., la:]
-
-
-def gram_schmidt_autograd(x):
-    """pc_wrapper.py:8-44 incl. the conjugated coefficient and the detached normaliser."""
-    B, n, _, Fq, T = x.shape
-    v = torch.complex(x[:, :, 0], x[:, :, 1]).reshape(B, n, -1)
-    outs, hats = [], []
-    for i in range(n):
-        w = v[:, i]
-        for wh in hats:
-            w = w - wh * (w.conj() * wh).sum(dim=1, keepdim=True)
-        wd = w.detach()
-        hats.append(wd / torch.linalg.vector_norm(wd, dim=1, keepdim=True))
-        outs.append(w)
-    out = torch.stack(outs, dim=1).reshape(B, n, Fq, T)
-    return torch.stack([out.real, out.imag], dim=2)
-
-
-def nppc_loss_autograd(w_mat, gt, pred, lam):
-    """trainer.py:259-298, 337-342."""
-    B, n = w_mat.shape[:2]
-    W = w_mat.reshape(B, n, 2, -1)
-    w_norms = torch.linalg.vector_norm(W, dim=(2, 3))
-    w_hat = W / (w_norms[..., None, None] + 1e-8)
-    err = (gt - pred).reshape(B, 2, -1)
-    err_norm = torch.linalg.vector_norm(err, dim=(1, 2))
-    err = err / (err_norm[:, None, None] + 1e-8)
-    w_norms = w_norms / (err_norm[:, None] + 1e-8)
-    err_proj = (torch.complex(w_hat[:, :, 0], w_hat[:, :, 1]).conj() * torch.complex(err[:, 0], err[:, 1])[:, None]).sum(-1)
-    mag = err_proj.abs()
-    reconst_err = 1 - mag.pow(2).sum(dim=1)
-    second_moment_mse = (w_norms.pow(2) - mag.detach().pow(2)).pow(2)
-    objective = reconst_err.mean() + lam * second_moment_mse.mean()
-    return dict(err_norm=err_norm, err_proj=err_proj, err_proj_mag=mag, w_norms=w_norms, reconst_err=reconst_err,
-                second_moment_mse=second_moment_mse, objective=objective)
+    return y.reshape(B, Fp, n, 2, Tp).permute(0, 2, 3, 1, 4)[..., la:].contiguous()
 
 
 # ---- data-parallel gradient exchange ------------------------------------------------------------------------------------
+class GradBucketReducer:
+    """DDP-style overlap without DDP: parameters are grouped into buckets in REVERSE registration order (the order their
+    gradients become final during backward: loss -> LSTM -> TCN -> attention); a post-accumulate hook counts a bucket down and
+    launches its all-reduce (async, NCCL stream) the moment its last gradient is in place, so the exchange of the LSTM
+    gradients rides under the TCN backward.  finish() waits, averages and scatters back.  'Mean of per-rank objectives'
+    semantics (upstream DDP averages the same way, nppc/auxil.py:297-302)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 16 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, size = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending: List[int] = []
+        self._work = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.reset()
+
+    def reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._work = []
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0 and self._active():
+            flat = torch.cat([q.grad.reshape(-1) for q in self.buckets[i]])
+            self._work.append((i, flat, dist.all_reduce(flat, async_op=True)))
+
+    def finish(self) -> int:
+        """Wait for the in-flight buckets (and exchange any whose hook never fired), write the averaged gradients back."""
+        if not self._active():
+            self.reset()
+            return 0
+        world = dist.get_world_size()
+        done = {i for i, _, _ in self._work}
+        for i, b in enumerate(self.buckets):
+            if i not in done and all(q.grad is not None for q in b):
+                flat = torch.cat([q.grad.reshape(-1) for q in b])
+                self._work.append((i, flat, dist.all_reduce(flat, async_op=True)))
+        n = len(self._work)
+        for i, flat, work in self._work:
+            work.wait()
+            flat.div_(world)
+            off = 0
+            for q in self.buckets[i]:
+                q.grad.copy_(flat[off:off + q.numel()].view_as(q.grad))
+                off += q.numel()
+        self.reset()
+        return n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> int:
-    """Mean-all-reduce the gradients of `params` over the default process group in flat buckets (NCCL over NVLink on GPUs,
-    gloo in the CPU tests).  DP parity is 'mean of per-rank objectives' (SURVEY.md §8e).  Returns the number of collectives."""
+    """Blocking variant (after backward): mean-all-reduce in flat buckets.  Returns the number of collectives."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
     world = dist.get_world_size()

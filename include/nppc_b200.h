@@ -111,6 +111,14 @@ int nppc_drop_band(const float* x, int B, int C, int F, int T, int groups, float
  * gram_schmidt_to_crm (nppc_audio/pc_wrapper.py:8-44): x [B,n,2,P] -> out [B,n,2,P]; complex MGS with the
  * reference's conjugated coefficient.  gram_schmidt_to_spec_mag (nppc_audio/inpainting/nppc/pc_wrapper.py:43-59):
  * x [B,n,P] real.  `scratch` must hold nppc_gs_scratch_bytes(B,n) bytes (fp64 Gram + coefficients). */
+/* Backward of Gram-Schmidt + objective (pc_wrapper.py:8-44 with its detach() at :37, trainer.py:259-298 with the detach()
+ * at :295): out[b,i] = sum_{k<n} C[b,i,k] x[b,k] + C[b,i,n] (gt[b] - pred[b]) with complex coefficients C [B, n, n+1, 2] that
+ * the host derives from the forward pass's Gram matrix (generative-audio_b200/gs_backward.py) — one streaming pass.
+ * x, out [B, n, 2, P]; gt, pred [B, 2, P].  The scratch of nppc_gs_loss_fused holds, per sample, the Hermitian Gram matrix
+ * of (x_0 .. x_{n-1}, gt - pred) as 13 x 13 complex doubles (upper triangle) followed by the 12 x 12 complex-float coefficient
+ * matrix A of w_i = sum_k A[i][k] x_k. */
+int nppc_complex_lincomb(const float* x, const float* gt, const float* pred, int B, int n, long long P, const float* coef,
+                         float* out, void* stream);
 size_t nppc_gs_scratch_bytes(int B, int n);
 int nppc_gram_schmidt_complex(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream);
 int nppc_gram_schmidt_real(const float* x, int B, int n, long long P, void* scratch, float* out, void* stream);

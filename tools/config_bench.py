@@ -54,11 +54,8 @@ clean = wave(32, 64000, 3, 0.03)
 noisy = clean + 0.3 * wave(32, 64000, 4, 1.0)
 ms = timeit(lambda: stepper.train_step((noisy.cuda(), clean.cuda()), opt), reps=3, warm=2)
 out["config3_train_step_b32_g2"] = {"ms_per_step": ms, "audio_s_per_s": 32 * 4.0 / (ms * 1e-3),
-                                     "note": "frozen half on the kernels, PC head fwd+bwd on torch autograd (fp32/TF32 off), Adam step"}
-stepper.amp_dtype = torch.bfloat16
-ms = timeit(lambda: stepper.train_step((noisy.cuda(), clean.cuda()), opt), reps=3, warm=2)
-out["config3_train_step_b32_g2_bf16"] = {"ms_per_step": ms, "audio_s_per_s": 32 * 4.0 / (ms * 1e-3),
-                                          "note": "same, head GEMMs / LSTM under bf16 autocast (fp32 master weights, fp32 loss)"}
+                                     "note": "frozen half on the inference kernels; PC head fwd + bwd hand-written (stepwise tcgen05 LSTM + BPTT, "
+                                             "tcgen05 GEMMs for all 1x1 convs fwd/dX/dW, coefficient-space GS + loss backward), Adam step"}
 del stepper, opt, m2
 torch.cuda.empty_cache()
 
