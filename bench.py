@@ -131,6 +131,118 @@ def gpu_eager_run(batch, steps=3, warmup=2):
                                       "cuDNN LSTM, cuFFT, library convolutions), device-resident input"}
 
 
+def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist):
+    """BASELINE config 3 / 5: one training step of the PC head per GPU per step (frozen backbone on the inference kernels, head
+    forward + hand-written backward, Adam), gradients averaged over the ranks by the bucketed all-reduce that overlaps the
+    backward.  Seeds differ per rank (base + rank) and the weights are identical, as DP requires."""
+    import torch
+    ops = G.ops
+    B = args.train_batch
+    model, _ = build_model(N_DIRS, 2, "tc")
+    stepper = G.NPPCAudioStep(model, 500, 1.0)
+    stepper.step = 600
+    opt = torch.optim.Adam(model.audio_pc_wrapper.parameters(), lr=1e-5)
+    clean_h = wave(B, L, 3000 + rank, 0.03).pin_memory()
+    noisy_h = (clean_h + 0.3 * wave(B, L, 4000 + rank, 1.0)).pin_memory()
+    clean_d, noisy_d = clean_h.to(dev), noisy_h.to(dev)
+    lstm_ev = []
+    of, ob = ops.lstm_step_forward, ops.lstm_step_backward
+
+    def tf(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = of(*a, **k); e1.record()
+        lstm_ev.append((e0, e1))
+        return r
+
+    def tb(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = ob(*a, **k); e1.record()
+        lstm_ev.append((e0, e1))
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    obj_host = torch.zeros(1).pin_memory()
+
+    def step_dev():
+        stepper.train_step((noisy_d, clean_d), opt)
+
+    def step_e2e():
+        obj, _ = stepper.train_step((noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True)), opt)
+        obj_host.copy_(obj.reshape(1), non_blocking=True)
+
+    run(args.warmup, step_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.lstm_step_forward, ops.lstm_step_backward = tf, tb
+    ops.reset_launch_count()
+    ms = run(args.steps, step_dev) / args.steps
+    launches = ops.launch_count()
+    ops.lstm_step_forward, ops.lstm_step_backward = of, ob
+    barrier()
+    run(1, step_e2e)
+    barrier()
+    ms_e2e = run(args.steps, step_e2e) / args.steps
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    from generative_audio_b200.sharding import aggregate_throughput
+    _, ms_step = aggregate_throughput(B * L / SR, ms)
+    _, ms_e2e_step = aggregate_throughput(B * L / SR, ms_e2e)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ms, ms_e2e, float(sampler.summary()["sm_mhz"] or 0)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu()
+        per_rank = {"ms_per_step": [round(v, 3) for v in allr[:, 0].tolist()], "sm_mhz": [int(v) for v in allr[:, 2].tolist()]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    R, Tp_ = B * (F // 2), TP
+    lstm_ms = sum(a.elapsed_time(b) for a, b in lstm_ev) / max(args.steps, 1)            # forward + backward per step
+    flops = 3 * LSTM_FLOP_PER_SEQ_STEP * R * Tp_                                          # forward + 2 x for BPTT (dX and dW)
+    pk = peaks()
+    achieved = flops / (max(lstm_ms, 1e-9) * 1e-3) / 1e12
+    audio_s = B * world * L / SR
+    nparams = sum(p.numel() for p in model.audio_pc_wrapper.parameters())
+    line = {"metric": "audio-sec/sec NPPC-audio PC-head training step (16 kHz, 5 PCs)", "value": audio_s / (ms_step * 1e-3), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "mode": "train",
+            "config": {"workload": f"BASELINE config 3: PC-head training step, {B} x 4 s utterances per GPU, n_dirs={N_DIRS}, drop_band groups=2, "
+                                   "frozen FullSubNet+ (inference kernels) + head fwd/bwd (hand-written) + Adam; DP gradient all-reduce "
+                                   f"({nparams} head parameters, fp32) bucketed and overlapped with the backward over NCCL when N > 1",
+                       "batch_per_gpu": B, "n_dirs": N_DIRS, "parallelism": f"dp{world}"},
+            "e2e": {"value": audio_s / (ms_e2e_step * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_step,
+                    "h2d_bytes_per_step": 2 * noisy_h.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "stepwise tcgen05 LSTM forward + BPTT + weight-gradient GEMMs per training step",
+                         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                         "traffic": None, "ms_per_step": lstm_ms, "share_of_step": lstm_ms / ms_step, "peak_source": pk["src"]},
+            "clocks": sampler.summary()}
+    if per_rank:
+        line["per_rank"] = per_rank
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -142,6 +254,10 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline leg (N = 1 only)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: NPPCModel.forward (the headline metric); train: BASELINE config 3, one PC-head training step per "
+                         "GPU (B = 32 x 4 s, drop_band groups = 2) with the DP gradient all-reduce over NCCL when N > 1")
+    ap.add_argument("--train-batch", type=int, default=32)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,8 +310,10 @@ def main():
     import generative_audio_b200 as G
     from helpers import build_model, wave
     ops = G.ops
-    model, _ = build_model(N_DIRS, 1, args.lstm_impl)
     dev = torch.device("cuda", local_rank)
+    if args.mode == "train":
+        return train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist)
+    model, _ = build_model(N_DIRS, 1, args.lstm_impl)
     B = args.batch
     x_host = wave(B, L, 1000 + rank).pin_memory()
     x_dev = x_host.to(dev)

@@ -147,12 +147,17 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const __grid_constan
     if (warp >= 2) {
         const int lg = warp & 3;                               // TMEM lane group this warp may touch
         const int row = m_blk * BM + lg * 32 + lane;
+        const float* bp = bias_p + n_blk * 128;
+        const size_t hoff = (size_t)row * H + n_blk * 32;
+        // c_{t-1} of this thread's 32 units is fetched while the MMAs run (a dependent global load per chunk inside the loop
+        // was the longest part of the CTA's life)
+        float4 cpre[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cpre[q] = __ldg(reinterpret_cast<const float4*>(c_prev + hoff) + q);
         mbar_wait(acc_full, 0);
         tcgen05_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
-        const float* bp = bias_p + n_blk * 128;
-        const size_t hoff = (size_t)row * H + n_blk * 32;
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 4; ++q) {                          // 8 units at a time
             uint32_t vi[8], vf[8], vg[8], vo[8];
             tmem_ld8(t_row + q * 8, vi);
@@ -160,12 +165,8 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const __grid_constan
             tmem_ld8(t_row + 64 + q * 8, vg);
             tmem_ld8(t_row + 96 + q * 8, vo);
             tmem_wait_ld();
-            float cp[8];
-            {
-                const float4 a = *reinterpret_cast<const float4*>(c_prev + hoff + q * 8);
-                const float4 b = *reinterpret_cast<const float4*>(c_prev + hoff + q * 8 + 4);
-                cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-            }
+            const float cp[8] = {cpre[2 * q].x, cpre[2 * q].y, cpre[2 * q].z, cpre[2 * q].w,
+                                 cpre[2 * q + 1].x, cpre[2 * q + 1].y, cpre[2 * q + 1].z, cpre[2 * q + 1].w};
             float cn[8], hn[8], gi[8], gf[8], gg[8], go[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -222,35 +223,49 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const __grid_constan
     if (warp >= 2) {
         const int lg = warp & 3;
         const int row = m_blk * BM + lg * 32 + lane;
+        // operands of one 8-unit chunk; chunk q+1 is loaded while chunk q is computed, chunk 0 while the MMAs run
+        struct Ops { uint4 ri, rf, rg, ro; float4 ct0, ct1, cp0, cp1, dc0, dc1; };
+        auto load_ops = [&](int q) {
+            Ops o;
+            const int u0 = n_blk * 64 + q * 8;
+            const size_t hoff = (size_t)row * H + u0;
+            const size_t goff = (size_t)row * 4 * H + (u0 >> 5) * 128 + (u0 & 31);
+            o.ri = __ldg(reinterpret_cast<const uint4*>(gates + goff));
+            o.rf = __ldg(reinterpret_cast<const uint4*>(gates + goff + 32));
+            o.rg = __ldg(reinterpret_cast<const uint4*>(gates + goff + 64));
+            o.ro = __ldg(reinterpret_cast<const uint4*>(gates + goff + 96));
+            o.ct0 = __ldg(reinterpret_cast<const float4*>(c_t + hoff));
+            o.ct1 = __ldg(reinterpret_cast<const float4*>(c_t + hoff + 4));
+            o.cp0 = __ldg(reinterpret_cast<const float4*>(c_prev + hoff));
+            o.cp1 = __ldg(reinterpret_cast<const float4*>(c_prev + hoff + 4));
+            if (first) {
+                o.dc0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                o.dc1 = o.dc0;
+            } else {
+                o.dc0 = *reinterpret_cast<const float4*>(dc_carry + hoff);
+                o.dc1 = *reinterpret_cast<const float4*>(dc_carry + hoff + 4);
+            }
+            return o;
+        };
+        Ops nxt = load_ops(0);
         mbar_wait(acc_full, 0);
         tcgen05_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) {                          // 8 units at a time: units u0 .. u0+7
+            const Ops cur = nxt;
+            if (q + 1 < 8) nxt = load_ops(q + 1);
             const int u0 = n_blk * 64 + q * 8;
             uint32_t vd[8];
             tmem_ld8(t_row + q * 8, vd);
             tmem_wait_ld();
             const size_t hoff = (size_t)row * H + u0;
             const size_t goff = (size_t)row * 4 * H + (u0 >> 5) * 128 + (u0 & 31);
-            const uint4 ri = *reinterpret_cast<const uint4*>(gates + goff), rf = *reinterpret_cast<const uint4*>(gates + goff + 32),
-                        rg = *reinterpret_cast<const uint4*>(gates + goff + 64), ro = *reinterpret_cast<const uint4*>(gates + goff + 96);
-            const __half *pi = reinterpret_cast<const __half*>(&ri), *pf = reinterpret_cast<const __half*>(&rf),
-                         *pg = reinterpret_cast<const __half*>(&rg), *po = reinterpret_cast<const __half*>(&ro);
-            float ct[8], cpv[8], dcc[8];
-            {
-                const float4 a = *reinterpret_cast<const float4*>(c_t + hoff), b = *reinterpret_cast<const float4*>(c_t + hoff + 4);
-                ct[0] = a.x; ct[1] = a.y; ct[2] = a.z; ct[3] = a.w; ct[4] = b.x; ct[5] = b.y; ct[6] = b.z; ct[7] = b.w;
-                const float4 c = *reinterpret_cast<const float4*>(c_prev + hoff), d = *reinterpret_cast<const float4*>(c_prev + hoff + 4);
-                cpv[0] = c.x; cpv[1] = c.y; cpv[2] = c.z; cpv[3] = c.w; cpv[4] = d.x; cpv[5] = d.y; cpv[6] = d.z; cpv[7] = d.w;
-                if (first) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) dcc[u] = 0.f;
-                } else {
-                    const float4 e = *reinterpret_cast<const float4*>(dc_carry + hoff), f = *reinterpret_cast<const float4*>(dc_carry + hoff + 4);
-                    dcc[0] = e.x; dcc[1] = e.y; dcc[2] = e.z; dcc[3] = e.w; dcc[4] = f.x; dcc[5] = f.y; dcc[6] = f.z; dcc[7] = f.w;
-                }
-            }
+            const __half *pi = reinterpret_cast<const __half*>(&cur.ri), *pf = reinterpret_cast<const __half*>(&cur.rf),
+                         *pg = reinterpret_cast<const __half*>(&cur.rg), *po = reinterpret_cast<const __half*>(&cur.ro);
+            const float ct[8] = {cur.ct0.x, cur.ct0.y, cur.ct0.z, cur.ct0.w, cur.ct1.x, cur.ct1.y, cur.ct1.z, cur.ct1.w};
+            const float cpv[8] = {cur.cp0.x, cur.cp0.y, cur.cp0.z, cur.cp0.w, cur.cp1.x, cur.cp1.y, cur.cp1.z, cur.cp1.w};
+            float dcc[8] = {cur.dc0.x, cur.dc0.y, cur.dc0.z, cur.dc0.w, cur.dc1.x, cur.dc1.y, cur.dc1.z, cur.dc1.w};
             float zi[8], zf[8], zg[8], zo[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -471,9 +486,14 @@ __global__ void split_f32_kernel(const float* __restrict__ x, long long n, __hal
     }
 }
 
-// y[r][o][t] = b[o] + sum_u W[o][u] (h[t][r][u] (+ h_lo)), one warp per (t, r); O <= 24
+// y[r][o][t] = b[o] + sum_u W[o][u] (h[t][r][u] (+ h_lo)), one warp per (t, r), 8 units (one 16-byte load) per lane and round;
+// the fc weights sit in shared memory transposed ([u][OP]) so a lane's 8 units read contiguous, conflict-free rows.  O <= 24
 __global__ void __launch_bounds__(256) fc_fwd_kernel(const __half* __restrict__ h, const __half* __restrict__ h_lo, int R, int RS, int Tp, int H,
                                                      const float* __restrict__ w, const float* __restrict__ b, int O, float* __restrict__ y) {
+    extern __shared__ float wsT[];                    // [H][OP], OP = O rounded up to odd stride
+    const int OP = O | 1;
+    for (int i = threadIdx.x; i < H * O; i += blockDim.x) { const int o = i / H, u = i - o * H; wsT[u * OP + o] = w[i]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (wid >= (long long)Tp * R) return;
@@ -483,11 +503,24 @@ __global__ void __launch_bounds__(256) fc_fwd_kernel(const __half* __restrict__ 
     float acc[24];
 #pragma unroll
     for (int o = 0; o < 24; ++o) acc[o] = 0.f;
-    for (int u = lane; u < H; u += 32) {
-        float hv = __half2float(hr[u]);
-        if (lr) hv += __half2float(lr[u]);
+    for (int u0 = lane * 8; u0 < H; u0 += 256) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(hr + u0));
+        const __half* hp = reinterpret_cast<const __half*>(&raw);
+        float hv[8];
 #pragma unroll
-        for (int o = 0; o < 24; ++o) if (o < O) acc[o] = fmaf(hv, __ldg(w + (size_t)o * H + u), acc[o]);
+        for (int e = 0; e < 8; ++e) hv[e] = __half2float(hp[e]);
+        if (lr) {
+            const uint4 rl = __ldg(reinterpret_cast<const uint4*>(lr + u0));
+            const __half* lp = reinterpret_cast<const __half*>(&rl);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hv[e] += __half2float(lp[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float* wr = wsT + (u0 + e) * OP;
+#pragma unroll
+            for (int o = 0; o < 24; ++o) if (o < O) acc[o] = fmaf(hv[e], wr[o], acc[o]);
+        }
     }
 #pragma unroll
     for (int o = 0; o < 24; ++o) if (o < O) {
@@ -661,12 +694,15 @@ int tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_
     return make_tmap_bf16_2d(m, base, rows, cols, cols * 2, box_rows, 64);
 }
 
+template <typename K>
+int allow_smem(K kern, int smem_bytes) {   // once per call site group, not per launch (the time loop launches ~1000 kernels)
+    NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    return NPPC_OK;
+}
 template <typename K, typename... Args>
 int launch_seg(K kern, int smem_bytes, dim3 grid, cudaStream_t s, Args... args) {
-    NPPC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     kern<<<grid, NTH, smem_bytes, s>>>(args...);
     NPPC_COUNT_LAUNCH(1);
-    NPPC_LAUNCH_OK();
     return NPPC_OK;
 }
 
@@ -732,6 +768,7 @@ extern "C" int nppc_lstm_step_forward(const nppc_lstm_weights* w, const void* xs
         xh = L.xhi;
     }
     NPPC_LAUNCH_OK();
+    if ((rc = allow_smem(lstm_step_fwd_kernel<true>, StepSmem<128>::TOTAL)) || (rc = allow_smem(lstm_step_fwd_kernel<false>, StepSmem<128>::TOTAL))) return rc;
     // ---- time loop, layer by layer (layer 1 reads the finished h sequence of layer 0) ----
     for (int l = 0; l < 2; ++l) {
         SegArgs g{};
@@ -768,8 +805,9 @@ extern "C" int nppc_lstm_step_forward(const nppc_lstm_weights* w, const void* xs
             else rc = launch_seg(lstm_step_fwd_kernel<false>, StepSmem<128>::TOTAL, grid, s, g, (const float*)L.bias[l], H, cprev, cout, hout, hlo, gt);
             if (rc) return rc;
         }
+        NPPC_LAUNCH_OK();
     }
-    fc_fwd_kernel<<<nppc::cdiv((long long)Tp * R, 8), 256, 0, s>>>(L.hseq[1] + (size_t)RS * H, precise ? L.hlo[1] + (size_t)RS * H : nullptr, R, RS, Tp, H,
+    fc_fwd_kernel<<<nppc::cdiv((long long)Tp * R, 8), 256, sizeof(float) * H * (w->O | 1), s>>>(L.hseq[1] + (size_t)RS * H, precise ? L.hlo[1] + (size_t)RS * H : nullptr, R, RS, Tp, H,
                                                                  w->fc_w, w->fc_b, w->O, y);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
@@ -800,6 +838,7 @@ extern "C" int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* x
     pack_fcT_kernel<<<nppc::cdiv(H * 64, 256), 256, 0, s>>>(w->fc_w, O, H, L.wfcT);
     NPPC_COUNT_LAUNCH(8);
     NPPC_LAUNCH_OK();
+    if ((rc = allow_smem(lstm_step_bwd_kernel, StepSmem<64>::TOTAL)) || (rc = allow_smem(seg_gemm_f32_kernel, StepSmem<128>::TOTAL))) return rc;
     // ---- BPTT: layer 1 (top) first, then layer 0 with layer 1's dZ as the gradient from above ----
     for (int l = 1; l >= 0; --l) {
         SegArgs g{};
@@ -826,6 +865,7 @@ extern "C" int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* x
                             L.dz[l] + (size_t)t * RS * 4 * H, (int)(t == Tp - 1));
             if (rc) return rc;
         }
+        NPPC_LAUNCH_OK();
     }
     // ---- weight / bias gradients: dW = dZ^T [input | h_prev] over all rows (MN-major operands, split-K partials) ----
     const int chunks = 592;
