@@ -141,7 +141,9 @@ def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockS
     model, _ = build_model(N_DIRS, 2, "tc")
     stepper = G.NPPCAudioStep(model, 500, 1.0)
     stepper.step = 600
-    opt = torch.optim.Adam(model.audio_pc_wrapper.parameters(), lr=1e-5)
+    graphed = os.environ.get("NPPC_TRAIN_GRAPH", "1") != "0"     # whole step as ONE CUDA graph replay (trainer.train_step_graphed)
+    opt = torch.optim.Adam(model.audio_pc_wrapper.parameters(), lr=1e-5, capturable=graphed)
+    do_step = stepper.train_step_graphed if graphed else stepper.train_step
     clean_h = wave(B, L, 3000 + rank, 0.03).pin_memory()
     noisy_h = (clean_h + 0.3 * wave(B, L, 4000 + rank, 1.0)).pin_memory()
     clean_d, noisy_d = clean_h.to(dev), noisy_h.to(dev)
@@ -179,20 +181,32 @@ def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockS
     obj_host = torch.zeros(1).pin_memory()
 
     def step_dev():
-        stepper.train_step((noisy_d, clean_d), opt)
+        do_step((noisy_d, clean_d), opt)
 
     def step_e2e():
-        obj, _ = stepper.train_step((noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True)), opt)
+        obj, _ = do_step((noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True)), opt)
         obj_host.copy_(obj.reshape(1), non_blocking=True)
 
     run(args.warmup, step_dev)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.lstm_step_forward, ops.lstm_step_backward = tf, tb
     ops.reset_launch_count()
     ms = run(args.steps, step_dev) / args.steps
     launches = ops.launch_count()
+    barrier()
+    # the LSTM's share: one EAGER step with CUDA events around nppc_lstm_step_forward / _backward (events cannot sit inside a
+    # captured graph); the same kernels with the same arguments as in the timed steps
+    ops.lstm_step_forward, ops.lstm_step_backward = tf, tb
+    ops.reset_launch_count()
+    stepper._graph_saved, stepper._graph = stepper._graph, None
+    eager_opt = torch.optim.Adam(model.audio_pc_wrapper.parameters(), lr=1e-5)
+    stepper._reducer_saved, stepper._reducer = stepper._reducer, None
+    stepper._step_body((noisy_d, clean_d), eager_opt)
+    torch.cuda.synchronize()
+    if graphed:
+        launches = ops.launch_count()     # kernels of one step (a replayed graph launches the same kernels without the counter)
+    stepper._graph, stepper._reducer = stepper._graph_saved, stepper._reducer_saved
     ops.lstm_step_forward, ops.lstm_step_backward = of, ob
     barrier()
     run(1, step_e2e)
@@ -216,7 +230,7 @@ def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockS
             dist.destroy_process_group()
         return
     R, Tp_ = B * (F // 2), TP
-    lstm_ms = sum(a.elapsed_time(b) for a, b in lstm_ev) / max(args.steps, 1)            # forward + backward per step
+    lstm_ms = sum(a.elapsed_time(b) for a, b in lstm_ev)                                  # forward + backward of ONE (eager) step
     flops = 3 * LSTM_FLOP_PER_SEQ_STEP * R * Tp_                                          # forward + 2 x for BPTT (dX and dW)
     pk = peaks()
     achieved = flops / (max(lstm_ms, 1e-9) * 1e-3) / 1e12
@@ -231,7 +245,7 @@ def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockS
                        "batch_per_gpu": B, "n_dirs": N_DIRS, "parallelism": f"dp{world}"},
             "e2e": {"value": audio_s / (ms_e2e_step * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_step,
                     "h2d_bytes_per_step": 2 * noisy_h.numel() * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * (args.steps if graphed else 1), "cuda_graph": graphed,
             "roofline": {"bound": "tensor", "kernel": "stepwise tcgen05 LSTM forward + BPTT + weight-gradient GEMMs per training step",
                          "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                          "traffic": None, "ms_per_step": lstm_ms, "share_of_step": lstm_ms / ms_step, "peak_source": pk["src"]},

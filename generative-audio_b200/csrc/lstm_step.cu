@@ -343,9 +343,11 @@ __global__ void __launch_bounds__(NTH) seg_gemm_f32_kernel(const __grid_constant
 //   columns: LBO = one box = 8192 B); a K = 16 step advances the start address by 2 atoms (2048 B).
 //   grid (Mo / 128, No / 64, splits).  BM = 128 (two A boxes per stage), BN = 64.
 // =====================================================================================================================
-constexpr int ATB_STAGE = 2 * 8192 + 8192;
 constexpr int ATB_STAGES = 4;
-constexpr int ATB_SMEM = ATB_STAGES * ATB_STAGE + 256 + 1024;
+template <int BN> struct AtbSmem {
+    static constexpr int STAGE = 2 * 8192 + (BN / 64) * 8192;     // two A boxes + BN/64 B boxes of [64 k][64 cols] fp16
+    static constexpr int TOTAL = ATB_STAGES * STAGE + 256 + 1024;
+};
 
 __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
@@ -357,8 +359,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t
     return d;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(NTH) gemm_atb_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                                        long long rows, int Mo, int No, float* __restrict__ P) {
+    constexpr int ATB_STAGE = AtbSmem<BN>::STAGE;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + ATB_STAGES * ATB_STAGE);
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(NTH) gemm_atb_kernel(const __grid_constant__ C
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<64>(tmem_ptr);
+    if (warp == 1) tmem_alloc<BN>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -390,14 +394,16 @@ __global__ void __launch_bounds__(NTH) gemm_atb_kernel(const __grid_constant__ C
                 mbar_arrive_expect_tx(&full[stage], ATB_STAGE);
                 tma_load_2d(sa, &tmap_a, &full[stage], m_blk * BM, (int)(kb * BK));
                 tma_load_2d(sa + 8192, &tmap_a, &full[stage], m_blk * BM + 64, (int)(kb * BK));
-                tma_load_2d(sa + 16384, &tmap_b, &full[stage], n_blk * 64, (int)(kb * BK));
+#pragma unroll
+                for (int bx = 0; bx < BN / 64; ++bx)
+                    tma_load_2d(sa + 16384 + bx * 8192, &tmap_b, &full[stage], n_blk * BN + bx * 64, (int)(kb * BK));
                 if (++stage == ATB_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // D f32, A/B fp16, BOTH MN-major (bits 15, 16), M = 128, N = 64
-            constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            // D f32, A/B fp16, BOTH MN-major (bits 15, 16), M = 128, N = BN
+            constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             for (long long kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
@@ -420,9 +426,9 @@ __global__ void __launch_bounds__(NTH) gemm_atb_kernel(const __grid_constant__ C
             tcgen05_fence_after();
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
-        float* dst = P + ((size_t)sp * Mo + m) * No + n_blk * 64;
+        float* dst = P + ((size_t)sp * Mo + m) * No + n_blk * BN;
 #pragma unroll 1
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < BN / 8; ++q) {
             uint32_t v[8];
             if (kb1 > kb0) {
                 tmem_ld8(t_row + q * 8, v);
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(NTH) gemm_atb_kernel(const __grid_constant__ C
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<64>(tmem_base);
+        tmem_dealloc<BN>(tmem_base);
     }
 }
 
@@ -487,12 +493,11 @@ __global__ void split_f32_kernel(const float* __restrict__ x, long long n, __hal
 }
 
 // y[r][o][t] = b[o] + sum_u W[o][u] (h[t][r][u] (+ h_lo)), one warp per (t, r), 8 units (one 16-byte load) per lane and round;
-// the fc weights sit in shared memory transposed ([u][OP]) so a lane's 8 units read contiguous, conflict-free rows.  O <= 24
+// the fc weights sit in shared memory as [O][H]: a lane reads the 8 weights of its units as two conflict-free float4.  O <= 24
 __global__ void __launch_bounds__(256) fc_fwd_kernel(const __half* __restrict__ h, const __half* __restrict__ h_lo, int R, int RS, int Tp, int H,
                                                      const float* __restrict__ w, const float* __restrict__ b, int O, float* __restrict__ y) {
-    extern __shared__ float wsT[];                    // [H][OP], OP = O rounded up to odd stride
-    const int OP = O | 1;
-    for (int i = threadIdx.x; i < H * O; i += blockDim.x) { const int o = i / H, u = i - o * H; wsT[u * OP + o] = w[i]; }
+    extern __shared__ __align__(16) float ws[];       // [O][H]
+    for (int i = threadIdx.x; i < H * O; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -516,10 +521,9 @@ __global__ void __launch_bounds__(256) fc_fwd_kernel(const __half* __restrict__ 
             for (int e = 0; e < 8; ++e) hv[e] += __half2float(lp[e]);
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float* wr = wsT + (u0 + e) * OP;
-#pragma unroll
-            for (int o = 0; o < 24; ++o) if (o < O) acc[o] = fmaf(hv[e], wr[o], acc[o]);
+        for (int o = 0; o < 24; ++o) if (o < O) {
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + o * H + u0), w1 = *reinterpret_cast<const float4*>(ws + o * H + u0 + 4);
+            acc[o] += hv[0] * w0.x + hv[1] * w0.y + hv[2] * w0.z + hv[3] * w0.w + hv[4] * w1.x + hv[5] * w1.y + hv[6] * w1.z + hv[7] * w1.w;
         }
     }
 #pragma unroll
@@ -609,17 +613,25 @@ __global__ void fcgrad_reduce_kernel(const float* __restrict__ P, int splits, in
     for (int sp = 0; sp < splits; ++sp) s += P[((size_t)sp * H + u) * 64 + o];
     grad[i] = s * scale[1];
 }
-// fc bias gradient: g_fc_b[o] = sum_{r,t} dy[r][o][t]  (one CTA per o, fp64 accumulation, deterministic)
-__global__ void __launch_bounds__(256) fcbias_grad_kernel(const float* __restrict__ dy, int R, int O, int Tp, float* __restrict__ grad) {
+// fc bias gradient: g_fc_b[o] = sum_{r,t} dy[r][o][t]: 64 chunk partials per o (fp64), then a fixed-order sum (deterministic)
+__global__ void __launch_bounds__(256) fcbias_partial_kernel(const float* __restrict__ dy, int R, int O, int Tp, double* __restrict__ part) {
     __shared__ double red[32];
-    const int o = blockIdx.x;
+    const int o = blockIdx.y;
+    const int per = (R + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(R, r0 + per);
     double s = 0.0;
-    for (long long i = threadIdx.x; i < (long long)R * Tp; i += blockDim.x) {
+    for (long long i = (long long)r0 * Tp + threadIdx.x; i < (long long)r1 * Tp; i += blockDim.x) {
         const int r = (int)(i / Tp), t = (int)(i - (long long)r * Tp);
         s += (double)dy[((size_t)r * O + o) * Tp + t];
     }
     s = nppc::block_sum(s, red);
-    if (threadIdx.x == 0) grad[o] = (float)s;
+    if (threadIdx.x == 0) part[o * gridDim.x + blockIdx.x] = s;
+}
+__global__ void fcbias_finish_kernel(const double* __restrict__ part, int chunks, int O, float* __restrict__ grad) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += part[o * chunks + c];
+    grad[o] = (float)s;
 }
 
 // ---- host helpers ----------------------------------------------------------------------------------------------------
@@ -712,8 +724,13 @@ int run_atb(const __half* A, int Mo, const __half* B, int No, long long rows, in
     if (rc) return rc;
     rc = tmap(&tb, B, (uint64_t)rows, (uint64_t)No, 64);
     if (rc) return rc;
-    NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
-    gemm_atb_kernel<<<dim3(Mo / 128, No / 64, splits), NTH, ATB_SMEM, s>>>(ta, tb, rows, Mo, No, P);
+    if (No % 128 == 0) {   // 128 x 128 tiles: half the operand bytes per FLOP through L2 / shared memory
+        NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_atb_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbSmem<128>::TOTAL));
+        gemm_atb_kernel<128><<<dim3(Mo / 128, No / 128, splits), NTH, AtbSmem<128>::TOTAL, s>>>(ta, tb, rows, Mo, No, P);
+    } else {
+        NPPC_CUDA_OK(cudaFuncSetAttribute(gemm_atb_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbSmem<64>::TOTAL));
+        gemm_atb_kernel<64><<<dim3(Mo / 128, No / 64, splits), NTH, AtbSmem<64>::TOTAL, s>>>(ta, tb, rows, Mo, No, P);
+    }
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -807,7 +824,7 @@ extern "C" int nppc_lstm_step_forward(const nppc_lstm_weights* w, const void* xs
         }
         NPPC_LAUNCH_OK();
     }
-    fc_fwd_kernel<<<nppc::cdiv((long long)Tp * R, 8), 256, sizeof(float) * H * (w->O | 1), s>>>(L.hseq[1] + (size_t)RS * H, precise ? L.hlo[1] + (size_t)RS * H : nullptr, R, RS, Tp, H,
+    fc_fwd_kernel<<<nppc::cdiv((long long)Tp * R, 8), 256, sizeof(float) * H * w->O, s>>>(L.hseq[1] + (size_t)RS * H, precise ? L.hlo[1] + (size_t)RS * H : nullptr, R, RS, Tp, H,
                                                                  w->fc_w, w->fc_b, w->O, y);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
@@ -872,10 +889,10 @@ extern "C" int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* x
     for (int l = 0; l < 2; ++l) {
         const int Kin = l == 0 ? w->I : H, Kl = l == 0 ? KP : H;
         const __half* a_in = l == 0 ? xh : L.hseq[0] + (size_t)RS * H;
-        int splits = Kl <= 64 ? 12 : 2;
+        int splits = Kl <= 64 ? 12 : 4;
         if ((rc = run_atb(L.dz[l], 4 * H, a_in, Kl, (long long)rows, splits, L.P, s))) return rc;
         wgrad_reduce_kernel<<<296, 256, 0, s>>>(L.P, splits, H, Kl, Kin, L.scale, gr->w_ih[l]);
-        splits = 2;
+        splits = 4;
         if ((rc = run_atb(L.dz[l], 4 * H, L.hseq[l], H, (long long)rows, splits, L.P, s))) return rc;   // h_{t-1}: un-shifted start
         wgrad_reduce_kernel<<<296, 256, 0, s>>>(L.P, splits, H, H, H, L.scale, gr->w_hh[l]);
         colsum_partial_kernel<<<chunks, 256, 0, s>>>(L.dz[l], (long long)rows, 4 * H, L.part);
@@ -886,8 +903,9 @@ extern "C" int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* x
         const int splits = 16;
         if ((rc = run_atb(L.hseq[1] + (size_t)RS * H, H, L.dyp, 64, (long long)rows, splits, L.P, s))) return rc;
         fcgrad_reduce_kernel<<<nppc::cdiv(O * H, 256), 256, 0, s>>>(L.P, splits, H, O, L.scale, gr->fc_w);
-        fcbias_grad_kernel<<<O, 256, 0, s>>>(dy, R, O, Tp, gr->fc_b);
-        NPPC_COUNT_LAUNCH(2);
+        fcbias_partial_kernel<<<dim3(64, O), 256, 0, s>>>(dy, R, O, Tp, reinterpret_cast<double*>(L.part));
+        fcbias_finish_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const double*>(L.part), 64, O, gr->fc_b);
+        NPPC_COUNT_LAUNCH(3);
     }
     if (dxs) {   // gradient w.r.t. the packed input: dZ0 W_ih0 -> [Tp RS][KP] fp32 (unscaled)
         SegArgs g{};

@@ -563,7 +563,7 @@ def gemm_f16_atb(a: torch.Tensor, b: torch.Tensor, splits: int = None):
     rows, Mo = a.shape
     No = b.shape[1]
     if splits is None:
-        tiles = (Mo // 128) * (No // 64)
+        tiles = (Mo // 128) * (No // (128 if No % 128 == 0 else 64))
         splits = max(1, min(64, 148 // max(tiles, 1), rows // 64))
     part = torch.empty(splits, Mo, No, device=a.device, dtype=torch.float32)
     c = torch.empty(Mo, No, device=a.device, dtype=torch.float32)

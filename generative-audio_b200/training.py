@@ -102,11 +102,11 @@ def _tsse_gate(m, x):
 
 # ---- TCN stack, channel-last, 1x1 convolutions on the tcgen05 GEMMs -----------------------------------------------------
 def _groupnorm1_cl(y, B, T, gamma, beta, eps=1e-8):
-    """GroupNorm(1, C) on channel-last rows y [B*T, C] (per-sample moments over all (T, C), biased variance)."""
-    v = y.reshape(B, -1)
-    mu = v.mean(dim=1, keepdim=True)
-    var = v.var(dim=1, unbiased=False, keepdim=True)
-    return ((v - mu) * torch.rsqrt(var + eps)).reshape(y.shape) * gamma[None, :] + beta[None, :]
+    """GroupNorm(1, C) on channel-last rows y [B*T, C] (per-sample moments over all (T, C), biased variance): the
+    normalisation itself is layout-agnostic (one fused native kernel each way on the [B, 1, T*C] view), the per-channel
+    affine follows on the channel-last rows."""
+    v = F.group_norm(y.reshape(B, 1, -1), 1, None, None, eps)
+    return torch.addcmul(beta[None, :], v.reshape(y.shape), gamma[None, :])
 
 
 def _dwconv3_cl(y, B, T, weight, bias, d):
@@ -120,7 +120,7 @@ def _dwconv3_cl(y, B, T, weight, bias, d):
 
 
 def _prelu(v, a):
-    return torch.where(v >= 0, v, a * v)
+    return F.prelu(v, a)
 
 
 def _pad_rows(v, Mp):
@@ -215,17 +215,17 @@ class GsLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, head, gt, pred, lam):
         w, st, G, A = ops.gs_loss_fused_with_gram(head, gt, pred)
-        objective = st["reconst_err"].mean() + lam * st["second_moment_mse"].mean()
-        ctx.save_for_backward(head, gt, pred, G, A)
-        ctx.lam = float(lam)
+        lam = torch.as_tensor(lam, dtype=torch.float64, device=head.device)      # device scalar: a captured step follows the schedule
+        objective = st["reconst_err"].mean() + (lam * st["second_moment_mse"].double().mean()).float()
+        ctx.save_for_backward(head, gt, pred, G, A, lam)
         outs = (w, st["err_norm"], torch.view_as_real(st["err_proj"]), st["w_norms"], st["reconst_err"], st["second_moment_mse"])
         ctx.mark_non_differentiable(*outs)
         return (objective, *outs)
 
     @staticmethod
     def backward(ctx, g_obj, *unused):
-        head, gt, pred, G, A = ctx.saved_tensors
-        coef = gs_loss_grad_coeffs(G, A.to(torch.complex128), ctx.lam) * g_obj.double()
+        head, gt, pred, G, A, lam = ctx.saved_tensors
+        coef = gs_loss_grad_coeffs(G, A.to(torch.complex128), lam) * g_obj.double()
         return ops.complex_lincomb(head, gt, pred, coef), None, None, None
 
 

@@ -123,6 +123,34 @@ def test_training_step_autograd_matches_reference_gradients():
         torch.backends.cudnn.allow_tf32 = True
 
 
+def test_training_step_cuda_graph_replay_matches_eager():
+    """train_step_graphed: the whole step as one CUDA graph.  With lr = 0 the weights stay put, so every replay must give the
+    eager step's objective and gradients, and a new batch copied into the static buffers must change the result."""
+    import generative_audio_b200 as G
+    g = load_golden("model_step_g2_b4")
+    m, sd = build_model(5, 2, "f32")
+    st = G.NPPCAudioStep(m, 500, 1.0)
+    st.step = 600
+    batch = (g["noisy"].cuda(), g["clean"].cuda())
+    other = (batch[0].flip(0).contiguous(), batch[1].flip(0).contiguous())
+    opt = torch.optim.Adam(m.audio_pc_wrapper.parameters(), lr=0.0, capturable=True)
+    w = m.audio_pc_wrapper.net.sb_model.fc_output_layer.weight
+    got = []
+    for b in (batch, batch, other):
+        obj_g, _ = st.train_step_graphed(b, opt)
+        got.append((obj_g.item(), w.grad.detach().clone()))
+    assert st.step == 603
+    # eager references afterwards (no autograd graph from an eager backward may be alive when the capture starts: its
+    # AccumulateGrad nodes would tie the legacy stream to the capturing one)
+    for b, (og, gg) in zip((batch, batch, other), got):
+        m.zero_grad(set_to_none=True)
+        _, obj_e, _ = st.base_step(b, requires_grad=True)
+        obj_e.backward()
+        assert abs(og - obj_e.item()) < 1e-5 * max(1.0, abs(obj_e.item()))
+        assert rel_err(gg.cpu(), w.grad.cpu()) < 1e-4
+    assert abs(got[0][0] - got[2][0]) > 0 or not torch.equal(got[0][1], got[2][1])   # the new batch did reach the static buffers
+
+
 def test_training_step_launches_no_library_rnn_or_conv():
     """the step's launch list holds the hand-written tcgen05 kernels and no cuDNN RNN / convolution."""
     import generative_audio_b200 as G
