@@ -38,14 +38,13 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ x, const floa
 
 // Gram rows J0..J1-1 (upper triangle, k >= j) of NV vectors. grid (chunks, B).
 template <bool COMPLEX, int NV, int J0, int J1>
-__global__ void __launch_bounds__(TPB) gram_kernel(const float* __restrict__ x, const float* __restrict__ gt,
-                                                  const float* __restrict__ pred, int n, long long P,
-                                                  SampleScratch* __restrict__ scr) {
+__device__ __forceinline__ void gram_tile(const float* __restrict__ x, const float* __restrict__ gt,
+                                          const float* __restrict__ pred, int n, long long P,
+                                          SampleScratch* __restrict__ scr, int b, int tile) {
     constexpr int NPAIR = (J1 - J0) * NV - (J1 * (J1 - 1) / 2 - J0 * (J0 - 1) / 2);
     constexpr int NACC = NPAIR * (COMPLEX ? 2 : 1);
-    const int b = blockIdx.y;
-    // one CTA = one run of TPB*RUN elements: fp32 per-thread partials over RUN (=16) products only, fp64 from there on
-    const long long base = (long long)blockIdx.x * TPB * RUN;
+    // one tile = one run of TPB*RUN elements: fp32 per-thread partials over RUN (=16) products only, fp64 from there on
+    const long long base = (long long)tile * TPB * RUN;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
@@ -94,6 +93,12 @@ __global__ void __launch_bounds__(TPB) gram_kernel(const float* __restrict__ x, 
         int k = j + pair;
         atomicAdd(&scr[b].G[(j * NV_MAX + k) * 2 + comp], d);
     }
+}
+template <bool COMPLEX, int NV, int J0, int J1>
+__global__ void __launch_bounds__(TPB) gram_kernel(const float* __restrict__ x, const float* __restrict__ gt,
+                                                  const float* __restrict__ pred, int n, long long P,
+                                                  SampleScratch* __restrict__ scr) {
+    gram_tile<COMPLEX, NV, J0, J1>(x, gt, pred, n, P, scr, blockIdx.y, blockIdx.x);
 }
 
 struct cd { double x, y; };
@@ -196,14 +201,16 @@ __device__ __forceinline__ cd warp_sum_cd(cd v) {
     }
     return v;
 }
+struct SolveSmem { cd Gs[NV_MAX][NV_MAX + 1], ahat_s[12][NV_MAX + 1], v_s[12][NV_MAX + 1]; };
+// one warp solves sample b (lane k owns coefficient k)
 template <bool COMPLEX>
-__global__ void __launch_bounds__(32) gs_solve_warp_kernel(SampleScratch* __restrict__ scr, int B, int n, int do_gs, int has_err,
-                                                          float* __restrict__ err_norm, float* __restrict__ err_proj,
-                                                          float* __restrict__ w_norms, float* __restrict__ reconst_err,
-                                                          float* __restrict__ second_moment) {
-    __shared__ cd Gs[NV_MAX][NV_MAX + 1], ahat_s[12][NV_MAX + 1], v_s[12][NV_MAX + 1];
-    const int b = blockIdx.x, lane = threadIdx.x;
-    if (b >= B) return;
+__device__ __noinline__ void solve_warp(SampleScratch* __restrict__ scr, int b, int n, int do_gs, int has_err,
+                                           float* __restrict__ err_norm, float* __restrict__ err_proj,
+                                           float* __restrict__ w_norms, float* __restrict__ reconst_err,
+                                           float* __restrict__ second_moment, SolveSmem& sm, int lane) {
+    auto& Gs = sm.Gs;
+    auto& ahat_s = sm.ahat_s;
+    auto& v_s = sm.v_s;
     SampleScratch& s = scr[b];
     const int nv = n + (has_err ? 1 : 0);
     for (int idx = lane; idx < nv * nv; idx += 32) {
@@ -265,6 +272,120 @@ __global__ void __launch_bounds__(32) gs_solve_warp_kernel(SampleScratch* __rest
     if (has_err && lane == 0) {
         reconst_err[b] = (float)(1.0 - nu_sum);
         err_norm[b] = (float)(eps_n + (COMPLEX ? 0.0 : 1e-6));
+    }
+}
+template <bool COMPLEX>
+__global__ void __launch_bounds__(32) gs_solve_warp_kernel(SampleScratch* __restrict__ scr, int B, int n, int do_gs, int has_err,
+                                                          float* __restrict__ err_norm, float* __restrict__ err_proj,
+                                                          float* __restrict__ w_norms, float* __restrict__ reconst_err,
+                                                          float* __restrict__ second_moment) {
+    __shared__ SolveSmem sm;
+    if ((int)blockIdx.x >= B) return;
+    solve_warp<COMPLEX>(scr, blockIdx.x, n, do_gs, has_err, err_norm, err_proj, w_norms, reconst_err, second_moment, sm, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-launch pipeline: Gram pass, coefficient solve and apply pass of ALL samples in ONE persistent kernel.
+// Tasks are handed out in order by an atomic counter: stage s = Gram tiles of sample s, then apply tiles of sample s - LAG.
+// The CTA that finishes the last Gram tile of a sample solves it (one warp, fp64) and publishes `ready[b]`; by the time the
+// apply tiles of that sample come up (LAG samples of work later) the solve is long done and the sample's 2.6 MB are still in
+// the 126 MB L2, so every vector is read from HBM once and written once (the three-launch version re-read x from HBM for
+// the apply pass: 495 MB moved for 330 MB algorithmic at B = 64) and the solve's latency hides behind other samples' tiles.
+// All CTAs are co-resident (grid <= SMs x occupancy) and a task only waits on tasks handed out before it: no deadlock.
+// LAG: with ~150 tasks in flight (one per CTA) and 16 tiles per sample and phase, tasks handed out together span ~5 stages; the
+// apply tiles of a sample must come up well after its solve (~10 us on one warp) has finished, or whole waves of CTAs spin on
+// `ready` (measured: LAG = 2 -> 395 us, slower than three launches).  8 samples = 21 MB of x, far inside the 126 MB L2.
+constexpr int PIPE_LAG = 8;
+struct PipeCtl { unsigned int next, pad[3]; };
+template <bool COMPLEX, int NV>
+__global__ void __launch_bounds__(TPB, 3) gs_pipeline_kernel(const float* __restrict__ x, const float* __restrict__ gt,
+                                                         const float* __restrict__ pred, int B, int n, long long P,
+                                                         SampleScratch* __restrict__ scr, PipeCtl* __restrict__ ctl,
+                                                         unsigned int* __restrict__ done, unsigned int* __restrict__ ready,
+                                                         int do_gs, int has_err, float* __restrict__ out,
+                                                         float* __restrict__ err_norm, float* __restrict__ err_proj,
+                                                         float* __restrict__ w_norms, float* __restrict__ reconst_err,
+                                                         float* __restrict__ second_moment) {
+    constexpr int N = 12;   // coefficient matrix stride
+    __shared__ SolveSmem sm;
+    __shared__ float2 A[N][N];
+    __shared__ unsigned int s_task, s_last;
+    const int tiles = (int)((P + (long long)TPB * RUN - 1) / ((long long)TPB * RUN));
+    const int LAG = B < PIPE_LAG ? B : PIPE_LAG;
+    const long long total = 2LL * B * tiles;
+    const size_t vs = (size_t)(COMPLEX ? 2 : 1) * P;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_task = atomicAdd(&ctl->next, 1u);
+        __syncthreads();
+        const long long t = s_task;
+        if (t >= total) break;
+        // decode: stages 0..LAG-1 Gram only, LAG..B-1 Gram(s) then apply(s - LAG), B..B+LAG-1 apply only
+        int b, tile;
+        bool is_gram;
+        const long long head = (long long)LAG * tiles, mid = (long long)(B - LAG) * 2 * tiles;
+        if (t < head) { b = (int)(t / tiles); tile = (int)(t % tiles); is_gram = true; }
+        else if (t < head + mid) {
+            const long long u = t - head;
+            const int sidx = LAG + (int)(u / (2 * tiles)), r = (int)(u % (2 * tiles));
+            is_gram = r < tiles;
+            b = is_gram ? sidx : sidx - LAG;
+            tile = is_gram ? r : r - tiles;
+        } else { const long long u = t - head - mid; b = B - LAG + (int)(u / tiles); tile = (int)(u % tiles); is_gram = false; }
+        if (is_gram) {
+            gram_tile<COMPLEX, NV, 0, NV>(x, gt, pred, n, P, scr, b, tile);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(&done[b], 1u) == (unsigned)(tiles - 1));
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (threadIdx.x < 32) {
+                    solve_warp<COMPLEX>(scr, b, n, do_gs, has_err, err_norm, err_proj, w_norms, reconst_err, second_moment, sm, threadIdx.x);
+                    __threadfence();
+                    __syncwarp();
+                    if (threadIdx.x == 0) atomicExch(&ready[b], 1u);
+                }
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                while (atomicAdd(&ready[b], 0u) == 0u) __nanosleep(64);
+                __threadfence();
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+                const int r = i / n, c = i % n;
+                A[r][c] = make_float2(__ldcg(&scr[b].A[(r * 12 + c) * 2]), __ldcg(&scr[b].A[(r * 12 + c) * 2 + 1]));
+            }
+            __syncthreads();
+            const float* xb = x + (size_t)b * n * vs;
+            float* ob = out + (size_t)b * n * vs;
+            const long long p0 = (long long)tile * TPB * RUN;
+#pragma unroll 4
+            for (int r = 0; r < RUN; ++r) {
+                const long long p = p0 + (long long)r * TPB + threadIdx.x;
+                if (p >= P) break;
+                float xr[NV], xi[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    if (k < n) { xr[k] = xb[k * vs + p]; xi[k] = COMPLEX ? xb[k * vs + P + p] : 0.f; }
+                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (i >= n) break;
+                    float wr = 0.f, wi = 0.f;
+#pragma unroll
+                    for (int k = 0; k <= i; ++k) {
+                        const float2 a = A[i][k];
+                        if (COMPLEX) { wr += a.x * xr[k] - a.y * xi[k]; wi += a.x * xi[k] + a.y * xr[k]; }
+                        else wr += a.x * xr[k];
+                    }
+                    if (i == 0) { wr = xr[0]; wi = xi[0]; }   // direction 0 is returned untouched (bit-exact)
+                    __stcs(&ob[i * vs + p], wr);
+                    if (COMPLEX) __stcs(&ob[i * vs + P + p], wi);
+                }
+            }
+        }
     }
 }
 
@@ -386,12 +507,50 @@ int run_chunk(const float* x, const float* gt, const float* pred, int B, int n, 
 // Optional L2-resident chunking (NPPC_GS_L2_MB=<MiB>): walk the batch in chunks of samples whose vectors fit in L2 so the
 // apply pass re-reads from L2.  Measured on B200 (B = 64, n = 5): 146 us unchunked vs 161 / 226 / 382 us at 80 / 40 / 20 MiB —
 // every chunk pays the serial fp64 coefficient solve (~28 us) and a small-grid launch, so the default is ONE chunk.
+template <bool COMPLEX, int NV>
+int launch_pipeline(const float* x, const float* gt, const float* pred, int B, int n, long long P, SampleScratch* scr, int do_gs,
+                    float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
+                    cudaStream_t s) {
+    // control block lives behind the per-sample scratch (nppc_gs_scratch_bytes reserves it): counter, done[B], ready[B]
+    PipeCtl* ctl = reinterpret_cast<PipeCtl*>(scr + B);
+    unsigned int* done = reinterpret_cast<unsigned int*>(ctl + 1);
+    unsigned int* ready = done + B;
+    NPPC_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(PipeCtl) + sizeof(unsigned int) * 2 * (size_t)B, s));
+    auto kern = gs_pipeline_kernel<COMPLEX, NV>;
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, 0) != cudaSuccess || occ < 1) occ = 1;
+    }
+    const long long total = 2LL * B * chunks_for(P, B);
+    long long grid = (long long)nppc::sm_count() * occ;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, TPB, 0, s>>>(x, gt, pred, B, n, P, scr, ctl, done, ready, do_gs, gt != nullptr, out, err_norm, err_proj,
+                                        w_norms, reconst_err, second_moment);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
 template <bool COMPLEX>
 int run(const float* x, const float* gt, const float* pred, int B, int n, long long P, void* scratch, int do_gs,
         float* out, float* err_norm, float* err_proj, float* w_norms, float* reconst_err, float* second_moment,
         cudaStream_t s) {
     SampleScratch* scr = (SampleScratch*)scratch;
     NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
+    // NPPC_GS_PIPELINE: 1 = always the single persistent launch, 0 = never, unset = only with the loss statistics.  Measured on
+    // B200 at B = 64, n = 5 (tools/kernel_bench.py): Gram-Schmidt alone 166 us pipelined vs 142 us in three launches (the Gram
+    // tiles' latency, ~30 us per 4096-element tile with its fp64 block reduction + atomics, needs the 4 CTAs/SM the small
+    // kernels reach; the merged kernel gets 3); with the error vector 192 us vs 208 us.  DRAM traffic 330 MB vs 495 MB either way.
+    static const int pipe_env = getenv("NPPC_GS_PIPELINE") ? atoi(getenv("NPPC_GS_PIPELINE")) : -1;
+    const int NVr = n + (gt != nullptr ? 1 : 0);
+    const bool pipeline = pipe_env == 1 || (pipe_env == -1 && gt != nullptr);
+    if (pipeline && out && NVr <= 7) {   // one persistent launch (register budget of the Gram tile: up to 7 vectors)
+        switch (NVr) {
+#define C(v) case v: return launch_pipeline<COMPLEX, v>(x, gt, pred, B, n, P, scr, do_gs, out, err_norm, err_proj, w_norms, reconst_err, second_moment, s);
+            C(1) C(2) C(3) C(4) C(5) C(6) C(7)
+#undef C
+        }
+    }
     static const long long budget = getenv("NPPC_GS_L2_MB") ? atoll(getenv("NPPC_GS_L2_MB")) << 20 : (1LL << 50);
     const long long per_sample = (long long)n * (COMPLEX ? 2 : 1) * P * 4;
     int chunk = out ? (int)(budget / (per_sample > 0 ? per_sample : 1)) : B;   // no apply pass -> nothing to re-read
@@ -458,7 +617,8 @@ extern "C" int nppc_complex_lincomb(const float* x, const float* gt, const float
 
 extern "C" size_t nppc_gs_scratch_bytes(int B, int n) {
     (void)n;
-    return sizeof(SampleScratch) * (size_t)(B > 0 ? B : 0);
+    const size_t b = (size_t)(B > 0 ? B : 0);
+    return sizeof(SampleScratch) * b + sizeof(PipeCtl) + sizeof(unsigned int) * 2 * b + 16;   // + the pipeline's control block
 }
 
 #define GS_ARGS_OK(name)                                                                          \

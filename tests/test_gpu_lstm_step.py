@@ -74,10 +74,11 @@ def test_lstm_step_backward_matches_autograd(I, H, O, R, T):
     y, ws = G.ops.lstm_step_forward(params, xs, R, train=True)
     grads, dxs = G.ops.lstm_step_backward(params, xs, R, ws, dy)
     # reference: fp64 autograd on the fp16-rounded input (what the kernels saw)
-    ps = [p.double().cpu().requires_grad_(True) for p in params]          # CPU: cuDNN's RNN backward needs training mode
-    xr = xs[:, :R, :I].permute(1, 0, 2).double().cpu().requires_grad_(True)
-    yr = _ref_lstm(ps, xr)
-    yr.backward(dy.double().cpu())
+    with torch.enable_grad():                                              # (another test module may have switched autograd off)
+        ps = [p.double().cpu().requires_grad_(True) for p in params]      # CPU: cuDNN's RNN backward needs training mode
+        xr = xs[:, :R, :I].permute(1, 0, 2).double().cpu().requires_grad_(True)
+        yr = _ref_lstm(ps, xr)
+        yr.backward(dy.double().cpu())
     assert rel_err(y.cpu(), yr.detach().cpu()) < 3e-3
     names = "w_ih0 w_hh0 b_ih0 b_hh0 w_ih1 w_hh1 b_ih1 b_hh1 fc_w fc_b".split()
     for n, g, p in zip(names, grads, ps):
