@@ -537,13 +537,16 @@ int run(const float* x, const float* gt, const float* pred, int B, int n, long l
         cudaStream_t s) {
     SampleScratch* scr = (SampleScratch*)scratch;
     NPPC_CUDA_OK(cudaMemsetAsync(scr, 0, sizeof(SampleScratch) * (size_t)B, s));
-    // NPPC_GS_PIPELINE: 1 = always the single persistent launch, 0 = never, unset = only with the loss statistics.  Measured on
-    // B200 at B = 64, n = 5 (tools/kernel_bench.py): Gram-Schmidt alone 166 us pipelined vs 142 us in three launches (the Gram
-    // tiles' latency, ~30 us per 4096-element tile with its fp64 block reduction + atomics, needs the 4 CTAs/SM the small
-    // kernels reach; the merged kernel gets 3); with the error vector 192 us vs 208 us.  DRAM traffic 330 MB vs 495 MB either way.
-    static const int pipe_env = getenv("NPPC_GS_PIPELINE") ? atoi(getenv("NPPC_GS_PIPELINE")) : -1;
+    // NPPC_GS_PIPELINE=1 opts into the single persistent launch.  It is NOT the default: measured on B200 at B = 64, n = 5
+    // (tools/kernel_bench.py, profiles/r02_hbm_ncu_summary.csv) Gram-Schmidt alone takes 166 us pipelined vs 142 us in three
+    // launches and 192-223 us vs 208 us with the error vector.  Two reasons, both visible in ncu: (1) the Gram tiles are
+    // latency-bound (~30 us per 4096-element tile incl. the fp64 block reduction + 42 fp64 atomics) and need the 4 CTAs/SM the
+    // small kernels reach — the merged kernel gets 3 (80 registers); (2) the apply pass does NOT find x in L2 (hit rate 27 %,
+    // 373 MB read for 198 MB algorithmic) although only ~50 MB of other traffic separates the two passes, with or without
+    // L2::evict_last / evict_first cache hints on the loads (tried: 172 / 223 us).
+    static const int pipe_env = getenv("NPPC_GS_PIPELINE") ? atoi(getenv("NPPC_GS_PIPELINE")) : 0;
     const int NVr = n + (gt != nullptr ? 1 : 0);
-    const bool pipeline = pipe_env == 1 || (pipe_env == -1 && gt != nullptr);
+    const bool pipeline = pipe_env == 1;
     if (pipeline && out && NVr <= 7) {   // one persistent launch (register budget of the Gram tile: up to 7 vectors)
         switch (NVr) {
 #define C(v) case v: return launch_pipeline<COMPLEX, v>(x, gt, pred, B, n, P, scr, do_gs, out, err_norm, err_proj, w_norms, reconst_err, second_moment, s);

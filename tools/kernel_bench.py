@@ -26,8 +26,13 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 torch.manual_seed(0)
 
 
+ONCE = os.environ.get("NPPC_KB_ONCE") == "1"   # one launch per op: the run that ncu --set full captures
+
+
 def timeit(fn, reps=7):
-    for _ in range(3):
+    if ONCE:
+        reps = 1
+    for _ in range(0 if ONCE else 3):
         fn()
     ts = []
     for _ in range(reps):
