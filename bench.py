@@ -131,6 +131,72 @@ def gpu_eager_run(batch, steps=3, warmup=2):
                                       "cuDNN LSTM, cuFFT, library convolutions), device-resident input"}
 
 
+def sweep_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist):
+    """BASELINE config 5 as written: a job of --utterances synthetic 4 s utterances, round-robin sharded over the ranks
+    (utterance i -> rank i % N, sharding.shard_utterances), each rank walking its shard in micro-batches of --batch with a
+    PARTIAL last micro-batch, pinned host waveforms in, pinned host w_mat out (forward_host).  value = all utterances' audio
+    seconds / the slowest rank's device time for its whole shard; `steps` = passes over the job."""
+    import torch
+    from generative_audio_b200.sharding import aggregate_throughput, shard_utterances
+    model, _ = build_model(N_DIRS, 1, args.lstm_impl)
+    mine = shard_utterances(args.utterances, rank, world)
+    B = args.batch
+    batches = [mine[i:i + B] for i in range(0, len(mine), B)]
+    # utterance i is wave(1, L, seed = 10_000 + i): the same job whatever the number of ranks
+    hosts = [torch.cat([wave(1, L, 10_000 + i) for i in idx]).pin_memory() for idx in batches]
+    outs = [torch.empty(len(idx), N_DIRS, 2, F, T, dtype=torch.float32).pin_memory() for idx in batches]
+
+    def one_pass():
+        for h, o in zip(hosts, outs):
+            model.forward_host(h, o)
+
+    def timed(n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            one_pass()
+        if getattr(model, "_copy_stream", None) is not None:
+            torch.cuda.current_stream().wait_stream(model._copy_stream)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    if hosts:
+        model.forward_host(hosts[0], outs[0])     # warm-up: plans, tables, allocator
+        if len(hosts[-1]) != len(hosts[0]):
+            model.forward_host(hosts[-1], outs[-1])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(args.steps) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        dist.barrier()
+    _, ms_job = aggregate_throughput(len(mine) * L / SR, ms)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    audio_s = args.utterances * L / SR
+    line = {"metric": "audio-sec/sec NPPC-audio inference, 1000-utterance sweep (16 kHz, 5 PCs)", "value": audio_s / (ms_job * 1e-3),
+            "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms_job, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.lstm_impl == "tc" else "f32", "data": "synthetic", "mode": "sweep",
+            "config": {"workload": f"BASELINE config 5: {args.utterances} synthetic 4 s utterances, round-robin over {world} rank(s), micro-batch "
+                                   f"{B} with a partial last batch ({len(batches)} micro-batches on rank 0, last = {len(batches[-1]) if batches else 0}), "
+                                   "host waveforms in / host w_mat out", "utterances": args.utterances, "batch_per_gpu": B, "n_dirs": N_DIRS,
+                       "parallelism": f"utterance-sharded x{world} (no data-path collective)"},
+            "e2e": {"value": audio_s / (ms_job * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_job,
+                    "h2d_bytes_per_step": sum(h.numel() for h in hosts) * 4, "d2h_bytes_per_step": sum(o.numel() for o in outs) * 4},
+            "clocks": sampler.summary()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist):
     """BASELINE config 3 / 5: one training step of the PC head per GPU per step (frozen backbone on the inference kernels, head
     forward + hand-written backward, Adam), gradients averaged over the ranks by the bucketed all-reduce that overlaps the
@@ -268,7 +334,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline leg (N = 1 only)")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+    ap.add_argument("--utterances", type=int, default=1000, help="--mode sweep: utterances in the whole job (BASELINE config 5)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "sweep"],
                     help="infer: NPPCModel.forward (the headline metric); train: BASELINE config 3, one PC-head training step per "
                          "GPU (B = 32 x 4 s, drop_band groups = 2) with the DP gradient all-reduce over NCCL when N > 1")
     ap.add_argument("--train-batch", type=int, default=32)
@@ -327,6 +394,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if args.mode == "train":
         return train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist)
+    if args.mode == "sweep":
+        return sweep_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockSampler, dist)
     model, _ = build_model(N_DIRS, 1, args.lstm_impl)
     B = args.batch
     x_host = wave(B, L, 1000 + rank).pin_memory()

@@ -44,7 +44,7 @@ PROTOTYPES = {
     "nppc_mix_scratch_bytes": (_sz, [_i]),
     "nppc_mix_with_snr": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "nppc_time_to_spec_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "nppc_subband_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_tsse": (_i, [_p, _i, _i, _i, C.POINTER(_i), C.POINTER(_p), C.POINTER(_p)] + [_p] * 6 + [_i, _p, _p, _p]),
     "nppc_prelu_stats": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "nppc_tcn_mid": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),

@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(TPB) subband_sum_kernel(const float* __restric
 constexpr int PK_ROWS = 8;
 constexpr int PK_T = 32;
 constexpr int PK_KP = 64;
-template <bool F16OUT>
+// CUM: norm_type = cumulative_laplace_norm (base_model.py:227-257 applied to the [B, F, S, T'] sub-band tensor, i.e. per LSTM
+// row: y[k, t] = x[k, t] / (cumsum_t(sum_k x[k, .]) / (S (t + 1)) + EPSILON)).  The CTA then owns its 8 rows for ALL frames
+// (grid.y = 1) and walks the 32-frame tiles in order, carrying each row's running sum (fp64) in its warp.
+template <bool F16OUT, bool CUM>
 __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restrict__ nbr, const float* __restrict__ fb,
                                                           const float* __restrict__ fbr, const float* __restrict__ fbi,
                                                           int B, int F, int Tp, int nn, int G, int RS,
@@ -342,11 +345,11 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
     const long long R = (long long)B * Fg;
     const int r = threadIdx.x >> 5, tt = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * PK_ROWS + r;
-    const int t = blockIdx.y * PK_T + tt;
     float* mine = tile + (size_t)r * RSK + tt;   // element k at mine[k * TS]
-    if (row < R && t < Tp) {
+    int sb = 0, f = 0;
+    if (row < R) {
         int ob = (int)(row / Fg), j = (int)(row % Fg);
-        int sb = ob, f = j;
+        sb = ob; f = j;
         if (G > 1) {  // drop_band: group g owns a run of output batches; sample = g + G*(ob - start), freq = g + G*j
             int g = 0, start = 0;
             for (; g < G; ++g) {
@@ -357,18 +360,49 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
             sb = g + G * (ob - start);
             f = g + G * j;
         }
-        const float den = (float)(sums[sb] / ((double)F * S * Tp)) + 1e-5f;
-        const float inv = 1.0f / den;   // x * (1/den): within 1 ulp of the reference's x / den, well inside the 1e-4 budget
+    }
+    double carry = 0.0;   // CUM: running sum of the row up to the previous tile (same value in every lane of the warp)
+    const int ntile = CUM ? (Tp + PK_T - 1) / PK_T : 1;
+    for (int tb = 0; tb < ntile; ++tb) {
+    const int tile_y = CUM ? tb : (int)blockIdx.y;
+    const int t = tile_y * PK_T + tt;
+    if (CUM && tb > 0) __syncthreads();   // the previous tile has been written out
+    if (row < R && t < Tp) {
         const float* base = nbr + (size_t)sb * F * Tp + t;
         const size_t off = (size_t)sb * F * Tp + t;
+        if (CUM) {
+            double ssum = 0.0;
 #pragma unroll 8
-        for (int k = 0; k < 2 * nn + 1; ++k) mine[k * TS] = base[reflect_idx(f + k - nn, F) * Tp] * inv;
-        mine[(2 * nn + 1) * TS] = fb[off + (size_t)f * Tp] * inv;
-        mine[(2 * nn + 2) * TS] = fbr[off + (size_t)f * Tp] * inv;
-        mine[(2 * nn + 3) * TS] = fbi[off + (size_t)f * Tp] * inv;
-        for (int k = S; k < PK_KP; ++k) mine[k * TS] = 0.f;
+            for (int k = 0; k < 2 * nn + 1; ++k) { const float v = base[reflect_idx(f + k - nn, F) * Tp]; mine[k * TS] = v; ssum += (double)v; }
+            const float v1 = fb[off + (size_t)f * Tp], v2 = fbr[off + (size_t)f * Tp], v3 = fbi[off + (size_t)f * Tp];
+            mine[(2 * nn + 1) * TS] = v1; mine[(2 * nn + 2) * TS] = v2; mine[(2 * nn + 3) * TS] = v3;
+            ssum += (double)v1 + (double)v2 + (double)v3;
+            double cum = ssum;   // inclusive scan over the warp's 32 frames
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, cum, o); if (tt >= o) cum += u; }
+            cum += carry;
+            const float inv = 1.0f / ((float)(cum / ((double)S * (t + 1))) + 1.1920929e-07f);
+            for (int k = 0; k < S; ++k) mine[k * TS] *= inv;
+            for (int k = S; k < PK_KP; ++k) mine[k * TS] = 0.f;
+            carry = __shfl_sync(0xffffffffu, cum, 31);
+        } else {
+            const float den = (float)(sums[sb] / ((double)F * S * Tp)) + 1e-5f;
+            const float inv = 1.0f / den;   // x * (1/den): within 1 ulp of the reference's x / den, well inside the 1e-4 budget
+#pragma unroll 8
+            for (int k = 0; k < 2 * nn + 1; ++k) mine[k * TS] = base[reflect_idx(f + k - nn, F) * Tp] * inv;
+            mine[(2 * nn + 1) * TS] = fb[off + (size_t)f * Tp] * inv;
+            mine[(2 * nn + 2) * TS] = fbr[off + (size_t)f * Tp] * inv;
+            mine[(2 * nn + 3) * TS] = fbi[off + (size_t)f * Tp] * inv;
+            for (int k = S; k < PK_KP; ++k) mine[k * TS] = 0.f;
+        }
     } else {
         for (int k = 0; k < PK_KP; ++k) mine[k * TS] = 0.f;
+        if (CUM) {   // keep the warp's shuffles convergent (only rows >= R or the last, partial tile get here)
+            double cum = 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, cum, o); if (tt >= o) cum += u; }
+            carry = __shfl_sync(0xffffffffu, cum + carry, 31);
+        }
     }
     __syncthreads();
     // write phase: piece = 8 consecutive k of one (frame, row); PK_T*PK_ROWS*8 pieces per CTA
@@ -376,7 +410,7 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
     for (int idx = threadIdx.x; idx < PIECES; idx += TPB) {
         const int kq = idx & 7, rr = (idx >> 3) & (PK_ROWS - 1), ft = idx >> 6;
         const long long orow = (long long)blockIdx.x * PK_ROWS + rr;
-        const int ot = blockIdx.y * PK_T + ft;
+        const int ot = tile_y * PK_T + ft;
         if (orow >= RS || ot >= Tp) continue;
         const float* src = tile + (size_t)rr * RSK + (size_t)(kq * 8) * TS + ft;
         float v[8];
@@ -397,6 +431,7 @@ __global__ void __launch_bounds__(TPB) subband_pack_kernel(const float* __restri
             d[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
+    }   // tile loop
 }
 
 // y [B*Fp, O, Tp] -> out [B, O, Fp, Tp-la] (drop first `la` frames)
@@ -556,7 +591,7 @@ extern "C" int nppc_drop_band(const float* x, int B, int C, int F, int T, int gr
 }
 
 extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B,
-                                 int F, int Tp, int num_neighbor, int groups, int KP, int R_stride, double* sums,
+                                 int F, int Tp, int num_neighbor, int groups, int KP, int R_stride, int cumulative, double* sums,
                                  float* xs_f32, void* xs_f16, void* stream) {
     NPPC_CHECK_ARG(nbr_src && fb && fbr && fbi && sums, "nppc_subband_pack: null pointer");
     NPPC_CHECK_ARG(xs_f32 || xs_f16, "nppc_subband_pack: no output requested");
@@ -576,14 +611,19 @@ extern "C" int nppc_subband_pack(const float* nbr_src, const float* fb, const fl
     dim3 grid((unsigned)nppc::cdiv(R_stride, PK_ROWS), (unsigned)nppc::cdiv(Tp, PK_T));
     int nlaunch = 1;
     const size_t smem = sizeof(float) * PK_ROWS * (PK_KP * (PK_T + 1) + 1);
-    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPPC_CUDA_OK(cudaFuncSetAttribute(subband_pack_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cumulative) grid.y = 1;   // the CTA walks all frames of its 8 rows (running mean along T')
     if (xs_f32) {
-        subband_pack_kernel<false><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f32);
+        if (cumulative) subband_pack_kernel<false, true><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f32);
+        else subband_pack_kernel<false, false><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f32);
         ++nlaunch;
     }
     if (xs_f16) {
-        subband_pack_kernel<true><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f16);
+        if (cumulative) subband_pack_kernel<true, true><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f16);
+        else subband_pack_kernel<true, false><<<grid, TPB, smem, s>>>(nbr_src, fb, fbr, fbi, B, F, Tp, num_neighbor, G, R_stride, sums, xs_f16);
         ++nlaunch;
     }
     NPPC_COUNT_LAUNCH(nlaunch);

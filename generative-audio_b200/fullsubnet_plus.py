@@ -83,22 +83,10 @@ class FullSubNet_Plus(nn.Module):
         impl = _IMPL[self.lstm_impl]
         dt = torch.float16 if impl == 1 else torch.float32
         G = self.num_groups_in_drop_band
-        if self.norm_type == "offline_laplace_norm":
-            xs, R = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt, pad_rows=(impl == 2))
-            Fp = R // B
-        else:
-            # explicit route through the standalone kernels (cumulative norm is not fused into the packer)
-            n = self.sb_num_neighbors
-            parts = [ops.unfold(nbr_src[:, None].contiguous(), n).reshape(B, F, 2 * n + 1, Tp)]
-            parts += [v.reshape(B, F, 1, Tp) for v in (fb, fbr, fbi)]
-            sb = ops.cumulative_laplace_norm(torch.cat(parts, dim=2).contiguous())
-            if B > 1:
-                sb = ops.drop_band(sb.permute(0, 2, 1, 3).contiguous(), G).permute(0, 2, 1, 3)
-            Fp = sb.shape[1]
-            S = sb.shape[2]
-            R = B * Fp
-            xs = torch.zeros(Tp, ops.padded_rows(R, torch.float16 if impl == 2 else dt), KP, device=fb.device, dtype=dt)
-            xs[:, :R, :S] = sb.reshape(R, S, Tp).permute(2, 0, 1).to(dt)
+        # one fused kernel for both norm types: unfold ++ cat ++ (offline | cumulative) norm ++ drop_band -> time-major input
+        xs, R = ops.subband_pack(nbr_src, fb, fbr, fbi, self.sb_num_neighbors, G, KP, dt, pad_rows=(impl == 2),
+                                 cumulative=(self.norm_type == "cumulative_laplace_norm"))
+        Fp = R // B
         return self.sb_model.lstm_forward(xs, impl, R), Fp
 
     @torch.no_grad()

@@ -426,10 +426,11 @@ def padded_rows(R: int, dtype) -> int:
 
 
 def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int = 64, dtype=torch.float32, pad_rows: bool = False,
-                 want_sums: bool = False):
+                 want_sums: bool = False, cumulative: bool = False):
     """Fused unfold ++ cat ++ offline_laplace_norm ++ drop_band -> time-major LSTM input [T', R_stride, KP]
     (R = B*F' real rows; rows R..R_stride-1 are zero padding for the tensor-core paths: always for fp16, for fp32 when
-    pad_rows). Returns (xs, R) or (xs, R, sums [B] fp64 = per-sample sum of the un-normalised sub-band tensor)."""
+    pad_rows). Returns (xs, R) or (xs, R, sums [B] fp64 = per-sample sum of the un-normalised sub-band tensor).
+    cumulative=True: norm_type "cumulative_laplace_norm" (running mean of each row's own features) instead of the offline norm."""
     nbr_src, fb, fbr, fbi = (_f32(v) for v in (nbr_src, fb, fbr, fbi))
     _chk(nbr_src, fb, fbr, fbi)
     B, F, Tp = nbr_src.shape
@@ -439,7 +440,7 @@ def subband_pack(nbr_src, fb, fbr, fbi, num_neighbor: int, groups: int, KP: int 
     xs = torch.empty(Tp, RS, KP, device=fb.device, dtype=dtype)
     sums = torch.empty(B, device=fb.device, dtype=torch.float64)
     _lib.check(_lib.load().nppc_subband_pack(nbr_src.data_ptr(), fb.data_ptr(), fbr.data_ptr(), fbi.data_ptr(), B, F, Tp,
-                                             num_neighbor, groups, KP, RS, sums.data_ptr(),
+                                             num_neighbor, groups, KP, RS, int(cumulative), sums.data_ptr(),
                                              xs.data_ptr() if dtype == torch.float32 else 0,
                                              xs.data_ptr() if dtype == _F16 else 0, _stream()), "nppc_subband_pack")
     return (xs, R, sums) if want_sums else (xs, R)

@@ -163,9 +163,11 @@ int nppc_mask_blend(const float* x_in, int Cin, const float* x, const float* mas
  * sample, drop_band(groups) row selection, written TIME-MAJOR as xs [T', R_stride, KP] (KP >= S, zero padded;
  * rows R..R_stride-1 of every step are zero: the tensor-core LSTM wants R_stride % 128 == 0),
  * R = B*F' rows ordered like the reference's reshape(B*F', S, T').  nbr_src/fb/fbr/fbi are [B,F,T'].
- * xs_f32 (fp32) and/or xs_f16 (IEEE fp16, saturating) may be NULL.  `sums` [B] fp64 scratch. */
+ * xs_f32 (fp32) and/or xs_f16 (IEEE fp16, saturating) may be NULL.  `sums` [B] fp64 scratch.
+ * cumulative != 0: norm_type = "cumulative_laplace_norm" (base_model.py:227-257 on the [B,F,S,T'] tensor): every row is divided
+ * by the running mean of its own S features, cumsum_t(sum_k x) / (S (t+1)) + EPSILON, instead of the per-sample mean. */
 int nppc_subband_pack(const float* nbr_src, const float* fb, const float* fbr, const float* fbi, int B, int F,
-                      int Tp, int num_neighbor, int groups, int KP, int R_stride, double* sums, float* xs_f32,
+                      int Tp, int num_neighbor, int groups, int KP, int R_stride, int cumulative, double* sums, float* xs_f32,
                       void* xs_f16, void* stream);
 
 /* ---- a3: TSSE channel attention ----------------------------------------------------------------------

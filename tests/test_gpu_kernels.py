@@ -191,6 +191,28 @@ def test_subband_pack(ops, B, G):
     assert torch.count_nonzero(xb[:, R:, :]) == 0
 
 
+@pytest.mark.parametrize("B,G,Tp", [(2, 1, 37), (3, 2, 70), (1, 1, 253)])
+def test_subband_pack_cumulative_norm(ops, B, G, Tp):
+    """norm_type = cumulative_laplace_norm fused into the packer (base_model.py:227-257 on the [B,F,S,T'] tensor): the running
+    mean crosses tile boundaries (Tp > 32) and, for signed inputs, zero — the fp64 oracle arbitrates like in the model test."""
+    gen = torch.Generator().manual_seed(18)
+    nbr, fb, fbr, fbi = (torch.rand(B, 257, Tp, generator=gen) + 0.05 for _ in range(4))
+    def ref_of(dt):
+        parts = [O.unfold(nbr.to(dt)[:, None], 15).reshape(B, 257, 31, Tp)] + [v.to(dt)[:, :, None] for v in (fb, fbr, fbi)]
+        sb = O.cumulative_laplace_norm(torch.cat(parts, dim=2))
+        if B > 1:
+            sb = O.drop_band(sb.permute(0, 2, 1, 3), G).permute(0, 2, 1, 3)
+        return sb.reshape(-1, 34, Tp).permute(2, 0, 1)
+    ref64, ref32 = ref_of(torch.float64), ref_of(torch.float32)
+    xs, R = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.float32, cumulative=True)
+    xs = xs.cpu()
+    assert R == ref64.shape[1] and xs.shape == (Tp, R, 64)
+    assert rel_err(xs[:, :, :34], ref64) < max(TOL, 2 * rel_err(ref32, ref64))
+    assert torch.count_nonzero(xs[:, :, 34:]) == 0
+    xh, _ = ops.subband_pack(cu(nbr), cu(fb), cu(fbr), cu(fbi), 15, G, 64, torch.float16, cumulative=True)
+    assert rel_err(xh.cpu().float()[:, :R, :34], ref64) < 1e-2 and torch.count_nonzero(xh[:, R:, :]) == 0
+
+
 def test_lstm_f32(ops):
     import weights
     p = weights.synth_state_dict(5, 0, "pretrained_restoration_model.")
