@@ -57,6 +57,10 @@ PROTOTYPES = {
     "nppc_lstm_step_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "nppc_lstm_step_backward": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p, _p, _p, _p]),
     "nppc_gemm_f16_atb": (_i, [_p, _p, _ll, _i, _i, _i, _p, _p, _p]),
+    "nppc_conv3x3_pack_weights": (_i, [_p, _i, _i, _i, _p, _p]),
+    "nppc_conv3x3_tc": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "nppc_nchw_to_nhwc_f16": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_conv1x1_out": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),
     "nppc_gemm_f16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),

@@ -60,6 +60,19 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // multicast variant: the tile lands at the same CTA-relative smem offset, and signals the same CTA-relative mbarrier,
 // in every CTA whose bit is set in cta_mask
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -254,6 +267,10 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 // row-major fp16 matrix [rows][cols] (cols % 64 == 0) viewed as [cols/64 K slabs][rows][64]: box = [n_slabs][box_rows][64],
 // 128B swizzle -> n_slabs consecutive K-major SW128 operand tiles in shared memory from ONE TMA (coords: 0, row, first slab)
 int make_tmap_f16_kslabs(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t n_slabs);
+
+// NHWC fp16 [B][H][W][C] as a 4-D map (C, W, H, B), box [box_c][box_w][box_h][1], 128B swizzle (3x3 halo = OOB zero fill)
+int make_tmap_f16_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
+                       uint32_t box_w, uint32_t box_h);
 
 }  // namespace tc
 }  // namespace nppc

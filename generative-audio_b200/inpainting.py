@@ -63,9 +63,29 @@ class _DoubleConv(nn.Module):
         return self._fold
 
     mc_dropout = False   # MC-dropout inference (utils.enable_dropout, utils.py:334-338): Dropout layers stay active in eval
-    compute_dtype = None  # None = fp32 (parity path); torch.float16 / bfloat16 = 16-bit tensor-core convolutions (set_compute_dtype)
+    compute_dtype = None  # None = fp32 (parity path, cuDNN); torch.float16 / bfloat16 = cuDNN tensor-core convolutions;
+    #                       "tc" = the in-house tcgen05 implicit-GEMM convolutions on NHWC fp16 (row N4, set_compute_dtype("tc"))
+
+    def forward_tc(self, x0, x1=None):
+        """x0 [B,H,W,C0p] (and x1: the decoder's cat([skip, up]) is two K-loop segments, never materialised) -> [B,H,W,Cout] fp16."""
+        (w0, b0), (w1, b1) = self._folded()
+        C_in = w0.shape[1]
+        C1 = 0 if x1 is None else x1.shape[3]
+        C0 = C_in - C1
+        key = (self._fold_key, C0, C1)
+        if getattr(self, "_tc_key", None) != key:
+            self._tc = (ops.conv3x3_pack_weights(w0, C0, C1), b0, ops.conv3x3_pack_weights(w1, w1.shape[1], 0), b1)
+            self._tc_key = key
+        p0, b0, p1, b1 = self._tc
+        y = ops.conv3x3_tc(x0, x1, p0, b0, 0.2)
+        y = ops.conv3x3_tc(y, None, p1, b1, 0.2)
+        if self.mc_dropout and len(self.conv) > 6:
+            y = F.dropout(y, self.conv[6].p, training=True)
+        return y
 
     def forward(self, x):
+        if self.compute_dtype == "tc":
+            return self.forward_tc(*x) if isinstance(x, tuple) else self.forward_tc(x)
         (w0, b0), (w1, b1) = self._folded()
         if self.compute_dtype is not None:
             dt = self.compute_dtype
@@ -96,6 +116,8 @@ class _Down(nn.Module):
         self.mpconv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(in_ch, out_ch, dropout))
 
     def forward(self, x):
+        if self.mpconv[1].compute_dtype == "tc":   # NHWC fp16: the pooled view is channels-last, i.e. contiguous NHWC again
+            return self.mpconv[1](F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous())
         return self.mpconv(x)
 
 
@@ -108,6 +130,11 @@ class _Up(nn.Module):
         self.conv = _DoubleConv(in_ch, out_ch, dropout)
 
     def forward(self, x1, x2):
+        if self.conv.compute_dtype == "tc":   # NHWC fp16 in and out; cat([skip, up]) becomes the conv kernel's two K segments
+            u = self.up(x1.permute(0, 3, 1, 2))
+            dy, dx = x2.size(1) - u.size(2), x2.size(2) - u.size(3)
+            u = F.pad(u, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2)).permute(0, 2, 3, 1).contiguous()
+            return self.conv((x2, u))
         x1 = self.up(x1)
         dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
         x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
@@ -146,6 +173,9 @@ class UNet(nn.Module):
             raise RuntimeError("generative_audio_b200.inpainting.UNet: CUDA tensors only (no CPU fallback)")
         if self.training:
             raise RuntimeError("inference only: call .eval() (BatchNorm is folded into the convolutions, dropout is off)")
+        tc = self.inc.conv.compute_dtype == "tc"
+        if tc:
+            x = ops.nchw_to_nhwc_f16(x, 64)
         x1 = self.inc(x)
         x2 = self.down1(x1)
         x3 = self.down2(x2)
@@ -155,6 +185,8 @@ class UNet(nn.Module):
         x = self.up2(x, x3)
         x = self.up3(x, x2)
         x = self.up4(x, x1)
+        if tc:
+            return ops.conv1x1_out(x, self.outc.conv.weight, self.outc.conv.bias)
         return self.outc(x.float().contiguous())
 
 

@@ -703,6 +703,56 @@ def tcn_out_cl(o, x32, B: int, T: int, C: int, Np: int, Kp: int, stats2, u, vb, 
                "nppc_tcn_out_cl")
 
 
+# ---- N4: UNet convolutions on tcgen05 (NHWC fp16 implicit GEMM) --------------------------------------------------------------
+def conv3x3_pack_weights(w: torch.Tensor, C0: int, C1: int = 0):
+    """w [Cout, C0 + C1, 3, 3] fp32 (BatchNorm folded) -> fp16 [Cout, 9 * (C0p + C1p)] for conv3x3_tc."""
+    w = _f32(w)
+    _chk(w)
+    Cout = w.shape[0]
+    assert w.shape[1] == C0 + C1 and w.shape[2:] == (3, 3)
+    C0p, C1p = -(-C0 // 64) * 64, -(-C1 // 64) * 64
+    out = torch.empty(Cout, 9 * (C0p + C1p), device=w.device, dtype=_F16)
+    _lib.check(_lib.load().nppc_conv3x3_pack_weights(w.data_ptr(), Cout, C0, C1, out.data_ptr(), _stream()), "nppc_conv3x3_pack_weights")
+    return out
+
+
+def conv3x3_tc(x0: torch.Tensor, x1, w_packed: torch.Tensor, bias: torch.Tensor, negative_slope: float = 0.2):
+    """leaky_relu(conv3x3(cat(x0, x1), padding=1) + bias): x0 [B,H,W,C0p], x1 [B,H,W,C1p] or None (NHWC fp16) -> [B,H,W,Cout] fp16."""
+    _chk(x0, x1, w_packed, bias)
+    assert x0.dtype == _F16 and w_packed.dtype == _F16 and bias.dtype == torch.float32
+    B, H, W, C0p = x0.shape
+    C1p = 0 if x1 is None else x1.shape[3]
+    assert x1 is None or (x1.dtype == _F16 and x1.shape[:3] == x0.shape[:3])
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 9 * (C0p + C1p)
+    y = torch.empty(B, H, W, Cout, device=x0.device, dtype=_F16)
+    _lib.check(_lib.load().nppc_conv3x3_tc(x0.data_ptr(), C0p, _ptr(x1), C1p, w_packed.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, Cout,
+                                           float(negative_slope), _stream()), "nppc_conv3x3_tc")
+    return y
+
+
+def nchw_to_nhwc_f16(x: torch.Tensor, Cp: int = 64):
+    x = _f32(x)
+    _chk(x)
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, Cp, device=x.device, dtype=_F16)
+    _lib.check(_lib.load().nppc_nchw_to_nhwc_f16(x.data_ptr(), B, C, H, W, Cp, y.data_ptr(), _stream()), "nppc_nchw_to_nhwc_f16")
+    return y
+
+
+def conv1x1_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """unet outc: x [B,H,W,Cin] fp16 NHWC, w [Cout,Cin(,1,1)] fp32 -> [B,Cout,H,W] fp32."""
+    w, bias = _f32(w.reshape(w.shape[0], -1)), _f32(bias)
+    _chk(x, w, bias)
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == Cin and x.dtype == _F16
+    y = torch.empty(B, Cout, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nppc_conv1x1_out(x.data_ptr(), B, H * W, Cin, w.data_ptr(), bias.data_ptr(), Cout, y.data_ptr(), _stream()),
+               "nppc_conv1x1_out")
+    return y
+
+
 def assemble_mask(y: torch.Tensor, B: int, Fp: int, look_ahead: int):
     """y [B*F', O, T'] -> [B, O, F', T'-la] (fullsubnet_plus.py:227-229)."""
     _chk(y)

@@ -254,6 +254,20 @@ int nppc_lstm_step_backward(const nppc_lstm_weights* w, const void* xs, int R, i
 int nppc_gemm_f16_atb(const void* A, const void* B, long long rows, int Mo, int No, int splits, float* partials, float* C,
                       void* stream);
 
+/* ---- N4: the inpainting UNet's convolutions on tcgen05 (implicit GEMM, NHWC fp16) -----------------------------------------
+ * Replaces F.conv2d(3x3, padding=1) + eval-mode BatchNorm + LeakyReLU(0.2) of double_conv (nppc_audio/inpainting/networks/
+ * tmp_utils.py:8-35) and the decoder's torch.cat([skip, up]) + conv (tmp_utils.py:76-88): the K loop walks 9 taps x channel
+ * blocks of up to TWO input tensors, the halo comes from TMA out-of-bounds zero fill.
+ *   nppc_conv3x3_pack_weights: w [Cout, C0 + C1, 3, 3] fp32 (BatchNorm folded) -> fp16 [Cout, 9, C0p + C1p] (Cxp = Cx rounded up to 64)
+ *   nppc_conv3x3_tc:           y [B,H,W,Cout] fp16 = leaky_relu(conv3x3(cat(x0 [B,H,W,C0p], x1 [B,H,W,C1p] or NULL)) + bias)
+ *   nppc_nchw_to_nhwc_f16:     x [B,C,H,W] fp32 -> [B,H,W,Cp] fp16, channels >= C zero (network input)
+ *   nppc_conv1x1_out:          outc (unet.py:276): x [B,H*W,Cin] fp16 -> y [B,Cout,H*W] fp32, Cout <= 16 */
+int nppc_conv3x3_pack_weights(const float* w, int Cout, int C0, int C1, void* out, void* stream);
+int nppc_conv3x3_tc(const void* x0, int C0p, const void* x1, int C1p, const void* w_packed, const float* bias, void* y, int B,
+                    int H, int W, int Cout, float negative_slope, void* stream);
+int nppc_nchw_to_nhwc_f16(const float* x, int B, int C, int H, int W, int Cp, void* y, void* stream);
+int nppc_conv1x1_out(const void* x, int B, int HW, int Cin, const float* w, const float* bias, int Cout, float* y, void* stream);
+
 /* ---- a8/a11 output assembly -----------------------------------------------------------------------
  * y [B*F', O, T'] -> out [B, O, F', T'-la] dropping the first `look_ahead` frames
  * (fullsubnet_plus.py:227-229; networks.py:156-161 is the same memory layout with O = 2*n_dirs). */

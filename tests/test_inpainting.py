@@ -154,3 +154,47 @@ def test_mc_dropout_baseline():
     # the MC mean stays close to the deterministic restoration inside the gap, and dropout is switched off again afterwards
     assert rel_err(out["mean_prediction"].cpu(), (det * gap).cpu()) < 0.5
     assert torch.equal(model(masked_n, m4), det)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", [(2, 8, 31, 64, 0, 64), (1, 40, 50, 3, 0, 128), (2, 16, 62, 128, 64, 256), (1, 9, 17, 64, 64, 64)])
+def test_conv3x3_tcgen05_vs_conv2d(B, H, W, C0, C1, Cout):
+    """Row N4: the implicit-GEMM 3x3 convolution (TMA halo by out-of-bounds zero fill, two-tensor K loop for the decoder's
+    cat) against F.conv2d in fp64 on the fp16-rounded operands; partial border tiles, channel padding, both BN tile widths."""
+    import generative_audio_b200 as g
+    ops = g.ops
+    gen = torch.Generator().manual_seed(B * 1000 + W)
+    x = torch.randn(B, C0 + C1, H, W, generator=gen)
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=gen) / (3 * (C0 + C1) ** 0.5)
+    bias = torch.randn(Cout, generator=gen) * 0.1
+    C0p, C1p = -(-C0 // 64) * 64, -(-C1 // 64) * 64
+    x0 = ops.nchw_to_nhwc_f16(x[:, :C0].contiguous().cuda(), C0p)
+    x1 = ops.nchw_to_nhwc_f16(x[:, C0:].contiguous().cuda(), C1p) if C1 else None
+    y = ops.conv3x3_tc(x0, x1, ops.conv3x3_pack_weights(w.cuda(), C0, C1), bias.cuda(), 0.2)
+    assert y.shape == (B, H, W, Cout) and y.dtype == torch.float16
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.half().double(), w.half().double(), bias.double(), padding=1), 0.2)
+    assert rel_err(y.float().cpu().permute(0, 3, 1, 2), ref) < 2e-3
+
+
+@pytest.mark.gpu
+def test_inpainting_unet_on_tcgen05_matches_fp32_path():
+    """set_compute_dtype(model, "tc"): every 3x3 convolution of both UNets on the in-house tcgen05 kernel (no cuDNN conv in
+    the launch list); w_mat within 5e-3 of the fp32 golden."""
+    import generative_audio_b200 as g
+    from torch.profiler import ProfilerActivity, profile
+    gd = load_golden("inpaint_model_b2")
+    m = _product_model()
+    _, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"].cuda(), gd["masked_spec"].cuda(), gd["mask"].cuda())
+    g.inpainting.set_compute_dtype(m, "tc")
+    try:
+        w = m(masked_n, m4)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            w = m(masked_n, m4)
+            torch.cuda.synchronize()
+    finally:
+        g.inpainting.set_compute_dtype(m, None)
+    assert rel_err(w.cpu(), gd["w_mat"]) < 5e-3
+    names = " ".join(e.key for e in prof.key_averages())
+    assert "conv3x3_tc_kernel" in names
+    lib = " ".join(n for n in names.split() if "nppc" not in n and "anonymous" not in n).lower()
+    assert "cudnn" not in lib and "implicit_convolve" not in lib and "conv2d" not in lib
