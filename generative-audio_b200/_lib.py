@@ -60,6 +60,8 @@ PROTOTYPES = {
     "nppc_conv3x3_pack_weights": (_i, [_p, _i, _i, _i, _p, _p]),
     "nppc_conv3x3_tc": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "nppc_nchw_to_nhwc_f16": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "nppc_maxpool2x2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "nppc_upsample2x_pad_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_conv1x1_out": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "nppc_assemble_mask": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "nppc_gemm_bf16_tn": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p]),

@@ -148,42 +148,109 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int Cout, int C0
     }
 }
 
-// NCHW fp32 [B][C][H][W] -> NHWC fp16 [B][H][W][Cp] (channels >= C zero)
-__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x, int C, int HW, int Cp, __half* __restrict__ y) {
-    const long long n = (long long)gridDim.y * HW * Cp;
-    (void)n;
-    const int b = blockIdx.y;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)HW * Cp; i += (long long)gridDim.x * blockDim.x) {
-        const int p = (int)(i / Cp), c = (int)(i - (long long)p * Cp);
-        y[(size_t)b * HW * Cp + i] = __float2half_rn(c < C ? x[((size_t)b * C + c) * HW + p] : 0.f);
+// NCHW fp32 [B][C][H][W] -> NHWC fp16 [B][H][W][Cp] (channels >= C zero); thread = (pixel, 8-channel group): 16-byte stores
+__global__ void __launch_bounds__(256) nchw_to_nhwc_f16_kernel(const float* __restrict__ x, int C, int HW, int Cp, __half* __restrict__ y) {
+    const int b = blockIdx.y, G = Cp / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)HW * G; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / G), g = (int)(i - (long long)p * G);
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = g * 8 + e;
+            h[e] = __float2half_rn(c < C ? x[((size_t)b * C + c) * HW + p] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(y + ((size_t)b * HW + p) * Cp + g * 8) = *reinterpret_cast<const uint4*>(h);
     }
 }
 
-// 1x1 output convolution (unet.py outc): NHWC fp16 [B*HW][Cin] -> NCHW fp32 [B][Cout][HW], Cout <= 16; one thread per pixel
+// MaxPool2d(2) on NHWC fp16 (tmp_utils.py:45 nn.MaxPool2d(2)): [B][H][W][C] -> [B][H/2][W/2][C]; thread = (out pixel, 8 channels)
+__global__ void __launch_bounds__(256) maxpool2x2_nhwc_kernel(const __half* __restrict__ x, int H, int W, int C, __half* __restrict__ y) {
+    const int b = blockIdx.y, Ho = H / 2, Wo = W / 2, G = C / 8;
+    const long long n = (long long)Ho * Wo * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G);
+        const long long po = i / G;
+        const int wo = (int)(po % Wo), ho = (int)(po / Wo);
+        const __half* base = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C + g * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(base)), c = __ldg(reinterpret_cast<const uint4*>(base + C));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C)), e = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C + C));
+        uint4 r;
+        const __half2 *pa = reinterpret_cast<const __half2*>(&a), *pc = reinterpret_cast<const __half2*>(&c),
+                      *pd = reinterpret_cast<const __half2*>(&d), *pe = reinterpret_cast<const __half2*>(&e);
+        __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pr[q] = __hmax2(__hmax2(pa[q], pc[q]), __hmax2(pd[q], pe[q]));
+        *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + ho) * Wo + wo) * C + g * 8) = r;
+    }
+}
+
+// nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) followed by the zero pad to the skip tensor's size
+// (tmp_utils.py:59-82), NHWC fp16: in [B][h][w][C] -> out [B][H][W][C]; the 2h x 2w upsampled image sits at (py, px).
+// thread = (out pixel, 8 channels); interpolation in fp32 like ATen's opmath, one rounding to fp16.
+__global__ void __launch_bounds__(256) upsample2x_pad_nhwc_kernel(const __half* __restrict__ x, int h, int w, int C, int H, int W, int py,
+                                                                  int px, __half* __restrict__ y) {
+    const int b = blockIdx.y, G = C / 8, uh = 2 * h, uw = 2 * w;
+    const float ry = uh > 1 ? (float)(h - 1) / (float)(uh - 1) : 0.f, rx = uw > 1 ? (float)(w - 1) / (float)(uw - 1) : 0.f;
+    const long long n = (long long)H * W * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G);
+        const long long po = i / G;
+        const int X = (int)(po % W), Y = (int)(po / W);
+        const int uy = Y - py, ux = X - px;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (uy >= 0 && uy < uh && ux >= 0 && ux < uw) {
+            const float sy = ry * uy, sx = rx * ux;
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+            const float ly = sy - y0, lx = sx - x0;
+            const __half* base = x + (size_t)b * h * w * C + g * 8;
+            const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C)), v01 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C));
+            const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C)), v11 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C));
+            const __half *a = reinterpret_cast<const __half*>(&v00), *c = reinterpret_cast<const __half*>(&v01),
+                         *d = reinterpret_cast<const __half*>(&v10), *e = reinterpret_cast<const __half*>(&v11);
+            __half* pr = reinterpret_cast<__half*>(&r);
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                pr[q] = __float2half_rn(w00 * __half2float(a[q]) + w01 * __half2float(c[q]) + w10 * __half2float(d[q]) + w11 * __half2float(e[q]));
+        }
+        *reinterpret_cast<uint4*>(y + (((size_t)b * H + Y) * W + X) * C + g * 8) = r;
+    }
+}
+
+// 1x1 output convolution (unet.py outc): NHWC fp16 [B*HW][Cin] -> NCHW fp32 [B][Cout][HW], Cout <= 16.  8 lanes share a pixel
+// (each loads 16 bytes of its row: a warp reads 4 rows = 512 contiguous bytes when Cin = 64), partial sums meet by shuffles.
 __global__ void __launch_bounds__(256) conv1x1_out_kernel(const __half* __restrict__ x, int Cin, int HW, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int Cout, float* __restrict__ y) {
     extern __shared__ float ws[];   // [Cout][Cin]
     for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
-    const int b = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= HW) return;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + ((size_t)b * HW + p) * Cin);
+    const int b = blockIdx.y, sub = threadIdx.x & 7;
+    const int p = blockIdx.x * 32 + (threadIdx.x >> 3);
     float acc[16];
 #pragma unroll
     for (int o = 0; o < 16; ++o) acc[o] = 0.f;
-    for (int c8 = 0; c8 < Cin / 8; ++c8) {
-        const uint4 raw = __ldg(xr + c8);
-        const __half* hp = reinterpret_cast<const __half*>(&raw);
+    if (p < HW) {
+        const __half* xr = x + ((size_t)b * HW + p) * Cin;
+        for (int c0 = sub * 8; c0 < Cin; c0 += 64) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + c0));
+            const __half* hp = reinterpret_cast<const __half*>(&raw);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float v = __half2float(hp[e]);
+            for (int e = 0; e < 8; ++e) {
+                const float v = __half2float(hp[e]);
 #pragma unroll
-            for (int o = 0; o < 16; ++o) if (o < Cout) acc[o] = fmaf(v, ws[o * Cin + c8 * 8 + e], acc[o]);
+                for (int o = 0; o < 16; ++o) if (o < Cout) acc[o] = fmaf(v, ws[o * Cin + c0 + e], acc[o]);
+            }
         }
     }
 #pragma unroll
-    for (int o = 0; o < 16; ++o) if (o < Cout) y[((size_t)b * Cout + o) * HW + p] = acc[o] + bias[o];
+    for (int o = 0; o < 16; ++o) if (o < Cout) {
+        float v = acc[o];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == (o & 7) && p < HW) y[((size_t)b * Cout + o) * HW + p] = v + bias[o];
+    }
 }
 
 template <int BN>
@@ -231,7 +298,8 @@ extern "C" int nppc_conv3x3_tc(const void* x0, int C0p, const void* x1, int C1p,
 
 extern "C" int nppc_nchw_to_nhwc_f16(const float* x, int B, int C, int H, int W, int Cp, void* y, void* stream) {
     NPPC_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && B <= 65535, "nppc_nchw_to_nhwc_f16: bad arguments");
-    nchw_to_nhwc_f16_kernel<<<dim3(nppc::cdiv((long long)H * W * Cp, 1024), B), 256, 0, (cudaStream_t)stream>>>(x, C, H * W, Cp, (__half*)y);
+    NPPC_CHECK_ARG(Cp % 8 == 0, "nppc_nchw_to_nhwc_f16: Cp must be a multiple of 8");
+    nchw_to_nhwc_f16_kernel<<<dim3(nppc::cdiv((long long)H * W * (Cp / 8), 1024), B), 256, 0, (cudaStream_t)stream>>>(x, C, H * W, Cp, (__half*)y);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;
@@ -240,8 +308,28 @@ extern "C" int nppc_nchw_to_nhwc_f16(const float* x, int B, int C, int H, int W,
 extern "C" int nppc_conv1x1_out(const void* x, int B, int HW, int Cin, const float* w, const float* bias, int Cout, float* y, void* stream) {
     NPPC_CHECK_ARG(x && w && bias && y && B > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 16 && B <= 65535,
                    "nppc_conv1x1_out: bad arguments (Cin %% 8 == 0, Cout <= 16)");
-    conv1x1_out_kernel<<<dim3(nppc::cdiv(HW, 256), B), 256, sizeof(float) * Cout * Cin, (cudaStream_t)stream>>>((const __half*)x, Cin, HW, w, bias,
+    conv1x1_out_kernel<<<dim3(nppc::cdiv(HW, 32), B), 256, sizeof(float) * Cout * Cin, (cudaStream_t)stream>>>((const __half*)x, Cin, HW, w, bias,
                                                                                                               Cout, y);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_maxpool2x2_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+    NPPC_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C % 8 == 0 && B <= 65535, "nppc_maxpool2x2_nhwc: bad arguments");
+    const long long n = (long long)(H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_nhwc_kernel<<<dim3(nppc::cdiv(n, 512), B), 256, 0, (cudaStream_t)stream>>>((const __half*)x, H, W, C, (__half*)y);
+    NPPC_COUNT_LAUNCH(1);
+    NPPC_LAUNCH_OK();
+    return NPPC_OK;
+}
+
+extern "C" int nppc_upsample2x_pad_nhwc(const void* x, int B, int h, int w, int C, int H, int W, void* y, void* stream) {
+    NPPC_CHECK_ARG(x && y && B > 0 && h > 0 && w > 0 && C % 8 == 0 && H >= 2 * h && W >= 2 * w && B <= 65535,
+                   "nppc_upsample2x_pad_nhwc: bad arguments (target must be at least 2h x 2w)");
+    const int dy = H - 2 * h, dx = W - 2 * w;   // tmp_utils.py:76-82: F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    const long long n = (long long)H * W * (C / 8);
+    upsample2x_pad_nhwc_kernel<<<dim3(nppc::cdiv(n, 512), B), 256, 0, (cudaStream_t)stream>>>((const __half*)x, h, w, C, H, W, dy / 2, dx / 2, (__half*)y);
     NPPC_COUNT_LAUNCH(1);
     NPPC_LAUNCH_OK();
     return NPPC_OK;

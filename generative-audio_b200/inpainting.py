@@ -116,8 +116,8 @@ class _Down(nn.Module):
         self.mpconv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(in_ch, out_ch, dropout))
 
     def forward(self, x):
-        if self.mpconv[1].compute_dtype == "tc":   # NHWC fp16: the pooled view is channels-last, i.e. contiguous NHWC again
-            return self.mpconv[1](F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous())
+        if self.mpconv[1].compute_dtype == "tc":   # NHWC fp16 in and out
+            return self.mpconv[1](ops.maxpool2x2_nhwc(x))
         return self.mpconv(x)
 
 
@@ -131,10 +131,7 @@ class _Up(nn.Module):
 
     def forward(self, x1, x2):
         if self.conv.compute_dtype == "tc":   # NHWC fp16 in and out; cat([skip, up]) becomes the conv kernel's two K segments
-            u = self.up(x1.permute(0, 3, 1, 2))
-            dy, dx = x2.size(1) - u.size(2), x2.size(2) - u.size(3)
-            u = F.pad(u, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2)).permute(0, 2, 3, 1).contiguous()
-            return self.conv((x2, u))
+            return self.conv((x2, ops.upsample2x_pad_nhwc(x1, x2.size(1), x2.size(2))))   # upsample + pad in one kernel
         x1 = self.up(x1)
         dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
         x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))

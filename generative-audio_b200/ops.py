@@ -740,6 +740,25 @@ def nchw_to_nhwc_f16(x: torch.Tensor, Cp: int = 64):
     return y
 
 
+def maxpool2x2_nhwc(x: torch.Tensor):
+    _chk(x)
+    B, H, W, C = x.shape
+    assert x.dtype == _F16
+    y = torch.empty(B, H // 2, W // 2, C, device=x.device, dtype=_F16)
+    _lib.check(_lib.load().nppc_maxpool2x2_nhwc(x.data_ptr(), B, H, W, C, y.data_ptr(), _stream()), "nppc_maxpool2x2_nhwc")
+    return y
+
+
+def upsample2x_pad_nhwc(x: torch.Tensor, H: int, W: int):
+    """bilinear x2 (align_corners=True) of x [B,h,w,C] fp16, zero-padded (centred like tmp_utils.py:76-82) to [B,H,W,C]."""
+    _chk(x)
+    B, h, w, C = x.shape
+    assert x.dtype == _F16
+    y = torch.empty(B, H, W, C, device=x.device, dtype=_F16)
+    _lib.check(_lib.load().nppc_upsample2x_pad_nhwc(x.data_ptr(), B, h, w, C, H, W, y.data_ptr(), _stream()), "nppc_upsample2x_pad_nhwc")
+    return y
+
+
 def conv1x1_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
     """unet outc: x [B,H,W,Cin] fp16 NHWC, w [Cout,Cin(,1,1)] fp32 -> [B,Cout,H,W] fp32."""
     w, bias = _f32(w.reshape(w.shape[0], -1)), _f32(bias)

@@ -267,6 +267,10 @@ int nppc_conv3x3_tc(const void* x0, int C0p, const void* x1, int C1p, const void
                     int H, int W, int Cout, float negative_slope, void* stream);
 int nppc_nchw_to_nhwc_f16(const float* x, int B, int C, int H, int W, int Cp, void* y, void* stream);
 int nppc_conv1x1_out(const void* x, int B, int HW, int Cin, const float* w, const float* bias, int Cout, float* y, void* stream);
+/* nn.MaxPool2d(2) (tmp_utils.py:45) and nn.Upsample(x2, bilinear, align_corners=True) + the zero pad to the skip tensor's
+ * H x W (tmp_utils.py:59-82) on NHWC fp16: [B,H,W,C] -> [B,H/2,W/2,C];  [B,h,w,C] -> [B,H,W,C]. */
+int nppc_maxpool2x2_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream);
+int nppc_upsample2x_pad_nhwc(const void* x, int B, int h, int w, int C, int H, int W, void* y, void* stream);
 
 /* ---- a8/a11 output assembly -----------------------------------------------------------------------
  * y [B*F', O, T'] -> out [B, O, F', T'-la] dropping the first `look_ahead` frames

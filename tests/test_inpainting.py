@@ -198,3 +198,21 @@ def test_inpainting_unet_on_tcgen05_matches_fp32_path():
     assert "conv3x3_tc_kernel" in names
     lib = " ".join(n for n in names.split() if "nppc" not in n and "anonymous" not in n).lower()
     assert "cudnn" not in lib and "implicit_convolve" not in lib and "conv2d" not in lib
+
+
+@pytest.mark.gpu
+def test_nhwc_pool_and_upsample_kernels_vs_torch():
+    """The NHWC fp16 glue of the tcgen05 UNet path: MaxPool2d(2) (bit-exact) and bilinear x2 (align_corners=True) + the pad to
+    the skip tensor's size (tmp_utils.py:59-82), incl. odd sizes (125 -> 62 columns, 62 -> 124 padded to 125)."""
+    import generative_audio_b200 as g
+    F = torch.nn.functional
+    x = torch.randn(2, 64, 33, 125, generator=torch.Generator().manual_seed(3)).cuda().half()
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    p = g.ops.maxpool2x2_nhwc(xh)
+    assert torch.equal(p.permute(0, 3, 1, 2), F.max_pool2d(x, 2))
+    small = x[:, :, :16, :62].contiguous()
+    u = g.ops.upsample2x_pad_nhwc(small.permute(0, 2, 3, 1).contiguous(), 33, 125)
+    ref = F.interpolate(small.float(), scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = 33 - ref.size(2), 125 - ref.size(3)
+    ref = F.pad(ref, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    assert rel_err(u.float().permute(0, 3, 1, 2).cpu(), ref.cpu()) < 1e-3
