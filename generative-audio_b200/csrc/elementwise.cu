@@ -9,23 +9,21 @@ constexpr int TPB = 256;
 
 __device__ __forceinline__ float decompress1(float m) {
     // mask.py:57-60: limit*(m>=limit) - limit*(m<=-limit) + m*(|m|<limit); -K*log((K-m)/(K+m)), K=10, limit=9.9
-    // = 2K atanh(c / K).  |c| <= 3: odd series 2K t (1 + t^2/3 + ... + t^14/15), t = c/K (truncation < 1e-9 relative; the
+    // = 2K atanh(c / K).  |c| <= 3: odd series 2K t (1 + t^2/3 + ... + t^10/11), t = c/K (truncation < 5e-8 relative; the
     // reference's own fp32 log of a ratio near 1 is only ~3e-5 relative there, and these small masks are what the PC head's
     // cancelling-mean normalisers amplify — speech fixtures).  |c| > 3: K ln2 (lg2(K + c) - lg2(K - c)) on two MUFU.LG2
     // (absolute error ~3e-6 on values >= 6.2); the libm logf + division this replaced made the kernel instruction-bound.
     float c = (m >= 9.9f) ? 9.9f : ((m <= -9.9f) ? -9.9f : m);
-    if (fabsf(c) <= 3.0f) {
-        const float t = c * 0.1f, u = t * t;
-        float p = fmaf(u, 1.0f / 15.0f, 1.0f / 13.0f);
-        p = fmaf(u, p, 1.0f / 11.0f);
-        p = fmaf(u, p, 1.0f / 9.0f);
-        p = fmaf(u, p, 1.0f / 7.0f);
-        p = fmaf(u, p, 1.0f / 5.0f);
-        p = fmaf(u, p, 1.0f / 3.0f);
-        p = fmaf(u, p, 1.0f);
-        return 20.0f * t * p;
-    }
-    return 6.931471805599453f * (__log2f(10.0f + c) - __log2f(10.0f - c));
+    // branch-free: both forms are a handful of instructions; the series wins for |c| <= 3 (t <= 0.3: truncation t^12/13 < 5e-8)
+    const float t = c * 0.1f, u = t * t;
+    float p = fmaf(u, 1.0f / 11.0f, 1.0f / 9.0f);
+    p = fmaf(u, p, 1.0f / 7.0f);
+    p = fmaf(u, p, 1.0f / 5.0f);
+    p = fmaf(u, p, 1.0f / 3.0f);
+    p = fmaf(u, p, 1.0f);
+    const float ys = 20.0f * t * p;
+    const float yl = 6.931471805599453f * (__log2f(10.0f + c) - __log2f(10.0f - c));
+    return fabsf(c) <= 3.0f ? ys : yl;
 }
 
 __device__ __forceinline__ float compress1(float m) {
