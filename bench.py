@@ -207,7 +207,11 @@ def train_bench(args, rank, world, local_rank, dev, G, build_model, wave, ClockS
     model, _ = build_model(N_DIRS, 2, "tc")
     stepper = G.NPPCAudioStep(model, 500, 1.0)
     stepper.step = 600
-    graphed = os.environ.get("NPPC_TRAIN_GRAPH", "1") != "0"     # whole step as ONE CUDA graph replay (trainer.train_step_graphed)
+    # whole step as ONE CUDA graph replay (trainer.train_step_graphed).  Default: on for one GPU; with N > 1 the step stays eager
+    # unless NPPC_TRAIN_GRAPH=1: the graph with the NCCL bucket all-reduces captured inside it was measured at N = 2
+    # (profiles/r02_bench_train_n2.json, 99.8 ms/step vs 97.9 at N = 1) but an N = 4 run did not finish inside its time limit and
+    # could not be diagnosed before the round's GPU budget ran out, so it is opt-in there.
+    graphed = os.environ.get("NPPC_TRAIN_GRAPH", "1" if world == 1 else "0") != "0"
     opt = torch.optim.Adam(model.audio_pc_wrapper.parameters(), lr=1e-5, capturable=graphed)
     do_step = stepper.train_step_graphed if graphed else stepper.train_step
     clean_h = wave(B, L, 3000 + rank, 0.03).pin_memory()
