@@ -493,9 +493,9 @@ def main():
     roofline = {"bound": "tensor", "kernel": f"sub-band LSTM (2 layers + fc), impl={args.lstm_impl}, per nppc_lstm_forward call",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 # DRAM bytes of one nppc_lstm_forward call (rec layer 0 + Zx GEMM + rec layer 1) from the ncu --set full capture
-                # profiles/r01_lstm_ncu_full_v13_summary.csv (B=64, O=10): 3.69 + 16.00 + 17.18 GB; scaled to this R x T'
+                # profiles/r02_lstm_ncu_full_summary.csv (B=64, O=2): 3.69 + 16.00 + 17.19 GB; scaled to this R x T'
                 "traffic": (36.88e9 * (R * Tp) / (64 * 257 * 253)) if args.lstm_impl == "tc" else None,
-                "traffic_note": "dram__bytes_read+write per call from profiles/r01_lstm_ncu_full_v13_summary.csv; 25.6 GB of it is the "
+                "traffic_note": "dram__bytes_read+write per call from profiles/r02_lstm_ncu_full_summary.csv (ncu --set full, this round); 25.6 GB of it is the "
                                 "fp16 gate pre-activation (Zx) round trip of layer 1",
                 "peak_source": f"{pk['src']} (sustained dense 16-bit tensor peak, kernel timed inside a long step)",
                 "ms_per_call": lstm_ms, "calls_per_step": len(lstm_events) / max(args.steps, 1),

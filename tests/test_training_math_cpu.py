@@ -1,0 +1,113 @@
+"""CPU checks of the hand-written training step's HOST-side mathematics (no GPU needed):
+  * gs_backward.gs_loss_grad_coeffs — backward of Gram-Schmidt (conjugated coefficient, detached normaliser: pc_wrapper.py:8-44)
+    + the NPPC objective (trainer.py:259-298,337-342, detached projection) in coefficient space — against torch.autograd of a
+    literal restatement of the reference formulas;
+  * training._dropband_maps — the row <-> (sample, frequency) permutation of drop_band (feature.py:254-285) against the oracle;
+  * training._tsse_gate — the convolution-free TSSE squeeze (windowed sums) against the oracle's depthwise-conv restatement;
+  * bench.py --impl reference — honours --steps / --warmup, prints our arm's config and says which sample it ran."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import nppc_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gs_ref(x):
+    n = x.shape[1]
+    v = torch.complex(x[:, :, 0], x[:, :, 1])
+    outs, hats = [], []
+    for i in range(n):
+        w = v[:, i]
+        for wh in hats:
+            w = w - wh * (w.conj() * wh).sum(dim=1, keepdim=True)
+        wd = w.detach()
+        hats.append(wd / torch.linalg.vector_norm(wd, dim=1, keepdim=True))
+        outs.append(w)
+    out = torch.stack(outs, 1)
+    return torch.stack([out.real, out.imag], 2)
+
+
+def _loss_ref(w, gt, pred, lam):
+    B, n = w.shape[:2]
+    W = w.reshape(B, n, 2, -1)
+    wn = torch.linalg.vector_norm(W, dim=(2, 3))
+    wh = W / (wn[..., None, None] + 1e-8)
+    err = (gt - pred).reshape(B, 2, -1)
+    en = torch.linalg.vector_norm(err, dim=(1, 2))
+    err = err / (en[:, None, None] + 1e-8)
+    wn = wn / (en[:, None] + 1e-8)
+    ep = (torch.complex(wh[:, :, 0], wh[:, :, 1]).conj() * torch.complex(err[:, 0], err[:, 1])[:, None]).sum(-1)
+    mag = ep.abs()
+    return (1 - mag.pow(2).sum(1)).mean() + lam * (wn.pow(2) - mag.detach().pow(2)).pow(2).mean()
+
+
+@pytest.mark.parametrize("B,n,P,lam", [(3, 5, 200, 0.37), (1, 1, 50, 1.0), (2, 10, 64, 1e-6)])
+def test_gs_loss_backward_in_coefficient_space_matches_autograd(B, n, P, lam):
+    from generative_audio_b200.gs_backward import gs_loss_grad_coeffs
+    g = torch.Generator().manual_seed(B * 100 + n)
+    x = torch.randn(B, n, 2, P, dtype=torch.float64, generator=g)
+    if n > 2:
+        x[:, 2] = 0.6 * x[:, 0] + 0.4 * x[:, 2]            # correlated directions: the projections matter
+    gt = torch.randn(B, 2, P, dtype=torch.float64, generator=g)
+    pred = torch.randn(B, 2, P, dtype=torch.float64, generator=g)
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_(True)
+        _loss_ref(_gs_ref(xr), gt, pred, lam).backward()
+    xc = torch.complex(x[:, :, 0], x[:, :, 1])
+    e = torch.complex((gt - pred)[:, 0], (gt - pred)[:, 1])
+    V = torch.cat([xc, e[:, None]], 1)
+    G = torch.einsum("bjp,bkp->bjk", V.conj(), V)                                   # what the forward kernel's scratch holds
+    with torch.no_grad():
+        w = _gs_ref(x)
+    wc = torch.complex(w[:, :, 0], w[:, :, 1])
+    A = torch.linalg.lstsq(xc.transpose(1, 2), wc.transpose(1, 2)).solution.transpose(1, 2)   # w_i = sum_k A_ik x_k
+    coef = gs_loss_grad_coeffs(G, A, lam)
+    d = torch.einsum("bik,bkp->bip", coef, V)                                       # what nppc_complex_lincomb streams out
+    got = torch.stack([d.real, d.imag], 2)
+    assert ((got - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-9
+    # a device-scalar lambda and an upstream gradient scale go through unchanged
+    coef2 = gs_loss_grad_coeffs(G, A, torch.tensor(lam, dtype=torch.float64), grad_scale=torch.tensor(2.0, dtype=torch.float64))
+    assert torch.allclose(coef2, 2 * coef)
+
+
+@pytest.mark.parametrize("B,Fq,G", [(4, 257, 2), (5, 11, 3), (3, 8, 1), (1, 9, 2)])
+def test_dropband_row_maps_match_reference_order(B, Fq, G):
+    from generative_audio_b200.training import _dropband_maps
+    x = (torch.arange(B)[:, None] * 1000 + torch.arange(Fq)[None, :]).float()[:, None, :, None]    # [B,1,F,1]: value = 1000 b + f
+    ref = O.drop_band(x, G) if B > 1 else x
+    Ge = G if (G > 1 and B > 1) else 1
+    sb, f, Fg = _dropband_maps(B, Fq, Ge, "cpu")
+    assert Fg == ref.shape[2] and sb.numel() == ref.shape[0] * Fg
+    assert torch.equal((sb * 1000 + f).float(), ref[:, 0, :, 0].reshape(-1))
+    assert len({(int(a), int(b)) for a, b in zip(sb, f)}) == sb.numel()     # unique pairs: the backward scatter needs no atomics
+
+
+def test_tsse_gate_without_convolutions_matches_oracle():
+    import generative_audio_b200 as G
+    import weights
+    from generative_audio_b200.training import _tsse_gate
+    sd = weights.synth_state_dict(5, 0, "audio_pc_wrapper.net.")
+    att = G.modules.ChannelTimeSenseSELayer(257)
+    att.load_state_dict({k[len("channel_attention."):]: v for k, v in sd.items() if k.startswith("channel_attention.")})
+    x = torch.randn(2, 257, 40, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        got = x * _tsse_gate(att, x)[:, :, None]
+        ref = O.tsse(x, sd, "channel_attention")
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_reference_arm_reports_what_it_ran():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0", "--cpu-batch", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 0          # K and W honoured, not clamped
+    assert line["config"]["batch_per_gpu"] == 64                                               # our arm's config ...
+    assert line["sample"]["batch_per_step"] == 1 and line["sample"]["of_batch"] == 64           # ... and the sample that actually ran
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
