@@ -40,6 +40,13 @@ class FullSubNet_Plus(nn.Module):
             raise NotImplementedError("only subband_num=1, TSSE attention, fb_num_neighbors=0 (every shipped config) are built")
         if self.norm_type not in ("offline_laplace_norm", "cumulative_laplace_norm"):
             raise NotImplementedError(f"norm_type {self.norm_type}")
+        # configuration fields the reference honours and this build does not: refuse them loudly instead of diverging silently
+        if config.fb_output_activate_function != "ReLU":
+            raise NotImplementedError("only fb_output_activate_function='ReLU' (every shipped config) is built, got "
+                                      f"{config.fb_output_activate_function!r}")
+        if config.weight_init:
+            raise NotImplementedError("weight_init=True (fullsubnet_plus.py:140-141 re-initialises the weights) is not built: "
+                                      "load a state_dict instead")
         if 2 * self.sb_num_neighbors + 4 > KP:
             raise NotImplementedError("sb_num_neighbors too large for the packed LSTM input")
         C = self.num_freqs

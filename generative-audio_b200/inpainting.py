@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .modules import _NoDerivedState
 
 
 class UNetConfig(pydantic.BaseModel):
@@ -38,7 +39,7 @@ def _double_conv(in_ch, out_ch, dropout=0.0):
     return nn.Sequential(*layers)
 
 
-class _DoubleConv(nn.Module):
+class _DoubleConv(_NoDerivedState, nn.Module):
     def __init__(self, in_ch, out_ch, dropout=0.0):
         super().__init__()
         self.conv = _double_conv(in_ch, out_ch, dropout)

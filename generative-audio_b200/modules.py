@@ -13,6 +13,29 @@ from . import ops
 
 TCN_DILATIONS = (1, 2, 5, 9, 1, 2, 5, 9)  # sequence_model.py:48-57
 
+# attributes that hold DERIVED caches (a ctypes LSTM plan handle, packed / folded / split 16-bit weights): rebuilt on demand from
+# the fp32 master parameters, so copy.deepcopy(model), pickling and torch.save(model) drop them instead of choking on a ctypes
+# pointer or carrying stale device buffers into the copy
+_DERIVED = ("_plan", "_plan_key", "_tplan", "_tplan_key", "_fold", "_fold_key", "_fold16", "_fold16_key", "_tc", "_tc_key")
+
+
+class _NoDerivedState:
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in _DERIVED:
+            if k in st:
+                st[k] = None
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            setattr_ = object.__setattr__
+            setattr_(new, k, copy.deepcopy(v, memo))
+        return new
+
 
 def _conv1x1_f32(w, x):
     """1x1 Conv1d of the fp32 path as a TRUE fp32 GEMM: w [O,C,1], x [B,C,T] -> [B,O,T].  F.conv1d goes through cuDNN, whose
@@ -52,7 +75,7 @@ class ChannelTimeSenseSELayer(nn.Module):
                         self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
 
 
-class TCNBlock(nn.Module):
+class TCNBlock(_NoDerivedState, nn.Module):
     """causal_conv.py:67-108 (use_skip_connection=True, causal=False)."""
 
     def __init__(self, in_channels=257, hidden_channel=512, out_channels=257, kernel_size=3, dilation=1):
@@ -99,7 +122,7 @@ class TCNBlock(nn.Module):
         return ops.tcn_out(o, x, z.shape[1], stats2, u, vb)
 
 
-class SequenceModel(nn.Module):
+class SequenceModel(_NoDerivedState, nn.Module):
     """sequence_model.py:5-123.  "TCN": runnable module.  "LSTM": parameter container whose forward goes through
     the hand-written kernels (input must already be packed time-major by ops.subband_pack)."""
 

@@ -72,3 +72,35 @@ def test_loss_lambda_schedule():
     for step in (0, 100, 250, 251, 400, 500, 600):
         assert g.second_moment_lambda(step, 500, 1.0) == O.second_moment_lambda(step, 500, 1.0)
     assert g.second_moment_lambda(0, 500, 1.0) == 1e-6 and g.second_moment_lambda(600, 500, 0.5) == 0.5
+
+
+def test_derived_caches_are_not_copied_or_pickled_and_unsupported_configs_raise():
+    """a SequenceModel / TCNBlock / UNet block that has already run holds derived caches (a ctypes LSTM-plan handle,
+    packed / folded 16-bit weights); copy.deepcopy / torch.save must drop them, and configuration fields this build does not
+    implement must raise instead of silently diverging from the reference."""
+    import copy
+    import ctypes
+    import io
+
+    import torch
+
+    import generative_audio_b200 as g
+    m = g.modules.SequenceModel(34, 2, 384, 2, False, "LSTM", False)
+    m._plan, m._plan_key = ctypes.c_void_p(1234), ("key",)
+    m2 = copy.deepcopy(m)
+    assert m2._plan is None and m2._plan_key is None and m._plan is not None
+    assert torch.equal(m2.fc_output_layer.weight, m.fc_output_layer.weight) and m2.fc_output_layer.weight is not m.fc_output_layer.weight
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    assert torch.load(buf, weights_only=False)._plan is None
+    t = g.modules.SequenceModel(257, 257, 512, 2, False, "TCN", "ReLU")
+    t._tplan, t.sequence_model[0]._fold = {"stale": 1}, ("stale",)
+    t2 = copy.deepcopy(t)
+    assert t2._tplan is None and t2.sequence_model[0]._fold is None
+    u = g.inpainting.UNet(g.inpainting.UNetConfig())
+    u.inc.conv._tc = ("stale",)
+    assert copy.deepcopy(u).inc.conv._tc is None
+    for bad in (dict(weight_init=True), dict(fb_output_activate_function="Tanh")):
+        with pytest.raises(NotImplementedError):
+            g.FullSubNet_Plus(g.FullSubNetPlusConfig(**bad))
