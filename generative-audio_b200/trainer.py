@@ -130,9 +130,10 @@ class NPPCAudioStep:
         model = self.nppc_model
         noisy, clean = batch
         G = model.audio_pc_wrapper.net.num_groups_in_drop_band
-        head, pred_crm = model.forward_stages(noisy)
+        taps = {}
+        head, pred_crm = model.forward_stages(noisy, taps)
         c = model.config.stft_configuration
-        _, nr, ni = ops.stft_mri(noisy.to(model.device), c.nfft, c.hop_length, c.win_length)
+        nr, ni = taps["real"], taps["imag"]          # the noisy STFT forward_stages already computed (one STFT, not two)
         _, cr, ci = ops.stft_mri(clean.to(model.device), c.nfft, c.hop_length, c.win_length)
         gt = ops.drop_band(ops.build_cirm(nr[:, 0], ni[:, 0], cr[:, 0], ci[:, 0]), G)
         pred = ops.drop_band(pred_crm, G)

@@ -111,3 +111,15 @@ def test_reference_arm_reports_what_it_ran():
     assert line["config"]["batch_per_gpu"] == 64                                               # our arm's config ...
     assert line["sample"]["batch_per_step"] == 1 and line["sample"]["of_batch"] == 64           # ... and the sample that actually ran
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def test_training_path_refuses_configurations_it_does_not_differentiate():
+    """the differentiable head must not silently optimise a different network than inference evaluates — a
+    norm_type it has no backward for raises before any kernel runs."""
+    import types
+
+    from generative_audio_b200 import training
+    net = types.SimpleNamespace(norm_type="cumulative_laplace_norm", look_ahead=2)
+    x = torch.zeros(2, 1, 257, 5)
+    with pytest.raises(NotImplementedError, match="offline_laplace_norm"):
+        training.head_forward_train(net, x, x, x, x, x, x)
