@@ -36,6 +36,15 @@ def test_argument_errors_without_gpu():
     assert lib.nppc_drop_band(1, 2, 3, 257, 7, 2, 1, None) == -1   # B must be > groups (feature.py:263)
     assert b"The batch size should larger than the num_groups" in lib.nppc_last_error()
     assert lib.nppc_gs_scratch_bytes(4, 5) > 0
+    # round-2 entry points: shapes are validated before any CUDA call
+    assert lib.nppc_gemm_f16_atb(1, 1, 100, 128, 64, 1, 1, 1, None) == -1 and b"rows % 64" in lib.nppc_last_error()
+    assert lib.nppc_gemm_f16_tn_ex(16, 16, None, 16, 128, 128, 128, 192, 0, None) == -1 and b"KA" in lib.nppc_last_error()   # KA > K
+    assert lib.nppc_conv3x3_tc(1, 48, None, 0, 1, 1, 1, 1, 8, 8, 64, 0.2, None) == -1 and b"multiples of 64" in lib.nppc_last_error()
+    assert lib.nppc_conv1x1_out(1, 1, 10, 64, 1, 1, 17, 1, None) == -1
+    assert lib.nppc_upsample2x_pad_nhwc(1, 1, 8, 8, 64, 15, 16, 1, None) == -1 and b"2h x 2w" in lib.nppc_last_error()
+    assert lib.nppc_cancel_depth(None, 1, 10, 10.0, None, None, None) == -1
+    assert lib.nppc_lstm_step_forward(None, None, 0, 1, 128, 1, 64, 0, 0, None, 0, None, None) == -1
+    assert lib.nppc_lstm_step_workspace_bytes(34, 384, 10, 4096, 253, 64, 1, 0) > lib.nppc_lstm_step_workspace_bytes(34, 384, 10, 4096, 253, 64, 0, 0) > 0
 
 
 def test_state_dict_contract():
