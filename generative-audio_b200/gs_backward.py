@@ -14,13 +14,18 @@ Derivation (delta = 1e-8, <u, v>_R = Re u^H v):  with nu_k = |w_k|, eps = |e|, q
         alpha_k = -(1/B) 2 conj(q_k) / ((nu_k + delta)^2 (eps + delta)^2)
         beta_k  =  (1/B) 2 |q_k|^2 / ((nu_k + delta)^3 nu_k (eps + delta)^2) + (lambda / (B n)) 4 (nu'_k^2 - pi_k^2) / (eps + delta)^2
 Gram-Schmidt with constant (detached) a_j = w_j / |w_j|:  w_i = M_{i-1} .. M_0 x_i,  M_j v = v - a_j conj(a_j^H v).  M_j is
-symmetric for <.,.>_R, so d/dx_i = M_0 M_1 .. M_{i-1} (d/dw_i)."""
+symmetric for <.,.>_R, so d/dx_i = M_0 M_1 .. M_{i-1} (d/dw_i).
+
+Real variant (`real=True`: the inpainting head, inpainting/nppc/pc_wrapper.py:43-59 + trainer/nppc_trainer.py:338-385): the same
+algebra on real numbers with delta = 1e-6 added to BOTH norms before any division, i.e. nu'_k = (nu_k + delta) / (eps + delta),
+which changes the second-moment term of beta_k to (lambda / (B n)) 4 (nu'_k^2 - pi_k^2) (nu_k + delta) / (nu_k (eps + delta)^2)."""
 import torch
 
 
-def gs_loss_grad_coeffs(G: torch.Tensor, A: torch.Tensor, lam: float, grad_scale=1.0) -> torch.Tensor:
+def gs_loss_grad_coeffs(G: torch.Tensor, A: torch.Tensor, lam: float, grad_scale=1.0, real: bool = False) -> torch.Tensor:
     """G [B, n+1, n+1] complex (G[j,k] = v_j^H v_k over the vectors x_0..x_{n-1}, e);  A [B, n, n] complex (w_i = sum_k A_ik x_k)
-    -> C [B, n, n+1] complex with d objective / d x_i = sum_k C[i,k] v_k  (times grad_scale, the incoming d/d objective)."""
+    -> C [B, n, n+1] complex with d objective / d x_i = sum_k C[i,k] v_k  (times grad_scale, the incoming d/d objective).
+    real=True: G, A (and C) real, the inpainting trainer's epsilon placement (module docstring)."""
     B, n1, _ = G.shape
     n = n1 - 1
     cd = G.dtype
@@ -32,12 +37,17 @@ def gs_loss_grad_coeffs(G: torch.Tensor, A: torch.Tensor, lam: float, grad_scale
     eps = G[:, n, n].real.clamp_min(0).sqrt()
     q = GW[:, :, n].conj()                                    # conj(e^H w_k)... = w_k^H e
     q = torch.einsum("bjm,bm->bj", Wc.conj(), G[:, :, n])     # w_k^H e, explicit
-    d = 1e-8
+    d = 1e-6 if real else 1e-8
     e2 = (eps + d) ** 2
     pi2 = (q.abs() ** 2) / ((nu + d) ** 2 * e2[:, None])
-    nup2 = nu2 / e2[:, None]
     alpha = -(1.0 / B) * 2 * q.conj() / ((nu + d) ** 2 * e2[:, None])
-    beta = (1.0 / B) * 2 * (q.abs() ** 2) / ((nu + d) ** 3 * nu * e2[:, None]) + (lam / (B * n)) * 4 * (nup2 - pi2) / e2[:, None]
+    if real:
+        nup2 = (nu + d) ** 2 / e2[:, None]
+        sm = (lam / (B * n)) * 4 * (nup2 - pi2) * (nu + d) / (nu * e2[:, None])
+    else:
+        nup2 = nu2 / e2[:, None]
+        sm = (lam / (B * n)) * 4 * (nup2 - pi2) / e2[:, None]
+    beta = (1.0 / B) * 2 * (q.abs() ** 2) / ((nu + d) ** 3 * nu * e2[:, None]) + sm
     a = Wc / nu[:, :, None].to(cd)                            # detached normalised directions (no epsilon, pc_wrapper.py:37)
     Ga = torch.einsum("bmk,bjk->bjm", G, a)                   # (G a_j)[m];  a_j^H v = sum_m conj((G a_j)[m]) ... see below
     out = torch.zeros(B, n, n1, dtype=cd, device=G.device)

@@ -8,10 +8,13 @@
     InpaintingNPPCStep.base_step         nppc_audio/inpainting/trainer/nppc_trainer.py:338-385 (forward statistics)
 
 Same module tree / state_dict keys as the reference (`inc.conv.conv.0.weight`, `down1.mpconv.1.conv.4.running_var`, ...),
-so reference checkpoints (`{"model_state_dict": ...}`) load with strict=True.  CUDA only, inference (eval-mode BatchNorm,
-dropout off).  The 3x3 convolutions run on the library (cuDNN) — SURVEY.md §8f row N4 — with BatchNorm folded into their
-weights; everything around them is hand-written: log-magnitude normalisation, mask blending, the real Gram-Schmidt and
-the projection / second-moment loss (two HBM passes, csrc/gram_schmidt.cu)."""
+so reference checkpoints (`{"model_state_dict": ...}`) load with strict=True.  CUDA only.  Eval mode (inference, the frozen
+restoration UNet): BatchNorm folded into the convolution weights, dropout off, 3x3 convolutions on the library (fp32 parity
+path) or on the in-house tcgen05 implicit GEMM (set_compute_dtype(model, "tc"), row N4); everything around them is
+hand-written: log-magnitude normalisation, mask blending, the real Gram-Schmidt and the projection / second-moment loss (two
+HBM passes, csrc/gram_schmidt.cu).  Train mode (the PC head during InpaintingNPPCStep.train_step): the module tree as written
+(BatchNorm batch statistics, dropout) through torch autograd, with the masking, Gram-Schmidt and objective — forward and
+backward — on the kernels (inpainting_training.py)."""
 from pathlib import Path
 from typing import Literal, Optional
 
@@ -84,7 +87,12 @@ class _DoubleConv(_NoDerivedState, nn.Module):
             y = F.dropout(y, self.conv[6].p, training=True)
         return y
 
+    def _tc(self):
+        return self.compute_dtype == "tc" and not self.training
+
     def forward(self, x):
+        if self.training:   # BatchNorm batch statistics (+ running-stat update) and dropout as written: autograd over the library
+            return self.conv(x)
         if self.compute_dtype == "tc":
             return self.forward_tc(*x) if isinstance(x, tuple) else self.forward_tc(x)
         (w0, b0), (w1, b1) = self._folded()
@@ -117,7 +125,7 @@ class _Down(nn.Module):
         self.mpconv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(in_ch, out_ch, dropout))
 
     def forward(self, x):
-        if self.mpconv[1].compute_dtype == "tc":   # NHWC fp16 in and out
+        if self.mpconv[1]._tc():   # NHWC fp16 in and out
             return self.mpconv[1](ops.maxpool2x2_nhwc(x))
         return self.mpconv(x)
 
@@ -131,7 +139,7 @@ class _Up(nn.Module):
         self.conv = _DoubleConv(in_ch, out_ch, dropout)
 
     def forward(self, x1, x2):
-        if self.conv.compute_dtype == "tc":   # NHWC fp16 in and out; cat([skip, up]) becomes the conv kernel's two K segments
+        if self.conv._tc():   # NHWC fp16 in and out; cat([skip, up]) becomes the conv kernel's two K segments
             return self.conv((x2, ops.upsample2x_pad_nhwc(x1, x2.size(1), x2.size(2))))   # upsample + pad in one kernel
         x1 = self.up(x1)
         dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
@@ -169,9 +177,10 @@ class UNet(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("generative_audio_b200.inpainting.UNet: CUDA tensors only (no CPU fallback)")
-        if self.training:
-            raise RuntimeError("inference only: call .eval() (BatchNorm is folded into the convolutions, dropout is off)")
-        tc = self.inc.conv.compute_dtype == "tc"
+        return self._forward(x)
+
+    def _forward(self, x):
+        tc = self.inc.conv._tc()   # train mode always takes the fp32 NCHW autograd path
         if tc:
             x = ops.nchw_to_nhwc_f16(x, 64)
         x1 = self.inc(x)
@@ -276,16 +285,58 @@ def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
 
 
 class InpaintingNPPCStep:
-    """Forward statistics of the inpainting NPPC trainer's base_step (nppc_trainer.py:338-385): one restoration pass is
-    shared by the PC head and the error (the reference runs it twice), Gram-Schmidt and the loss statistics are fused."""
+    """The inpainting NPPC trainer's base_step (nppc_trainer.py:338-385) and the body of its train() loop (:146-154): one
+    restoration pass is shared by the PC head and the error (the reference runs it twice), Gram-Schmidt and the loss statistics
+    are fused.  base_step(batch) is the no-grad statistics path (every op a kernel; the head in whatever mode it is in);
+    base_step(batch, requires_grad=True) / train_step build the autograd graph of inpainting_training.py."""
 
-    def __init__(self, nppc_model: NPPCModel, second_moment_loss_lambda: float = 1.0, second_moment_loss_grace: float = 500.0):
+    def __init__(self, nppc_model: NPPCModel, second_moment_loss_lambda: float = 1.0, second_moment_loss_grace: float = 500.0,
+                 max_grad_norm: float = 1.0):
         self.nppc_model = nppc_model
         self.lambda0, self.grace = second_moment_loss_lambda, second_moment_loss_grace
+        self.max_grad_norm = max_grad_norm      # NPPCAudioInpaintingTrainerConfig.max_grad_norm (nppc_trainer.py:39)
         self.step = 0
 
-    @torch.no_grad()
-    def base_step(self, batch):
+    def base_step(self, batch, requires_grad: bool = False):
+        """batch = (masked_spec [B,2,F,T], mask [B,T], clean_spec [B,2,F,T]) -> (reconst_err [B], objective [], log dict)."""
+        if requires_grad:
+            return self._base_step_autograd(batch)
+        with torch.no_grad():
+            return self._base_step_kernels(batch)
+
+    def _base_step_autograd(self, batch):
+        from . import inpainting_training as IT
+        masked_spec, mask, clean_spec = batch
+        model = self.nppc_model
+        with torch.no_grad():
+            clean, m, masked = preprocess_data(clean_spec.cuda(), masked_spec.cuda(), mask.cuda())
+            pred = model.get_pred_spec_mag_norm(masked, m)
+            x = torch.cat((masked, pred), dim=1)
+        lam = second_moment_lambda(self.step, self.grace, self.lambda0)
+        with torch.enable_grad():
+            head = IT.head_forward_train(model.pc_wrapper, x, m)
+            objective, w_mat, err_norm, err_proj, w_norms, reconst_err, second_moment = IT.GsLossRealFn.apply(head, clean, pred, lam)
+        log = dict(w_mat=w_mat, err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst_err,
+                   second_moment_mse=second_moment, objective=objective.detach())
+        return reconst_err, objective, log
+
+    def train_step(self, batch, optimizer):
+        """One iteration of NPPCAudioInpaintingTrainer.train (nppc_trainer.py:146-154, :184): the PC head in train mode, the
+        restoration UNet frozen in eval mode; zero_grad -> backward -> clip_grad_norm_(max_grad_norm) -> optimizer.step.
+        Returns (objective, log); log["grad_norm"] is the pre-clip global norm (a device scalar: no host sync in the step)."""
+        from . import inpainting_training as IT
+        model = self.nppc_model
+        model.pc_wrapper.train()
+        model.pretrained_restoration_model.eval()
+        _, objective, log = self.base_step(batch, requires_grad=True)
+        optimizer.zero_grad(set_to_none=True)
+        objective.backward()
+        log["grad_norm"] = IT.clip_grad_norm_(list(model.parameters()), self.max_grad_norm)
+        optimizer.step()
+        self.step += 1
+        return objective.detach(), log
+
+    def _base_step_kernels(self, batch):
         masked_spec, mask, clean_spec = batch
         clean, m, masked = preprocess_data(clean_spec.cuda(), masked_spec.cuda(), mask.cuda())
         pred = self.nppc_model.get_pred_spec_mag_norm(masked, m)

@@ -301,6 +301,47 @@ def gs_loss_fused_real(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor)
     return w, dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm)
 
 
+def gs_loss_fused_real_with_gram(head: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
+    """gs_loss_fused_real that also returns what the backward needs from the forward's scratch: the symmetric Gram matrix
+    G [B, n+1, n+1] float64 of (x_0 .. x_{n-1}, gt - pred) and the coefficient matrix A [B, n, n] float32 (w = A x).
+    The real kernels use the .re slots of the same SampleScratch the complex ones fill (gram_schmidt.cu)."""
+    head, gt, pred = _f32(head), _f32(gt), _f32(pred)
+    _chk(head, gt, pred)
+    B, n = head.shape[:2]
+    P = head[0, 0].numel()
+    assert gt.shape == pred.shape and gt[0].numel() == P
+    w = torch.empty_like(head)
+    err_norm, err_proj, w_norms, reconst, sm = _loss_outputs_real(B, n, head.device)
+    scr = _gs_scratch(B, n, head.device)
+    assert scr.numel() >= B * GS_SCRATCH_BYTES
+    _lib.check(_lib.load().nppc_gs_loss_fused_real(head.data_ptr(), gt.data_ptr(), pred.data_ptr(), B, n, P, scr.data_ptr(),
+                                                   w.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(),
+                                                   w_norms.data_ptr(), reconst.data_ptr(), sm.data_ptr(), _stream()),
+               "nppc_gs_loss_fused_real")
+    scr = scr[:B * GS_SCRATCH_BYTES].reshape(B, GS_SCRATCH_BYTES)
+    Gu = scr[:, :13 * 13 * 16].contiguous().view(torch.float64).reshape(B, 13, 13, 2)[:, :n + 1, :n + 1, 0]
+    up = torch.triu(Gu, diagonal=1)
+    G = torch.diag_embed(torch.diagonal(Gu, dim1=1, dim2=2)) + up + up.transpose(1, 2)
+    A = scr[:, 13 * 13 * 16:].contiguous().view(torch.float32).reshape(B, 12, 12, 2)[:, :n, :n, 0].contiguous()
+    return w, dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm), G, A
+
+
+def real_lincomb(x: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor, coef: torch.Tensor):
+    """out[b,i] = sum_k coef[b,i,k] x[b,k] + coef[b,i,n] (gt - pred)[b] for REAL vectors: x [B,n,...], gt / pred [B,...],
+    coef [B,n,n+1] real — the streaming pass of the inpainting head's Gram-Schmidt + loss backward.  Runs on
+    nppc_complex_lincomb: with purely real coefficients the planar complex kernel treats its two planes independently, so the
+    two halves of every real vector ride as its "real" and "imaginary" planes (needs an even vector length)."""
+    x, gt, pred = _f32(x), _f32(gt), _f32(pred)
+    B, n = x.shape[:2]
+    P = x[0, 0].numel()
+    if P % 2:
+        raise ValueError(f"real_lincomb: vector length must be even (got {P})")
+    assert gt[0].numel() == P and pred[0].numel() == P and tuple(coef.shape) == (B, n, n + 1) and not coef.is_complex()
+    c = torch.complex(coef.float(), torch.zeros_like(coef, dtype=torch.float32))
+    out = complex_lincomb(x.reshape(B, n, 2, P // 2), gt.reshape(B, 2, P // 2), pred.reshape(B, 2, P // 2), c)
+    return out.reshape(x.shape)
+
+
 def projection_loss_real(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
     """Loss statistics of the inpainting NPPC trainer's base_step for an explicit w_mat [B,n,F,T]."""
     w_mat, gt, pred = _f32(w_mat), _f32(gt), _f32(pred)

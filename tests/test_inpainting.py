@@ -216,3 +216,150 @@ def test_nhwc_pool_and_upsample_kernels_vs_torch():
     dy, dx = 33 - ref.size(2), 125 - ref.size(3)
     ref = F.pad(ref, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
     assert rel_err(u.float().permute(0, 3, 1, 2).cpu(), ref.cpu()) < 1e-3
+
+
+# ---- the training step (a16 grad path): PC head in train mode, hand-written masking / Gram-Schmidt / objective backward ----
+PICKS = {"outc.conv.weight": 1, "outc.conv.bias": 1, "inc.conv.conv.0.weight": 1, "inc.conv.conv.1.weight": 1,
+         "inc.conv.conv.4.bias": 1, "down4.mpconv.1.conv.3.weight": 4099, "down4.mpconv.1.conv.4.weight": 1,
+         "up1.conv.conv.0.weight": 8191, "up4.conv.conv.4.bias": 1}        # == oracle/make_golden_inpainting_grads.py
+
+
+def _check_step_against_reference(net, gg, step, objective, grad_norm, before, tol):
+    """Gradients (taken BEFORE clipping: `before` holds them), objective, clip norm, BatchNorm running mean and the parameters
+    after the clipped Adam step against the unmodified reference's training step."""
+    params = dict(net.named_parameters())
+    assert abs(float(objective) - gg[f"s{step}_objective"].item()) < tol * abs(gg[f"s{step}_objective"].item())
+    assert abs(float(grad_norm) - gg[f"s{step}_grad_norm"].item()) < tol * gg[f"s{step}_grad_norm"].item()
+    for k, s in PICKS.items():
+        ref = gg[f"s{step}_grad_{k}"]
+        assert rel_err(before[k].flatten()[::s].cpu(), ref) < tol, (step, k)
+        # Adam's first step moves every weight by lr * g / (|g| + eps): compare the UPDATE where the gradient is not noise
+        w0 = weights.synth_unet_tensor("head." + k, params[k].shape, 0).flatten()[::s]
+        upd_ref = gg[f"s{step}_after_{k}"] - w0
+        upd = params[k].detach().flatten()[::s].cpu() - w0
+        sel = (ref.abs() * min(1.0, 1.0 / gg[f"s{step}_grad_norm"].item())) > 1e-5
+        assert sel.any() and (upd[sel] - upd_ref[sel]).abs().max().item() < 0.02 * 1e-4, (step, k)
+    rm = dict(net.named_buffers())["inc.conv.conv.1.running_mean"]
+    assert rel_err(rm.cpu(), gg[f"s{step}_bn_running_mean"]) < max(tol, 1e-5)
+
+
+@pytest.mark.parametrize("step", [0, 600])
+def test_inpainting_training_step_host_math_vs_reference_gradients(step):
+    """CPU: everything of InpaintingNPPCStep.train_step that is NOT a kernel — the product UNet in train mode (module tree,
+    BatchNorm batch statistics, state_dict naming), the coefficient-space backward of masking + real Gram-Schmidt + objective
+    (gs_backward.gs_loss_grad_coeffs(real=True)) fed with the Gram / coefficient matrices the forward kernel leaves in its
+    scratch (restated here in fp64), and the sync-free clip_grad_norm_ — against ONE training step of the unmodified reference
+    (tests/golden/inpaint_step_b2_grads.npz)."""
+    import generative_audio_b200 as g
+    from generative_audio_b200.gs_backward import gs_loss_grad_coeffs
+    from generative_audio_b200.inpainting import second_moment_lambda
+    from generative_audio_b200.inpainting_training import clip_grad_norm_
+    gd, gg = load_golden("inpaint_model_b2"), load_golden("inpaint_step_b2_grads")
+    net, p_head = _params(2, N_DIRS, "head.")
+    net.load_state_dict(p_head)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    m4 = gd["mask"][:, None, None, :].expand(-1, 1, gd["clean_n"].shape[2], -1)
+    with torch.enable_grad():
+        head = net._forward(torch.cat((gd["masked_n"], gd["pred"]), dim=1)) * (1 - m4)
+        X = head.detach().double().flatten(2)
+        V = torch.cat([X, (gd["clean_n"] - gd["pred"]).double().flatten(1)[:, None]], 1)
+        G = torch.einsum("bjp,bkp->bjk", V, V)
+        W = O.gram_schmidt_real(head.detach().double()).flatten(2)
+        # w = A x with A lower triangular (the gap holds 9 x 40 bins: the three directions are independent)
+        A = torch.linalg.lstsq(X.transpose(1, 2), W.transpose(1, 2)).solution.transpose(1, 2)
+        lam = second_moment_lambda(step, 500, 1.0)
+        coef = gs_loss_grad_coeffs(G, A, lam, real=True)
+        head.backward(torch.einsum("bik,bkp->bip", coef, V).view_as(head).float())
+    st = O.inpaint_loss(W.view_as(head).float(), gd["clean_n"], gd["pred"], step=step, grace=500, lambda0=1.0)
+    before = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    norm = clip_grad_norm_(list(net.parameters()), 1.0)
+    opt.step()
+    _check_step_against_reference(net, gg, step, st["objective"], norm, before, 2e-4)
+    assert not gg[f"s{step}_rest_has_grad"].item()
+
+
+def _cpu_kernel_stubs(monkeypatch):
+    """CPU restatements (oracle functions, fp64 Gram / coefficient matrices) of the kernels InpaintingNPPCStep calls, installed
+    over generative_audio_b200.ops, so that the Python glue of the training step (autograd Functions, argument order, shapes,
+    non-differentiable outputs, log keys, optimizer plumbing) can be rehearsed end to end without a GPU.  TEST ONLY."""
+    import generative_audio_b200 as g
+    ops, I = g.ops, g.inpainting
+
+    def logmag_normalize(clean_spec, masked_spec):
+        c, _, m = O.inpaint_preprocess(clean_spec, masked_spec, torch.ones(clean_spec.shape[0], clean_spec.shape[3]))
+        return c, m, None, None
+
+    def mask_blend(x_in, x, mask):
+        mask = mask.reshape(x.shape[0], 1, *x.shape[2:])
+        return x * (1 - mask) if x_in is None else x_in[:, :1] * mask + x * (1 - mask)
+
+    def with_gram(head, gt, pred):
+        X = head.double().flatten(2)
+        V = torch.cat([X, (gt - pred).double().flatten(1)[:, None]], 1)
+        w = O.gram_schmidt_real(head.double())
+        A = torch.linalg.lstsq(X.transpose(1, 2), w.flatten(2).transpose(1, 2)).solution.transpose(1, 2)
+        st = O.inpaint_loss(w.float(), gt, pred, step=600, grace=500, lambda0=1.0)
+        st = {k: st[k] for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse")}
+        return w.float(), st, torch.einsum("bjp,bkp->bjk", V, V), A.float()
+
+    def real_lincomb(x, gt, pred, coef):
+        V = torch.cat([x.double().flatten(2), (gt - pred).double().flatten(1)[:, None]], 1)
+        return torch.einsum("bik,bkp->bip", coef.double(), V).view_as(x).float()
+
+    monkeypatch.setattr(ops, "logmag_normalize", logmag_normalize)
+    monkeypatch.setattr(ops, "mask_blend", mask_blend)
+    monkeypatch.setattr(ops, "gs_loss_fused_real_with_gram", with_gram)
+    monkeypatch.setattr(ops, "gs_loss_fused_real", lambda h, a, b: with_gram(h, a, b)[:2])
+    monkeypatch.setattr(ops, "real_lincomb", real_lincomb)
+    monkeypatch.setattr(I.UNet, "forward", I.UNet._forward)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+
+
+def _cpu_product_model():
+    import generative_audio_b200 as g
+    I = g.inpainting
+    rest, p_rest = _params(1, 1, "rest.")
+    rest.load_state_dict(p_rest)
+    m = I.NPPCModel.__new__(I.NPPCModel)          # NPPCModel.__init__ refuses to build without CUDA: assemble its parts
+    torch.nn.Module.__init__(m)
+    m.pretrained_restoration_model = I.RestorationWrapper(rest).eval()
+    m.pc_wrapper = I.AudioInpaintingPCWrapper(I.AudioInpaintingPCWrapperConfig(
+        model_configuration=I.UNetConfig(in_channels=2, out_channels=N_DIRS), n_dirs=N_DIRS))
+    m.pc_wrapper.net.load_state_dict(weights.synth_unet_state_dict(_shapes(m.pc_wrapper.net), 0, "head."))
+    return m.eval()
+
+
+@pytest.mark.parametrize("step", [0, 600])
+def test_inpainting_train_step_glue_rehearsal_on_cpu(monkeypatch, step):
+    """InpaintingNPPCStep.train_step end to end with the kernels replaced by CPU restatements: the product's own autograd
+    Functions, mode handling, clipping and optimizer plumbing reproduce the reference's training step (same checks as the GPU
+    test in test_zz_inpainting_training_gpu.py)."""
+    import generative_audio_b200 as g
+    _cpu_kernel_stubs(monkeypatch)
+    gd, gg = load_golden("inpaint_model_b2"), load_golden("inpaint_step_b2_grads")
+    batch = (gd["masked_spec"], gd["mask"], gd["clean_spec"])
+    m = _cpu_product_model()
+    m.pc_wrapper.train()
+    stepper = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+    stepper.step = step
+    with torch.enable_grad():
+        reconst, objective, log = stepper.base_step(batch, requires_grad=True)
+        objective.backward()
+    assert set(log) == {"w_mat", "err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse", "objective"}
+    assert not log["w_mat"].requires_grad and rel_err(reconst.detach(), gg[f"s{step}_reconst_err"]) < 1e-4
+    assert all(p.grad is None for p in m.pretrained_restoration_model.parameters())
+    before = {k: p.grad.detach().clone() for k, p in m.pc_wrapper.net.named_parameters()}
+    m2 = _cpu_product_model()
+    stepper2 = g.inpainting.InpaintingNPPCStep(m2, 1.0, 500, max_grad_norm=1.0)
+    stepper2.step = step
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    with torch.enable_grad():
+        obj2, log2 = stepper2.train_step(batch, opt)
+    assert stepper2.step == step + 1 and m2.pc_wrapper.training and not m2.pretrained_restoration_model.training
+    # 2e-3: the restoration output comes from the product's BatchNorm-folded convolutions here (1e-5 off the reference's
+    # unfolded ones) and the head's train-mode BatchNorm over 2 x 3 bottleneck pixels amplifies that in the gradients
+    _check_step_against_reference(m2.pc_wrapper.net, gg, step, obj2.item(), log2["grad_norm"].item(), before, 2e-3)
+    with torch.no_grad():
+        _, obj3, _ = stepper.base_step(batch)
+    assert abs(obj3.item() - objective.item()) < 1e-4 * abs(objective.item())

@@ -123,3 +123,58 @@ def test_training_path_refuses_configurations_it_does_not_differentiate():
     x = torch.zeros(2, 1, 257, 5)
     with pytest.raises(NotImplementedError, match="offline_laplace_norm"):
         training.head_forward_train(net, x, x, x, x, x, x)
+
+
+def _gs_real_ref(x):
+    """inpainting/nppc/pc_wrapper.py:43-59, literally."""
+    sh = x.shape
+    x = x.flatten(2)
+    outs, hats = [], []
+    for i in range(x.shape[1]):
+        w = x[:, i, :]
+        for w2 in hats:
+            w = w - w2 * torch.sum(w * w2, dim=-1, keepdim=True)
+        hats.append(w.detach() / w.detach().norm(dim=-1, keepdim=True))
+        outs.append(w)
+    return torch.stack(outs, dim=1).view(*sh)
+
+
+def _loss_real_ref(w_mat, clean, pred, lam):
+    """inpainting/trainer/nppc_trainer.py:347-373, literally (objective = reconst.mean() + lam * second_moment.mean())."""
+    w_ = w_mat.flatten(2)
+    w_norms = w_.norm(dim=2) + 1e-6
+    w_hat = w_ / w_norms[:, :, None]
+    err = (clean - pred).flatten(1)
+    err_norm = err.norm(dim=1) + 1e-6
+    err = err / err_norm[:, None]
+    w_norms = w_norms / err_norm[:, None]
+    err_proj = torch.einsum("bki,bi->bk", w_hat, err)
+    reconst = 1 - err_proj.pow(2).sum(dim=1)
+    second = (w_norms.pow(2) - err_proj.detach().pow(2)).pow(2)
+    return reconst.mean() + lam * second.mean()
+
+
+@pytest.mark.parametrize("B,n,P,lam", [(3, 5, 200, 0.37), (1, 1, 50, 1.0), (2, 10, 64, 1e-6), (2, 3, 30, 1.0)])
+def test_real_gs_loss_backward_in_coefficient_space_matches_autograd(B, n, P, lam):
+    """The inpainting head's backward (real Gram-Schmidt with detached normalisers + the 1e-6-regularised projection /
+    second-moment objective) from the Gram matrix and the coefficient matrix the forward kernel leaves in its scratch."""
+    from generative_audio_b200.gs_backward import gs_loss_grad_coeffs
+    g = torch.Generator().manual_seed(B * 100 + n + 7)
+    x = torch.randn(B, n, 1, P, dtype=torch.float64, generator=g) * 0.3        # small norms: the 1e-6 terms are visible
+    if n > 2:
+        x[:, 2] = 0.6 * x[:, 0] + 0.4 * x[:, 2]
+    clean = torch.randn(B, 1, 1, P, dtype=torch.float64, generator=g)
+    pred = torch.randn(B, 1, 1, P, dtype=torch.float64, generator=g)
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_(True)
+        _loss_real_ref(_gs_real_ref(xr), clean, pred, lam).backward()
+    X = x.flatten(2)
+    V = torch.cat([X, (clean - pred).flatten(1)[:, None]], 1)
+    G = torch.einsum("bjp,bkp->bjk", V, V)
+    with torch.no_grad():
+        W = _gs_real_ref(x).flatten(2)
+    A = torch.linalg.lstsq(X.transpose(1, 2), W.transpose(1, 2)).solution.transpose(1, 2)
+    coef = gs_loss_grad_coeffs(G, A, lam, real=True)
+    assert not coef.is_complex()
+    got = torch.einsum("bik,bkp->bip", coef, V).view_as(x)
+    assert ((got - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-9
