@@ -48,6 +48,20 @@ def build(force: bool = False, verbose: bool = True) -> str:
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
+    # one builder at a time: the N ranks of a torchrun launch all come through here on a box that received no prebuilt
+    # library; the first one compiles, the others wait on the lock and then find the stamp current
+    import fcntl
+    with open(os.path.join(OBJ, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+                return LIB
+            return _build_locked(dig, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig: str, stamp: str, verbose: bool) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
@@ -61,10 +75,12 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)      # atomic: a process that already mapped the old file keeps it, nobody sees a half-written one
     with open(stamp, "w") as f:
         f.write(dig)
     if verbose:
