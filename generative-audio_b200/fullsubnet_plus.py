@@ -1,8 +1,9 @@
 """FullSubNet+ backbone (a8) on B200: mirrors FullSubNet_Plus (fullsubnet_plus.py:45-230).
 
 Data flow per forward (all device-resident, fp32 unless noted):
-  pad+offline-norm (1 fused kernel per plane) -> TSSE -> TCN (torch library ops, "next" row N2)
-  -> fused sub-band pack (unfold ++ cat ++ norm ++ drop_band, written time-major [T',R,64]; fp16 for the
+  pad+offline-norm (1 fused kernel per plane) -> TSSE (3 fused kernels) -> TCN ("tc": channel-last, every 1x1 convolution on
+  the in-house tcgen05 GEMM with split-precision operands; "f32" / "tcp": fp32 SGEMM + 3 fused kernels per block)
+  -> fused sub-band pack (unfold ++ cat ++ offline | cumulative norm ++ drop_band, written time-major [T',R,64]; fp16 for the
      tensor-core LSTM) -> 2-layer LSTM + fc kernels -> mask assembly kernel.
 The [B,F,34,T'] sub-band tensor of the reference is never materialised."""
 from typing import Optional

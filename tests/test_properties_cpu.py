@@ -1,0 +1,162 @@
+"""Property tests (hypothesis) of the oracle and of the host-side index logic — SURVEY.md §4 (iv): size-independent invariants
+the domain offers, on randomly drawn shapes incl. the ragged / degenerate ones (single frame, one frequency group, one
+direction).  The `-m gpu` tests check the kernels against this oracle; these pin what the oracle itself must satisfy.
+
+  * unfold: the reflect index map out[b,f,k,t] = x[b, reflect(f+k-N), t] (base_model.py:15-46), N = 0 is a pure reshape;
+  * drop_band: a permutation of (sample, frequency) pairs — every kept pair appears exactly once, dropped ones never
+    (feature.py:254-285);
+  * Gram-Schmidt (pc_wrapper.py:8-44): direction 0 untouched, Re<w_{i-1}, w_i> = 0 for ADJACENT directions only (the
+    conjugated coefficient leaves the imaginary parts of the inner products, which re-contaminate earlier directions: the
+    reference's output is neither unitary- nor fully Re-orthogonal), invariance of w_i under a positive rescaling of EARLIER
+    inputs (the normaliser is scale-free); the real (inpainting) variant is plainly orthogonal and idempotent;
+  * STFT -> iSTFT round trip for any length >= one hop, linearity of the STFT;
+  * cIRM compress -> decompress round trip inside the clamp, oddness of decompress, saturation at +-9.9;
+  * cRM apply: the conj quirk equals complex multiplication by conj(M), the plain one by M (utils.py:241-249, mask.py:57-60);
+  * round-robin sharding: the shards partition the job for every (n, world), sizes differ by at most one."""
+import os
+import sys
+
+import pytest
+import torch
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+import nppc_oracle as O  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FAST = settings(max_examples=25, deadline=None)
+
+
+def _randn(seed, *shape, dtype=torch.float64):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=dtype)
+
+
+@FAST
+@given(B=st.integers(1, 3), F=st.integers(2, 40), T=st.integers(1, 9), N=st.integers(0, 15), seed=st.integers(0, 10**6))
+def test_unfold_is_the_reflect_index_map(B, F, T, N, seed):
+    N = min(N, F - 1)                                       # F.pad(reflect) needs N < F, as in the reference
+    x = _randn(seed, B, 1, F, T, dtype=torch.float32)
+    out = O.unfold(x, N)                                    # [B, F, 1, 2N+1, T]
+    assert out.shape == (B, F, 1, 2 * N + 1, T)
+    f = torch.arange(F)[:, None] + torch.arange(2 * N + 1)[None, :] - N
+    f = torch.where(f < 0, -f, f)
+    f = torch.where(f > F - 1, 2 * (F - 1) - f, f)
+    assert torch.equal(out[:, :, 0], x[:, 0][:, f])         # bit-exact gather
+    if N == 0:
+        assert torch.equal(out.reshape(B, F, T), x[:, 0])
+
+
+@FAST
+@given(B=st.integers(2, 9), F=st.integers(1, 33), G=st.integers(1, 5), T=st.integers(1, 4))
+def test_drop_band_is_a_permutation_of_kept_pairs(B, F, G, T):
+    if B <= G:
+        with pytest.raises(AssertionError):
+            O.drop_band(torch.zeros(B, 1, F, T), G)          # feature.py:263 asserts B > groups first
+        return
+    tag = (torch.arange(B)[:, None] * 1000 + torch.arange(F)[None, :]).float()[:, None, :, None].expand(B, 1, F, T).contiguous()
+    out = O.drop_band(tag, G)
+    if G <= 1:
+        assert torch.equal(out, tag)
+        return
+    Fg = F // G
+    assert out.shape[2] == Fg and torch.equal(out[..., 0], out[..., -1])
+    got = out[:, 0, :, 0].reshape(-1).long().tolist()
+    want = [b * 1000 + f for g in range(G) for b in range(g, B, G) for f in range(g, Fg * G, G)]
+    assert got == want and len(set(got)) == len(got)
+
+
+@FAST
+@given(B=st.integers(1, 3), n=st.integers(1, 8), P=st.integers(8, 60), seed=st.integers(0, 10**6))
+def test_gram_schmidt_invariants(B, n, P, seed):
+    P = max(P, n + 2)
+    x = _randn(seed, B, n, 2, P, 1)
+    w = O.gram_schmidt_complex(x)
+    assert torch.equal(w[:, 0], x[:, 0])                                           # direction 0 is returned untouched
+    wc = torch.complex(w[:, :, 0], w[:, :, 1]).flatten(2)
+    gram = torch.einsum("bip,bjp->bij", wc.conj(), wc)
+    nrm = wc.norm(dim=2)
+    cosr = gram.real / (nrm[:, :, None] * nrm[:, None, :])
+    # The reference's conjugated coefficient removes conj(<what_j, w>) what_j: the LAST projection leaves Re<w_{i-1}, w_i> = 0,
+    # but the imaginary parts of the inner products survive, so earlier directions are re-contaminated (Re<w_0, w_2> != 0 in
+    # general) and the procedure is not idempotent.  Asserted both ways so nobody "fixes" the kernel.
+    for i in range(1, n):
+        assert cosr[:, i - 1, i].abs().max().item() < 1e-10
+    if n > 1:
+        assert (gram.imag.abs().max() / nrm.max() ** 2).item() > 1e-9
+    if n > 1:                                                                       # normalisers are scale-free
+        xs = x.clone()
+        xs[:, 0] *= 3.5
+        ws = O.gram_schmidt_complex(xs)
+        assert ((ws[:, 1:] - w[:, 1:]).abs().max() / w.abs().max()).item() < 1e-10
+    # the real (inpainting) variant: plain orthogonality
+    xr = _randn(seed + 1, B, n, P)
+    wr = O.gram_schmidt_real(xr)
+    gr = torch.einsum("bip,bjp->bij", wr, wr)
+    nr = wr.norm(dim=2)
+    assert ((gr / (nr[:, :, None] * nr[:, None, :])) - torch.eye(n)).abs().max().item() < 1e-10 and torch.equal(wr[:, 0], xr[:, 0])
+    assert ((O.gram_schmidt_real(wr) - wr).abs().max() / wr.abs().max()).item() < 1e-10   # idempotent on an orthogonal set
+
+
+@FAST
+@given(B=st.integers(1, 2), hops=st.integers(1, 12), extra=st.integers(0, 255), seed=st.integers(0, 10**6))
+def test_stft_istft_round_trip_and_linearity(B, hops, extra, seed):
+    L = 256 * hops + extra + 256                            # reflect padding of 256 needs L > 256
+    x, y = _randn(seed, B, L), _randn(seed + 1, B, L)
+    mag, re, im = O.stft_mri(x)
+    T = 1 + L // 256
+    assert mag.shape == (B, 1, 257, T)
+    assert ((mag - torch.sqrt(re * re + im * im)).abs().max() / mag.abs().max()).item() < 1e-12
+    back = O.istft(re[:, 0], im[:, 0], L)
+    cover = 256 * (L // 256)              # T frames reconstruct hop * (T - 1) samples; torch.istft(length=L) zero-pads the rest
+    assert back.shape == (B, L)
+    assert ((back[:, :cover] - x[:, :cover]).abs().max() / x.abs().max()).item() < 1e-10
+    assert torch.all(back[:, cover:] == 0)
+    _, re2, im2 = O.stft_mri(2.0 * x - 0.5 * y)
+    _, rey, imy = O.stft_mri(y)
+    scale = re.abs().max()
+    assert ((re2 - (2.0 * re - 0.5 * rey)).abs().max() / scale).item() < 1e-12
+    assert ((im2 - (2.0 * im - 0.5 * imy)).abs().max() / scale).item() < 1e-12
+
+
+@FAST
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 200))
+def test_cirm_compress_decompress(seed, n):
+    m = _randn(seed, n) * 30.0                                                     # uncompressed mask values
+    c = O.compress_cirm(m)
+    assert c.abs().max().item() <= 10.0
+    inside = c.abs() < 9.9
+    d = O.decompress_cirm(c)
+    if inside.any():
+        assert ((d[inside] - m[inside]).abs() / m[inside].abs().clamp_min(1e-3)).max().item() < 1e-9
+    assert torch.allclose(O.decompress_cirm(-c), -d, rtol=0, atol=1e-12)             # odd
+    sat = O.decompress_cirm(torch.tensor([9.9, 12.0, -9.9, -50.0], dtype=torch.float64))
+    assert torch.allclose(sat[0], sat[1]) and torch.allclose(sat[2], sat[3]) and torch.allclose(sat[0], -sat[2])
+    assert abs(sat[0].item() - 52.933) < 1e-3                                        # -10 ln(0.1 / 19.9)
+
+
+@FAST
+@given(seed=st.integers(0, 10**6), B=st.integers(1, 2), F=st.integers(1, 9), T=st.integers(1, 7))
+def test_crm_apply_is_complex_multiplication(seed, B, F, T):
+    m0, m1, re, im = (_randn(seed + i, B, F, T) for i in range(4))
+    M, N = torch.complex(m0, m1), torch.complex(re, im)
+    for conj, ref in ((True, M.conj() * N), (False, M * N)):
+        out = O.crm_apply(m0, m1, re, im, conj)
+        mag, r, i = out
+        assert torch.allclose(r, ref.real, atol=1e-12) and torch.allclose(i, ref.imag, atol=1e-12)
+        assert torch.allclose(mag, ref.abs(), atol=1e-12)
+
+
+@FAST
+@given(n=st.integers(0, 2000), world=st.integers(1, 16))
+def test_round_robin_shards_partition_the_job(n, world):
+    from generative_audio_b200.sharding import shard_utterances
+    shards = [shard_utterances(n, r, world) for r in range(world)]
+    flat = sorted(i for s in shards for i in s)
+    assert flat == list(range(n))
+    sizes = [len(s) for s in shards]
+    assert max(sizes) - min(sizes) <= 1
+    assert all(i % world == r for r, s in enumerate(shards) for i in s)
