@@ -59,3 +59,32 @@ def gs_loss_grad_coeffs(G: torch.Tensor, A: torch.Tensor, lam: float, grad_scale
             v = v - a[:, j] * s.conj()[:, None]
         out[:, i] = v
     return out * grad_scale
+
+
+def gs_grad_coeffs(G2: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """Backward of Gram-Schmidt ALONE, for an arbitrary upstream gradient (the reference trainer's own pattern:
+    `w_mat = nppc_model(noisy)`, a loss written in torch, `.backward()`, trainer.py:255-298,100-106).
+
+    G2 [B, 2n, 2n]: Gram matrix (G2[j,k] = v_j^H v_k) of the 2n vectors (x_0 .. x_{n-1}, g_0 .. g_{n-1}), g_i = d L / d w_i;
+    A [B, n, n]: w_i = sum_k A_ik x_k from the forward.  Returns C [B, n, 2n] with d L / d x_i = sum_k C[i,k] v_k.
+    d/dx_i = M_0 .. M_{i-1} g_i (module docstring): every M_j moves its argument along a_j only, so the result stays in
+    span{g_i, x_0 .. x_{i-1}} and the whole recursion is arithmetic on 2n-vectors.  Works for real G2 / A as well (the
+    inpainting head: conj() is then a no-op)."""
+    B, n2, _ = G2.shape
+    n = n2 // 2
+    cd = G2.dtype
+    Wc = torch.zeros(B, n, n2, dtype=cd, device=G2.device)
+    Wc[:, :, :n] = A.to(cd)
+    GW = torch.einsum("bmk,bjk->bjm", G2, Wc)
+    nu = torch.einsum("bjm,bjm->bj", Wc.conj(), GW).real.clamp_min(0).sqrt()
+    a = Wc / nu[:, :, None].to(cd)                            # detached normalised directions (no epsilon, pc_wrapper.py:37)
+    Ga = torch.einsum("bmk,bjk->bjm", G2, a)
+    out = torch.zeros(B, n, n2, dtype=cd, device=G2.device)
+    for i in range(n):
+        v = torch.zeros(B, n2, dtype=cd, device=G2.device)
+        v[:, n + i] = 1
+        for j in range(i - 1, -1, -1):
+            s = torch.einsum("bm,bm->b", Ga[:, j].conj(), v)  # a_j^H v
+            v = v - a[:, j] * s.conj()[:, None]
+        out[:, i] = v
+    return out

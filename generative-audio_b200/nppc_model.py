@@ -79,9 +79,33 @@ class NPPCModel(nn.Module):
         d = ops.cancel_depth(taps["ereal"], count)
         return ops.cancel_depth(taps["eimag"], count, d)
 
-    @torch.no_grad()
+    # Opt-in: `model.differentiable_forward = True` makes forward() build an autograd graph through the PC head whenever grad
+    # mode is on — the reference trainer's own pattern (`w_mat = self.nppc_model(noisy)`, a loss in torch, `.backward()`,
+    # nppc_audio/trainer.py:255-298,100-106) then works unchanged.  Off by default: inference callers rarely wrap their calls
+    # in no_grad, and the training forward keeps every LSTM gate for BPTT (18 GB at B = 32).  NPPCAudioStep (trainer.py)
+    # is the faster way to train: it fuses Gram-Schmidt with the objective and shares the backbone pass with get_pred_crm.
+    differentiable_forward = False
+
+    def forward_train(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
+        """forward() with gradients w.r.t. the PC head's parameters: frozen half on the inference kernels (no_grad, as
+        nppc_model.py:94), head + Gram-Schmidt through the hand-written autograd Functions of training.py."""
+        from . import training
+        with torch.no_grad():
+            mag, real, imag = self._stft(noisy_waveform)
+            pred_crm = self.pretrained_restoration_model(mag, real, imag)
+            emag, ereal, eimag = ops.crm_decompress_apply(pred_crm, real, imag, conj=True)
+        with torch.enable_grad():
+            head = training.head_forward_train(self.audio_pc_wrapper.net, mag, real, imag, emag[:, None], ereal[:, None], eimag[:, None])
+            return training.GramSchmidtFn.apply(head)
+
     def forward(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
         """noisy_waveform [B, L] -> w_mat [B, n_dirs, 2, F', T]."""
+        if self.differentiable_forward and torch.is_grad_enabled():
+            return self.forward_train(noisy_waveform)
+        with torch.no_grad():
+            return self._forward_inference(noisy_waveform)
+
+    def _forward_inference(self, noisy_waveform: torch.Tensor) -> torch.Tensor:
         if self.config.lstm_impl != "auto":
             head, _ = self.forward_stages(noisy_waveform)
             return ops.gram_schmidt_complex(head)

@@ -264,6 +264,41 @@ def complex_lincomb(x: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor, coef:
     return out
 
 
+def _decode_gs_scratch(scr: torch.Tensor, B: int, n: int):
+    """SampleScratch of gram_schmidt.cu -> (Hermitian Gram matrix [B,n,n] complex128 of the n input vectors, coefficient
+    matrix A [B,n,n] complex64 with w = A x)."""
+    scr = scr[:B * GS_SCRATCH_BYTES].reshape(B, GS_SCRATCH_BYTES)
+    Gu = torch.view_as_complex(scr[:, :13 * 13 * 16].contiguous().view(torch.float64).reshape(B, 13, 13, 2))[:, :n, :n]
+    up = torch.triu(Gu, diagonal=1)
+    G = torch.diag_embed(torch.diagonal(Gu, dim1=1, dim2=2).real.to(Gu.dtype)) + up + up.conj().transpose(1, 2)
+    A = torch.view_as_complex(scr[:, 13 * 13 * 16:].contiguous().view(torch.float32).reshape(B, 12, 12, 2))[:, :n, :n]
+    return G, A
+
+
+def gram_schmidt_complex_with_coeffs(x: torch.Tensor):
+    """gram_schmidt_complex that also returns (G, A) from the kernel's scratch: the Gram matrix of the inputs and the
+    coefficients of w = A x — what the backward of a differentiable Gram-Schmidt needs (training.GramSchmidtFn)."""
+    x = _f32(x)
+    _chk(x)
+    B, n = x.shape[:2]
+    assert x.shape[2] == 2
+    P = x[0, 0, 0].numel()
+    out = torch.empty_like(x)
+    scr = _gs_scratch(B, n, x.device)
+    assert scr.numel() >= B * GS_SCRATCH_BYTES
+    _lib.check(_lib.load().nppc_gram_schmidt_complex(x.data_ptr(), B, n, P, scr.data_ptr(), out.data_ptr(), _stream()),
+               "nppc_gram_schmidt_complex")
+    G, A = _decode_gs_scratch(scr, B, n)
+    return out, G, A
+
+
+def gram_matrix_complex(v: torch.Tensor):
+    """Hermitian Gram matrix G [B,m,m] complex128 (G[j,k] = v_j^H v_k) of m <= 12 complex vectors v [B,m,2,...]: the fp64 Gram
+    pass of the Gram-Schmidt kernels (one read of v), taken from the scratch of a nppc_gram_schmidt_complex call whose
+    orthogonalised output is discarded."""
+    return gram_schmidt_complex_with_coeffs(v)[1]
+
+
 def projection_loss(w_mat: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor):
     """Loss statistics of NPPCAudioTrainer.base_step (trainer.py:259-298) for an explicit w_mat."""
     w_mat, gt, pred = _f32(w_mat), _f32(gt), _f32(pred)

@@ -24,7 +24,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
-from .gs_backward import gs_loss_grad_coeffs
+from .gs_backward import gs_grad_coeffs, gs_loss_grad_coeffs
 from .modules import TCN_DILATIONS, TCNBlock
 
 
@@ -227,6 +227,34 @@ class GsLossFn(torch.autograd.Function):
         head, gt, pred, G, A, lam = ctx.saved_tensors
         coef = gs_loss_grad_coeffs(G, A.to(torch.complex128), lam) * g_obj.double()
         return ops.complex_lincomb(head, gt, pred, coef), None, None, None
+
+
+class GramSchmidtFn(torch.autograd.Function):
+    """gram_schmidt_to_crm (pc_wrapper.py:8-44) with a backward for an ARBITRARY upstream gradient: the reference trainer's own
+    pattern — `w_mat = nppc_model(noisy)`, a loss written in torch, `.backward()` (trainer.py:255-298) — when the fused
+    GsLossFn is not what the caller uses.  head [B, n, 2, F', T] -> w_mat, n <= 6.
+    Backward: one Gram pass over the 2n vectors (x_0 .. x_{n-1}, g_0 .. g_{n-1}), the coefficient recursion of
+    gs_backward.gs_grad_coeffs on 2n-vectors, one streaming linear combination — all on the Gram-Schmidt kernels."""
+
+    @staticmethod
+    def forward(ctx, head):
+        n = head.shape[1]
+        if n > 6:
+            raise NotImplementedError("differentiable Gram-Schmidt: n_dirs <= 6 (the backward stacks 2 n vectors; kernels take 12)")
+        w, _, A = ops.gram_schmidt_complex_with_coeffs(head)
+        ctx.save_for_backward(head, A)
+        return w
+
+    @staticmethod
+    def backward(ctx, g):
+        head, A = ctx.saved_tensors
+        B, n = head.shape[:2]
+        S = torch.cat([head, g.to(head.dtype)], dim=1).contiguous()           # [B, 2n, 2, F', T]
+        coef = gs_grad_coeffs(ops.gram_matrix_complex(S), A.to(torch.complex128))       # [B, n, 2n]
+        full = torch.zeros(B, 2 * n, 2 * n + 1, dtype=coef.dtype, device=coef.device)   # rows n..2n-1 and the error column stay 0
+        full[:, :n, :2 * n] = coef
+        zero = torch.zeros(B, *head.shape[2:], device=head.device, dtype=head.dtype)
+        return ops.complex_lincomb(S, zero, zero, full)[:, :n].contiguous()
 
 
 # ---- the PC head, training forward ----------------------------------------------------------------------------------------

@@ -178,3 +178,81 @@ def test_real_gs_loss_backward_in_coefficient_space_matches_autograd(B, n, P, la
     assert not coef.is_complex()
     got = torch.einsum("bik,bkp->bip", coef, V).view_as(x)
     assert ((got - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-9
+
+
+@pytest.mark.parametrize("B,n,P", [(2, 5, 120), (1, 1, 30), (3, 6, 64)])
+def test_gram_schmidt_backward_for_an_arbitrary_upstream_gradient(B, n, P):
+    """gs_backward.gs_grad_coeffs: the backward of Gram-Schmidt alone (what NPPCModel's differentiable forward needs when the
+    loss is written in torch by the caller, as in the reference trainer) against autograd, complex and real."""
+    from generative_audio_b200.gs_backward import gs_grad_coeffs
+    g = torch.Generator().manual_seed(B * 10 + n)
+    x = torch.randn(B, n, 2, P, dtype=torch.float64, generator=g)
+    up = torch.randn(B, n, 2, P, dtype=torch.float64, generator=g)               # arbitrary d L / d w
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_(True)
+        (_gs_ref(xr) * up).sum().backward()
+    xc, gc = torch.complex(x[:, :, 0], x[:, :, 1]), torch.complex(up[:, :, 0], up[:, :, 1])
+    V = torch.cat([xc, gc], 1)
+    G2 = torch.einsum("bjp,bkp->bjk", V.conj(), V)
+    with torch.no_grad():
+        w = _gs_ref(x)
+    wc = torch.complex(w[:, :, 0], w[:, :, 1])
+    A = torch.linalg.lstsq(xc.transpose(1, 2), wc.transpose(1, 2)).solution.transpose(1, 2)
+    d = torch.einsum("bik,bkp->bip", gs_grad_coeffs(G2, A), V)
+    got = torch.stack([d.real, d.imag], 2)
+    assert ((got - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-9
+    # real variant (inpainting head)
+    xre = torch.randn(B, n, 1, P, dtype=torch.float64, generator=g)
+    upr = torch.randn(B, n, 1, P, dtype=torch.float64, generator=g)
+    with torch.enable_grad():
+        xg = xre.clone().requires_grad_(True)
+        (_gs_real_ref(xg) * upr).sum().backward()
+    Vr = torch.cat([xre.flatten(2), upr.flatten(2)], 1)
+    with torch.no_grad():
+        Wr = _gs_real_ref(xre).flatten(2)
+    Ar = torch.linalg.lstsq(xre.flatten(2).transpose(1, 2), Wr.transpose(1, 2)).solution.transpose(1, 2)
+    dr = torch.einsum("bik,bkp->bip", gs_grad_coeffs(torch.einsum("bjp,bkp->bjk", Vr, Vr), Ar), Vr).view_as(xre)
+    assert ((dr - xg.grad).abs().max() / xg.grad.abs().max()).item() < 1e-9
+
+
+def test_differentiable_gram_schmidt_function_glue_on_cpu(monkeypatch):
+    """training.GramSchmidtFn with its three kernel calls replaced by CPU restatements: the Function's own plumbing (stacking
+    [x; g], padding the coefficient matrix to the lincomb kernel's [2n, 2n+1] shape, slicing the n useful rows) reproduces
+    autograd of the reference's Gram-Schmidt for a loss written in torch.  TEST-ONLY stubs."""
+    import generative_audio_b200 as G
+    from generative_audio_b200 import training
+    ops = G.ops
+
+    def cplx(t):
+        return torch.complex(t[:, :, 0].double(), t[:, :, 1].double()).flatten(2)
+
+    def with_coeffs(x):
+        w = _gs_ref(x.double().flatten(3)).view_as(x)
+        xc, wc = cplx(x), cplx(w)
+        A = torch.linalg.lstsq(xc.transpose(1, 2), wc.transpose(1, 2)).solution.transpose(1, 2)
+        return w.to(x.dtype), torch.einsum("bjp,bkp->bjk", xc.conj(), xc), A.to(torch.complex64)
+
+    def lincomb(x, gt, pred, coef):
+        B, n = x.shape[:2]
+        assert tuple(coef.shape) == (B, n, n + 1) and gt.shape == pred.shape == (B, *x.shape[2:])
+        e = torch.complex((gt - pred)[:, 0].double(), (gt - pred)[:, 1].double()).flatten(1)
+        d = torch.einsum("bik,bkp->bip", coef.to(torch.complex128), torch.cat([cplx(x), e[:, None]], 1))
+        return torch.stack([d.real, d.imag], 2).reshape(x.shape).to(x.dtype)
+
+    monkeypatch.setattr(ops, "gram_schmidt_complex_with_coeffs", with_coeffs)
+    monkeypatch.setattr(ops, "gram_matrix_complex", lambda v: with_coeffs(v)[1])
+    monkeypatch.setattr(ops, "complex_lincomb", lincomb)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 5, 2, 6, 9, dtype=torch.float64, generator=g)
+    tgt = torch.randn(2, 5, 2, 6, 9, dtype=torch.float64, generator=g)
+    with torch.enable_grad():
+        a = x.clone().requires_grad_(True)
+        w = training.GramSchmidtFn.apply(a)
+        ((w - tgt) ** 2).sum().backward()                                           # any torch loss, as the reference trainer writes it
+        b = x.clone().requires_grad_(True)
+        wr = _gs_ref(b.flatten(3)).view_as(b)
+        ((wr - tgt) ** 2).sum().backward()
+    assert ((w.detach() - wr.detach()).abs().max() / wr.abs().max()).item() < 1e-12
+    assert ((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-6       # A rides in complex64, as on the device
+    with pytest.raises(NotImplementedError):
+        training.GramSchmidtFn.apply(torch.zeros(1, 7, 2, 4, 4))
