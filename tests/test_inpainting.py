@@ -363,3 +363,25 @@ def test_inpainting_train_step_glue_rehearsal_on_cpu(monkeypatch, step):
     with torch.no_grad():
         _, obj3, _ = stepper.base_step(batch)
     assert abs(obj3.item() - objective.item()) < 1e-4 * abs(objective.item())
+
+
+def test_inpainting_eval_forward_glue_rehearsal_on_cpu(monkeypatch):
+    """The eval-mode forward (folded BatchNorm, fp32 path) and the no-grad base_step with the kernels replaced by CPU
+    restatements: the Python side of the GPU-verified inference path keeps reproducing the reference golden after the
+    train-mode additions."""
+    import generative_audio_b200 as g
+    _cpu_kernel_stubs(monkeypatch)
+    monkeypatch.setattr(g.ops, "gram_schmidt_real", lambda x: O.gram_schmidt_real(x))
+    gd = load_golden("inpaint_model_b2")
+    m = _cpu_product_model()
+    assert not m.training
+    clean_n, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"], gd["masked_spec"], gd["mask"])
+    assert rel_err(m.get_pred_spec_mag_norm(masked_n, m4), gd["pred"]) < 1e-4
+    assert rel_err(m(masked_n, m4), gd["w_mat"]) < 1e-3
+    stepper = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+    stepper.step = 600
+    _, objective, log = stepper.base_step((gd["masked_spec"], gd["mask"], gd["clean_spec"]))
+    assert abs(objective.item() - gd["s600_objective"].item()) < 2e-3 * abs(gd["s600_objective"].item())
+    monkeypatch.undo()                                  # without the test-only stubs the product refuses CPU tensors
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m.pc_wrapper.net(masked_n)
