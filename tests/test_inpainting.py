@@ -237,7 +237,7 @@ def _check_step_against_reference(net, gg, step, objective, grad_norm, before, t
         w0 = weights.synth_unet_tensor("head." + k, params[k].shape, 0).flatten()[::s]
         upd_ref = gg[f"s{step}_after_{k}"] - w0
         upd = params[k].detach().flatten()[::s].cpu() - w0
-        sel = (ref.abs() * min(1.0, 1.0 / gg[f"s{step}_grad_norm"].item())) > 1e-5
+        sel = ref.abs() > 0.05 * ref.abs().max()          # well above any gradient noise: no sign flips, |g| >> Adam's eps
         assert sel.any() and (upd[sel] - upd_ref[sel]).abs().max().item() < 0.02 * 1e-4, (step, k)
     rm = dict(net.named_buffers())["inc.conv.conv.1.running_mean"]
     assert rel_err(rm.cpu(), gg[f"s{step}_bn_running_mean"]) < max(tol, 1e-5)
