@@ -2,6 +2,7 @@
   #2 enhance-only (STFT -> FullSubNet+ -> cRM -> iSTFT), batch 64 x 4 s
   #3 NPPC-audio training step (frozen backbone on the kernels, PC head through autograd, Adam), batch 32, groups 2
   #4 inpainting NPPC forward, batch 128 x [128 x 500] log-mag spectrograms, n_dirs = 10 (library convolutions)
+     + one training iteration of the inpainting NPPC trainer at the same batch size
   N1 validator consumer (pc_variations: 5 directions x 6 alphas -> audio), batch 8 x 4 s
 CUDA events, 3 warm-up + 5 timed iterations, 256 MiB L2 flush between iterations.  usage: python tools/config_bench.py"""
 import json
@@ -98,4 +99,22 @@ with torch.no_grad():
                                                               "two-tensor K loop instead of the decoder's cat); no cuDNN convolution in the step",
                                                       "w_mat_rel_err_vs_fp32": ((wtc - w32).abs().max() / w32.abs().max()).item()}
     I.set_compute_dtype(mi, None)
+
+# config 4, training: one iteration of the inpainting NPPC trainer (nppc_trainer.py:146-154) at the shipped batch size — frozen
+# restoration UNet on the tcgen05 convolutions, PC head in train mode through autograd (library convolutions), masking + real
+# Gram-Schmidt + objective forward / backward on the kernels, clipped Adam.  Reported, never fatal (first added without GPU access).
+try:
+    I.set_compute_dtype(mi.pretrained_restoration_model, "tc")
+    st = I.InpaintingNPPCStep(mi, 1.0, 500, max_grad_norm=1.0)
+    st.step = 600
+    opt_i = torch.optim.Adam(mi.pc_wrapper.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    batch = (spec * mask[:, None, None, :], mask, spec)
+    ms = timeit(lambda: st.train_step(batch, opt_i), reps=3, warm=2)
+    out["config4_inpainting_train_step_b128_ndirs10"] = {"ms_per_step": ms, "audio_s_per_s": B * 4.0 / (ms * 1e-3),
+                                                         "note": "head UNet fwd/bwd on the library (fp32 autograd), everything else on the kernels"}
+except Exception as e:   # noqa: BLE001
+    out["config4_inpainting_train_step_b128_ndirs10"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+finally:
+    I.set_compute_dtype(mi, None)
+    mi.eval()
 print(json.dumps(out, indent=1))
