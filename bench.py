@@ -374,6 +374,13 @@ def main():
         print(json.dumps(line))
         return
 
+    # watchdog: a rank that stops making progress (a wedged collective, a kernel that never returns) dumps every thread's
+    # Python stack to stderr and exits instead of holding the box until the caller's limit (an N = 4 training run did exactly
+    # that in round 2); torchrun then tears the other ranks down.  NPPC_BENCH_WATCHDOG_S=0 disables it.
+    import faulthandler
+    watchdog_s = int(os.environ.get("NPPC_BENCH_WATCHDOG_S", "1500"))
+    if watchdog_s > 0:
+        faulthandler.dump_traceback_later(watchdog_s, exit=True)
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
