@@ -525,7 +525,9 @@ def main():
         except Exception as e:   # reported, never fatal: it is a side-by-side bar, not the product
             line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(3, 1, args.cpu_batch)
+        # bounded sample, ~10 s of host work: 12 timed + 2 warm-up passes over --cpu-batch utterances (3 + 1 in round 1 moved by
+        # +-25 % from box to box: too few passes for a 16-thread oneDNN LSTM to settle)
+        r = cpu_reference_run(12, 2, args.cpu_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
     if world > 1:
