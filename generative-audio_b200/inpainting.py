@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .checkpoint import CheckpointMixin
 from .modules import _NoDerivedState
 
 
@@ -284,7 +285,7 @@ def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
     return max(min(-1.0 + 2.0 * step / grace, 1.0), 1e-6) * lambda0
 
 
-class InpaintingNPPCStep:
+class InpaintingNPPCStep(CheckpointMixin):
     """The inpainting NPPC trainer's base_step (nppc_trainer.py:338-385) and the body of its train() loop (:146-154): one
     restoration pass is shared by the PC head and the error (the reference runs it twice), Gram-Schmidt and the loss statistics
     are fused.  base_step(batch) is the no-grad statistics path (every op a kernel; the head in whatever mode it is in);

@@ -10,6 +10,7 @@ are all-reduced bucket by bucket while the backward is still running (training.G
 import torch
 
 from . import ops, training
+from .checkpoint import CheckpointMixin
 from .nppc_model import NPPCModel
 
 
@@ -17,7 +18,7 @@ def second_moment_lambda(step: int, grace: float, lambda0: float) -> float:
     return max(min(-1 + 2 * step / grace, 1), 1e-6) * lambda0
 
 
-class NPPCAudioStep:
+class NPPCAudioStep(CheckpointMixin):
     """Holds what base_step reads from the reference trainer: model, step counter, loss hyper-parameters."""
 
     def __init__(self, nppc_model: NPPCModel, second_moment_loss_grace: float = 500, second_moment_loss_lambda: float = 1.0,

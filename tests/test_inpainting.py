@@ -385,3 +385,39 @@ def test_inpainting_eval_forward_glue_rehearsal_on_cpu(monkeypatch):
     monkeypatch.undo()                                  # without the test-only stubs the product refuses CPU tensors
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         m.pc_wrapper.net(masked_n)
+
+
+def test_checkpoint_round_trip_in_the_reference_format(monkeypatch, tmp_path):
+    """save_checkpoint writes the reference trainers' file ({'model_state_dict', 'optimizer_state_dict', 'step'},
+    nppc_trainer.py:604-618 / trainer.py:319-335); load_checkpoint restores model, Adam moments and the step counter, so that a
+    resumed run continues bit-identically (CPU rehearsal with stubbed kernels)."""
+    import generative_audio_b200 as g
+    _cpu_kernel_stubs(monkeypatch)
+    gd = load_golden("inpaint_model_b2")
+    batch = (gd["masked_spec"], gd["mask"], gd["clean_spec"])
+
+    def fresh():
+        m = _cpu_product_model()
+        return m, g.inpainting.InpaintingNPPCStep(m, 1.0, 500), torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.5, 0.999))
+
+    m1, s1, o1 = fresh()
+    s1.step = 7
+    with torch.enable_grad():
+        s1.train_step(batch, o1)
+    path = s1.save_checkpoint(str(tmp_path / "ck" / "checkpoint_final.pt"), o1)
+    ck = torch.load(path, weights_only=True)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "step"} and ck["step"] == 8
+    with open(os.path.join(GOLD, "unet_manifest.json")) as f:
+        unet_keys = [k for k, _ in json.load(f)["entries"]]
+    assert list(ck["model_state_dict"]) == ["pretrained_restoration_model.net." + k for k in unet_keys] + \
+        ["pc_wrapper.net." + k for k in unet_keys]                     # the reference NPPCModel's keys: its validator loads them strictly
+    m2, s2, o2 = fresh()
+    assert s2.load_checkpoint(path, o2, map_location="cpu") == 8
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with torch.enable_grad():
+        obj1, _ = s1.train_step(batch, o1)
+        obj2, _ = s2.train_step(batch, o2)
+    assert obj1.item() == obj2.item() and s1.step == s2.step == 9
+    for a, b in zip(m1.pc_wrapper.parameters(), m2.pc_wrapper.parameters()):
+        assert torch.equal(a, b)                                       # same Adam moments -> the same second update
