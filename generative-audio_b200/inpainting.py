@@ -297,6 +297,7 @@ class InpaintingNPPCStep(CheckpointMixin):
         self.lambda0, self.grace = second_moment_loss_lambda, second_moment_loss_grace
         self.max_grad_norm = max_grad_norm      # NPPCAudioInpaintingTrainerConfig.max_grad_norm (nppc_trainer.py:39)
         self.step = 0
+        self._reducer = None                    # data parallel: bucketed gradient all-reduce overlapping the backward
 
     def base_step(self, batch, requires_grad: bool = False):
         """batch = (masked_spec [B,2,F,T], mask [B,T], clean_spec [B,2,F,T]) -> (reconst_err [B], objective [], log dict)."""
@@ -324,14 +325,25 @@ class InpaintingNPPCStep(CheckpointMixin):
     def train_step(self, batch, optimizer):
         """One iteration of NPPCAudioInpaintingTrainer.train (nppc_trainer.py:146-154, :184): the PC head in train mode, the
         restoration UNet frozen in eval mode; zero_grad -> backward -> clip_grad_norm_(max_grad_norm) -> optimizer.step.
-        Returns (objective, log); log["grad_norm"] is the pre-clip global norm (a device scalar: no host sync in the step)."""
+        Returns (objective, log); log["grad_norm"] is the pre-clip global norm (a device scalar: no host sync in the step).
+        Under torch.distributed (one process per GPU) the head's gradients are averaged over the ranks bucket by bucket while
+        the backward is still running (training.GradBucketReducer), BatchNorm statistics stay per rank (plain DDP semantics)."""
+        import torch.distributed as dist
+
         from . import inpainting_training as IT
         model = self.nppc_model
         model.pc_wrapper.train()
         model.pretrained_restoration_model.eval()
+        if self._reducer is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .training import GradBucketReducer     # one process per GPU: mean of the per-rank gradients (SURVEY.md §8e),
+            self._reducer = GradBucketReducer(model.pc_wrapper.parameters())   # each bucket exchanged as soon as it is final
         _, objective, log = self.base_step(batch, requires_grad=True)
         optimizer.zero_grad(set_to_none=True)
+        if self._reducer is not None:
+            self._reducer.reset()
         objective.backward()
+        if self._reducer is not None:
+            self._reducer.finish()                       # clip AFTER averaging: the norm of the global-batch gradient, as DDP would
         log["grad_norm"] = IT.clip_grad_norm_(list(model.parameters()), self.max_grad_norm)
         optimizer.step()
         self.step += 1

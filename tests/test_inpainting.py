@@ -307,13 +307,14 @@ def _cpu_kernel_stubs(monkeypatch):
         V = torch.cat([x.double().flatten(2), (gt - pred).double().flatten(1)[:, None]], 1)
         return torch.einsum("bik,bkp->bip", coef.double(), V).view_as(x).float()
 
-    monkeypatch.setattr(ops, "logmag_normalize", logmag_normalize)
-    monkeypatch.setattr(ops, "mask_blend", mask_blend)
-    monkeypatch.setattr(ops, "gs_loss_fused_real_with_gram", with_gram)
-    monkeypatch.setattr(ops, "gs_loss_fused_real", lambda h, a, b: with_gram(h, a, b)[:2])
-    monkeypatch.setattr(ops, "real_lincomb", real_lincomb)
-    monkeypatch.setattr(I.UNet, "forward", I.UNet._forward)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    setattr_ = monkeypatch.setattr if monkeypatch is not None else setattr     # None: a spawned worker process, nothing to undo
+    setattr_(ops, "logmag_normalize", logmag_normalize)
+    setattr_(ops, "mask_blend", mask_blend)
+    setattr_(ops, "gs_loss_fused_real_with_gram", with_gram)
+    setattr_(ops, "gs_loss_fused_real", lambda h, a, b: with_gram(h, a, b)[:2])
+    setattr_(ops, "real_lincomb", real_lincomb)
+    setattr_(I.UNet, "forward", I.UNet._forward)
+    setattr_(torch.Tensor, "cuda", lambda self, *a, **k: self)
 
 
 def _cpu_product_model():
@@ -421,3 +422,56 @@ def test_checkpoint_round_trip_in_the_reference_format(monkeypatch, tmp_path):
     assert obj1.item() == obj2.item() and s1.step == s2.step == 9
     for a, b in zip(m1.pc_wrapper.parameters(), m2.pc_wrapper.parameters()):
         assert torch.equal(a, b)                                       # same Adam moments -> the same second update
+
+
+def _inpaint_dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    import generative_audio_b200 as g
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    _cpu_kernel_stubs(None)
+    gd = load_golden("inpaint_model_b2")
+    gen = torch.Generator().manual_seed(5)
+    batches = []
+    for r in range(world):                                   # rank r trains on its own batch: the golden one, perturbed
+        clean = gd["clean_spec"] + 0.3 * r * torch.randn(gd["clean_spec"].shape, generator=gen)
+        batches.append((clean * gd["mask"][:, None, None, :], gd["mask"], clean))
+
+    def grads_of(batch):
+        m = _cpu_product_model()
+        m.pc_wrapper.train()
+        st = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+        st.step = 600
+        with torch.enable_grad():
+            _, obj, _ = st.base_step(batch, requires_grad=True)
+            obj.backward()
+        return [p.grad.clone() for p in m.pc_wrapper.parameters()]
+
+    ref = None
+    if rank == 0:                                            # single-process reference: mean of the per-rank gradients
+        per = [grads_of(b) for b in batches]
+        ref = [sum(gs) / world for gs in zip(*per)]
+    m = _cpu_product_model()
+    st = g.inpainting.InpaintingNPPCStep(m, 1.0, 500, max_grad_norm=1e9)      # no clipping: compare raw averaged gradients
+    st.step = 600
+    opt = torch.optim.SGD(m.pc_wrapper.parameters(), lr=0.0)
+    with torch.enable_grad():
+        _, log = st.train_step(batches[rank], opt)
+    if rank == 0:
+        errs = [((p.grad - r_).abs().max() / r_.abs().max().clamp_min(1e-12)).item() for p, r_ in zip(m.pc_wrapper.parameters(), ref)
+                if r_.abs().max() > 1e-6]
+        ret["max_err"], ret["buckets"] = max(errs), len(st._reducer.buckets)
+        ret["norm_ok"] = abs(log["grad_norm"].item() - torch.sqrt(sum((r_ ** 2).sum() for r_ in ref)).item()) < 1e-4 * log["grad_norm"].item()
+    dist.destroy_process_group()
+
+
+def test_inpainting_train_step_data_parallel_world2():
+    """InpaintingNPPCStep.train_step under torch.distributed (gloo, 2 ranks, kernels stubbed on CPU): the head's gradients
+    after the overlapped bucket all-reduce are the mean of the per-rank gradients, and the clip norm is taken after averaging."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_inpaint_dp_worker, args=(2, 29671, ret), nprocs=2, join=True)
+    assert ret["buckets"] >= 2 and ret["max_err"] < 1e-5 and ret["norm_ok"]
