@@ -322,8 +322,11 @@ class GradBucketReducer:
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
         if self._pending[i] == 0 and self._active():
-            flat = torch.cat([q.grad.reshape(-1) for q in self.buckets[i]])
-            self._work.append((i, flat, dist.all_reduce(flat, async_op=True)))
+            self._launch(i, self.buckets[i])
+
+    def _launch(self, i, members):
+        flat = torch.cat([q.grad.reshape(-1) for q in members])
+        self._work.append((i, members, flat, dist.all_reduce(flat, async_op=True)))
 
     def finish(self) -> int:
         """Wait for the in-flight buckets (and exchange any whose hook never fired), write the averaged gradients back."""
@@ -331,17 +334,21 @@ class GradBucketReducer:
             self.reset()
             return 0
         world = dist.get_world_size()
-        done = {i for i, _, _ in self._work}
+        done = {i for i, _, _, _ in self._work}
         for i, b in enumerate(self.buckets):
-            if i not in done and all(q.grad is not None for q in b):
-                flat = torch.cat([q.grad.reshape(-1) for q in b])
-                self._work.append((i, flat, dist.all_reduce(flat, async_op=True)))
+            if i not in done:
+                # a bucket whose count-down never finished holds parameters this step's graph did not reach: exchange the ones
+                # that do have a gradient (every rank runs the same graph, so every rank picks the same members) instead of
+                # silently leaving the whole bucket un-averaged
+                members = [q for q in b if q.grad is not None]
+                if members:
+                    self._launch(i, members)
         n = len(self._work)
-        for i, flat, work in self._work:
+        for i, members, flat, work in self._work:
             work.wait()
             flat.div_(world)
             off = 0
-            for q in self.buckets[i]:
+            for q in members:
                 q.grad.copy_(flat[off:off + q.numel()].view_as(q.grad))
                 off += q.numel()
         self.reset()

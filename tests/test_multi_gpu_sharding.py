@@ -93,7 +93,7 @@ def _reducer_worker(rank, world, port, ret):
         net(xs[r]).pow(2).mean().backward()
         g = [p.grad.clone() for p in net.parameters()]
         ref = g if ref is None else [a + b for a, b in zip(ref, g)]
-        for _, _, w in red._work:
+        for _, _, _, w in red._work:
             w.wait()
     ref = [g / world for g in ref]
     dist.barrier()
@@ -103,8 +103,20 @@ def _reducer_worker(rank, world, port, ret):
     launched_in_backward = len(red._work)
     n = red.finish()
     ok = all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(net.parameters(), ref))
+    # a parameter the graph never reaches shares a bucket with live ones: its bucket's count-down never finishes, and finish()
+    # must still average the members that have a gradient (it used to skip such a bucket silently)
+    red.remove()
+    unused = torch.nn.Parameter(torch.zeros(7))
+    red2 = GradBucketReducer(list(net.parameters()) + [unused], bucket_bytes=1 << 30)       # ONE bucket
+    net.zero_grad(set_to_none=True)
+    red2.reset()
+    net(xs[rank]).pow(2).mean().backward()
+    early2 = len(red2._work)
+    n2 = red2.finish()
+    ok2 = early2 == 0 and n2 == 1 and unused.grad is None and \
+        all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(net.parameters(), ref))
     if rank == 0:
-        ret["ok"], ret["n"], ret["early"], ret["buckets"] = ok, n, launched_in_backward, len(red.buckets)
+        ret["ok"], ret["n"], ret["early"], ret["buckets"], ret["ok_unused"] = ok, n, launched_in_backward, len(red.buckets), ok2
     dist.destroy_process_group()
 
 
@@ -115,3 +127,4 @@ def test_dp_bucket_reducer_overlaps_backward_world2():
     ret = mgr.dict()
     mp.spawn(_reducer_worker, args=(2, 29651, ret), nprocs=2, join=True)
     assert ret["ok"] and ret["buckets"] >= 2 and ret["n"] == ret["buckets"] and ret["early"] == ret["buckets"]
+    assert ret["ok_unused"]
