@@ -353,12 +353,19 @@ def gs_loss_fused_real_with_gram(head: torch.Tensor, gt: torch.Tensor, pred: tor
                                                    w.data_ptr(), err_norm.data_ptr(), err_proj.data_ptr(),
                                                    w_norms.data_ptr(), reconst.data_ptr(), sm.data_ptr(), _stream()),
                "nppc_gs_loss_fused_real")
+    G, A = _decode_gs_scratch_real(scr, B, n, n + 1)
+    return w, dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm), G, A
+
+
+def _decode_gs_scratch_real(scr: torch.Tensor, B: int, n: int, nv: int):
+    """SampleScratch of the REAL kernels (the .re slots of the complex layout) -> (symmetric Gram matrix [B,nv,nv] float64 of the
+    nv vectors of the Gram pass, coefficient matrix A [B,n,n] float32 with w = A x)."""
     scr = scr[:B * GS_SCRATCH_BYTES].reshape(B, GS_SCRATCH_BYTES)
-    Gu = scr[:, :13 * 13 * 16].contiguous().view(torch.float64).reshape(B, 13, 13, 2)[:, :n + 1, :n + 1, 0]
+    Gu = scr[:, :13 * 13 * 16].contiguous().view(torch.float64).reshape(B, 13, 13, 2)[:, :nv, :nv, 0]
     up = torch.triu(Gu, diagonal=1)
     G = torch.diag_embed(torch.diagonal(Gu, dim1=1, dim2=2)) + up + up.transpose(1, 2)
     A = scr[:, 13 * 13 * 16:].contiguous().view(torch.float32).reshape(B, 12, 12, 2)[:, :n, :n, 0].contiguous()
-    return w, dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst, second_moment_mse=sm), G, A
+    return G, A
 
 
 def real_lincomb(x: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor, coef: torch.Tensor):

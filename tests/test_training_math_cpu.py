@@ -256,3 +256,43 @@ def test_differentiable_gram_schmidt_function_glue_on_cpu(monkeypatch):
     assert ((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-6       # A rides in complex64, as on the device
     with pytest.raises(NotImplementedError):
         training.GramSchmidtFn.apply(torch.zeros(1, 7, 2, 4, 4))
+
+
+def test_gram_schmidt_scratch_decoders_follow_the_struct_layout():
+    """ops._decode_gs_scratch(_real): the backward reads the Gram and coefficient matrices out of the forward kernel's scratch,
+    `struct SampleScratch { double G[13*13*2]; float A[12*12*2]; }` per sample (csrc/gram_schmidt.cu: G row-major complex,
+    UPPER triangle only, entry (j,k) at (j*13+k)*2 + {re,im}; A row i = direction i at (i*12+k)*2 + {re,im}).  A scratch buffer
+    packed here with numpy in exactly that layout must come back as the full Hermitian / symmetric matrices."""
+    import numpy as np
+
+    import generative_audio_b200 as G_
+    ops = G_.ops
+    B, n = 3, 5
+    rng = np.random.default_rng(0)
+    assert ops.GS_SCRATCH_BYTES == 13 * 13 * 2 * 8 + 12 * 12 * 2 * 4
+    for real in (False, True):
+        nv = n + 1 if real else n
+        M = rng.standard_normal((B, nv, nv)) + (0 if real else 1j) * rng.standard_normal((B, nv, nv))
+        H = M + np.conj(np.transpose(M, (0, 2, 1)))                      # Hermitian (symmetric when real)
+        A = np.tril(rng.standard_normal((B, n, n)) + (0 if real else 1j) * rng.standard_normal((B, n, n)))
+        buf = np.zeros((B + 2, ops.GS_SCRATCH_BYTES), dtype=np.uint8)    # + trailing bytes, as nppc_gs_scratch_bytes over-allocates
+        for b in range(B):
+            Gs = np.full((13, 13, 2), 777.0)                             # garbage where the kernel never writes ...
+            As = np.full((12, 12, 2), 555.0, dtype=np.float32)
+            for j in range(nv):
+                for k in range(j, nv):                                   # ... the upper triangle is all it fills
+                    Gs[j, k] = (H[b, j, k].real, H[b, j, k].imag)
+            Gs[np.arange(nv), np.arange(nv), 1] = 1e-9                   # rounding dust in Im of the diagonal must be dropped
+            As[:n, :n, 0], As[:n, :n, 1] = A[b].real, A[b].imag
+            buf[b, :13 * 13 * 16] = np.frombuffer(Gs.tobytes(), dtype=np.uint8)
+            buf[b, 13 * 13 * 16:] = np.frombuffer(As.tobytes(), dtype=np.uint8)
+        scr = torch.from_numpy(buf.reshape(-1))
+        if real:
+            Gd, Ad = ops._decode_gs_scratch_real(scr, B, n, nv)
+            assert Gd.dtype == torch.float64 and Ad.dtype == torch.float32
+        else:
+            Gd, Ad = ops._decode_gs_scratch(scr, B, n)
+            assert Gd.dtype == torch.complex128 and Ad.dtype == torch.complex64
+            H = H - 1j * np.imag(H) * np.eye(nv)[None]
+        assert np.allclose(Gd.numpy(), H, atol=1e-12)
+        assert np.allclose(Ad.numpy(), A.astype(np.complex64 if not real else np.float32), atol=1e-6)
