@@ -88,3 +88,25 @@ def gs_grad_coeffs(G2: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
             v = v - a[:, j] * s.conj()[:, None]
         out[:, i] = v
     return out
+
+
+def gs_coeffs_from_gram(G: torch.Tensor, n: int) -> torch.Tensor:
+    """The coefficient matrix A [B, n, n] of Gram-Schmidt (w_i = sum_k A_ik x_k) replayed from the Gram matrix G [B, >=n, >=n]
+    of the inputs alone, in G's precision (fp64): the same recurrences the kernel's solve runs (conjugated coefficient,
+    normaliser without epsilon), so the backward need not go through the fp32 copy of A the forward leaves in its scratch."""
+    B = G.shape[0]
+    Gx = G[:, :n, :n]
+    A = torch.zeros(B, n, n, dtype=G.dtype, device=G.device)
+    ahat, v = [], []
+    for i in range(n):
+        a = torch.zeros(B, n, dtype=G.dtype, device=G.device)
+        a[:, i] = 1
+        for j in range(i):
+            c = torch.einsum("bk,bk->b", a.conj(), v[j])              # sum_p conj(w[p]) what_j[p]
+            a = a - ahat[j] * c[:, None]
+        nrm = torch.einsum("bk,bkl,bl->b", a.conj(), Gx, a).real.clamp_min(0).sqrt()
+        A[:, i] = a
+        ah = a / nrm[:, None].to(G.dtype)
+        ahat.append(ah)
+        v.append(torch.einsum("bkl,bl->bk", Gx, ah))
+    return A

@@ -17,7 +17,7 @@ What runs where:
 import torch
 
 from . import ops
-from .gs_backward import gs_loss_grad_coeffs
+from .gs_backward import gs_coeffs_from_gram, gs_loss_grad_coeffs
 
 
 class MaskOutFn(torch.autograd.Function):
@@ -42,18 +42,19 @@ class GsLossRealFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, head, gt, pred, lam):
-        w, st, G, A = ops.gs_loss_fused_real_with_gram(head, gt, pred)
+        w, st, G, _ = ops.gs_loss_fused_real_with_gram(head, gt, pred)
         lam = torch.as_tensor(lam, dtype=torch.float64, device=head.device)
         objective = st["reconst_err"].mean() + (lam * st["second_moment_mse"].double().mean()).float()
-        ctx.save_for_backward(head, gt, pred, G, A, lam)
+        ctx.save_for_backward(head, gt, pred, G, lam)
         outs = (w, st["err_norm"], st["err_proj"], st["w_norms"], st["reconst_err"], st["second_moment_mse"])
         ctx.mark_non_differentiable(*outs)
         return (objective, *outs)
 
     @staticmethod
     def backward(ctx, g_obj, *unused):
-        head, gt, pred, G, A, lam = ctx.saved_tensors
-        coef = gs_loss_grad_coeffs(G, A.double(), lam, real=True) * g_obj.double()
+        head, gt, pred, G, lam = ctx.saved_tensors
+        A = gs_coeffs_from_gram(G, head.shape[1])        # fp64 replay from the fp64 Gram matrix (the scratch holds A in fp32 only)
+        coef = gs_loss_grad_coeffs(G, A, lam, real=True) * g_obj.double()
         return ops.real_lincomb(head, gt, pred, coef), None, None, None
 
 

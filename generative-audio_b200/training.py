@@ -24,7 +24,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
-from .gs_backward import gs_grad_coeffs, gs_loss_grad_coeffs
+from .gs_backward import gs_coeffs_from_gram, gs_grad_coeffs, gs_loss_grad_coeffs
 from .modules import TCN_DILATIONS, TCNBlock
 
 
@@ -241,16 +241,16 @@ class GramSchmidtFn(torch.autograd.Function):
         n = head.shape[1]
         if n > 6:
             raise NotImplementedError("differentiable Gram-Schmidt: n_dirs <= 6 (the backward stacks 2 n vectors; kernels take 12)")
-        w, _, A = ops.gram_schmidt_complex_with_coeffs(head)
-        ctx.save_for_backward(head, A)
-        return w
+        ctx.save_for_backward(head)
+        return ops.gram_schmidt_complex(head)
 
     @staticmethod
     def backward(ctx, g):
-        head, A = ctx.saved_tensors
+        (head,) = ctx.saved_tensors
         B, n = head.shape[:2]
         S = torch.cat([head, g.to(head.dtype)], dim=1).contiguous()           # [B, 2n, 2, F', T]
-        coef = gs_grad_coeffs(ops.gram_matrix_complex(S), A.to(torch.complex128))       # [B, n, 2n]
+        G2 = ops.gram_matrix_complex(S)                                        # fp64 Gram pass over (x; g); its top-left block is G_x
+        coef = gs_grad_coeffs(G2, gs_coeffs_from_gram(G2, n))                  # w = A x replayed in fp64 from G_x; C [B, n, 2n]
         full = torch.zeros(B, 2 * n, 2 * n + 1, dtype=coef.dtype, device=coef.device)   # rows n..2n-1 and the error column stay 0
         full[:, :n, :2 * n] = coef
         zero = torch.zeros(B, *head.shape[2:], device=head.device, dtype=head.dtype)

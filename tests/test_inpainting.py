@@ -475,3 +475,48 @@ def test_inpainting_train_step_data_parallel_world2():
     ret = mgr.dict()
     mp.spawn(_inpaint_dp_worker, args=(2, 29671, ret), nprocs=2, join=True)
     assert ret["buckets"] >= 2 and ret["max_err"] < 1e-5 and ret["norm_ok"]
+
+
+@pytest.mark.parametrize("step", [0, 600])
+def test_inpainting_train_step_through_the_real_ops_wrappers_on_an_emulated_cabi(monkeypatch, step):
+    """Same training step as the rehearsal above, but through the product's REAL ops.py wrappers: only the shared library
+    is replaced, by tests/cabi_emulator.py (numpy on host memory, written from the contract in include/nppc_b200.h).  Covers
+    what the rehearsal's stubs skipped — pointer / size marshalling, the SampleScratch decode of gs_loss_fused_real_with_gram,
+    real_lincomb riding on nppc_complex_lincomb's two planes, the mask kernel in forward and backward."""
+    import cabi_emulator
+    import generative_audio_b200 as g
+    lib = cabi_emulator.install(monkeypatch)
+    gd, gg = load_golden("inpaint_model_b2"), load_golden("inpaint_step_b2_grads")
+    batch = (gd["masked_spec"], gd["mask"], gd["clean_spec"])
+    m = _cpu_product_model()
+    # inference path first (eval head): preprocess, restoration, head, real Gram-Schmidt, fused loss statistics
+    clean_n, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"], gd["masked_spec"], gd["mask"])
+    assert rel_err(clean_n, gd["clean_n"]) < 1e-5 and rel_err(masked_n, gd["masked_n"]) < 1e-5
+    assert rel_err(m(masked_n, m4), gd["w_mat"]) < 1e-3
+    st0 = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+    st0.step = step
+    _, obj0, log0 = st0.base_step(batch)
+    assert abs(obj0.item() - gd[f"s{step}_objective"].item()) < 2e-3 * abs(gd[f"s{step}_objective"].item()) if f"s{step}_objective" in gd else True
+    for k in ("err_norm", "err_proj", "w_norms", "reconst_err", "second_moment_mse"):
+        if f"s{step}_{k}" in gd:
+            assert rel_err(log0[k], gd[f"s{step}_{k}"]) < 2e-3, k
+    # training step: gradients before clipping, then the whole iteration on a fresh model
+    m.pc_wrapper.train()
+    with torch.enable_grad():
+        reconst, objective, _ = st0.base_step(batch, requires_grad=True)
+        objective.backward()
+    before = {k: p.grad.detach().clone() for k, p in m.pc_wrapper.net.named_parameters()}
+    m2 = _cpu_product_model()
+    st2 = g.inpainting.InpaintingNPPCStep(m2, 1.0, 500, max_grad_norm=1.0)
+    st2.step = step
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    lib.calls.clear()
+    with torch.enable_grad():
+        obj2, log2 = st2.train_step(batch, opt)
+    # 5e-3: fp32 pre-processing, fp32 coefficient matrices out of the scratch and the fp32 linear combination put ~3e-5 of
+    # noise on the head's output gradient, which the train-mode BatchNorm over the 2 x 3 bottleneck pixels of this tiny fixture
+    # amplifies ~100 x (measured 2.7e-3 on inc.conv.conv.0.weight); the GPU test allows 2e-2
+    _check_step_against_reference(m2.pc_wrapper.net, gg, step, obj2.item(), log2["grad_norm"].item(), before, 5e-3)
+    assert lib.calls == ["nppc_logmag_stats", "nppc_logmag_apply", "nppc_logmag_apply", "nppc_mask_blend",      # frozen half
+                         "nppc_mask_blend", "nppc_gs_loss_fused_real",                                         # head forward
+                         "nppc_complex_lincomb", "nppc_mask_blend"]                                            # backward

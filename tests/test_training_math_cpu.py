@@ -239,7 +239,7 @@ def test_differentiable_gram_schmidt_function_glue_on_cpu(monkeypatch):
         d = torch.einsum("bik,bkp->bip", coef.to(torch.complex128), torch.cat([cplx(x), e[:, None]], 1))
         return torch.stack([d.real, d.imag], 2).reshape(x.shape).to(x.dtype)
 
-    monkeypatch.setattr(ops, "gram_schmidt_complex_with_coeffs", with_coeffs)
+    monkeypatch.setattr(ops, "gram_schmidt_complex", lambda x: with_coeffs(x)[0])
     monkeypatch.setattr(ops, "gram_matrix_complex", lambda v: with_coeffs(v)[1])
     monkeypatch.setattr(ops, "complex_lincomb", lincomb)
     g = torch.Generator().manual_seed(11)
@@ -253,7 +253,7 @@ def test_differentiable_gram_schmidt_function_glue_on_cpu(monkeypatch):
         wr = _gs_ref(b.flatten(3)).view_as(b)
         ((wr - tgt) ** 2).sum().backward()
     assert ((w.detach() - wr.detach()).abs().max() / wr.abs().max()).item() < 1e-12
-    assert ((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-6       # A rides in complex64, as on the device
+    assert ((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-9       # coefficients replayed in fp64 from the Gram matrix
     with pytest.raises(NotImplementedError):
         training.GramSchmidtFn.apply(torch.zeros(1, 7, 2, 4, 4))
 
@@ -296,3 +296,26 @@ def test_gram_schmidt_scratch_decoders_follow_the_struct_layout():
             H = H - 1j * np.imag(H) * np.eye(nv)[None]
         assert np.allclose(Gd.numpy(), H, atol=1e-12)
         assert np.allclose(Ad.numpy(), A.astype(np.complex64 if not real else np.float32), atol=1e-6)
+
+
+def test_differentiable_gram_schmidt_through_the_real_ops_wrappers_on_an_emulated_cabi(monkeypatch):
+    """training.GramSchmidtFn through the product's real ops wrappers (gram_schmidt_complex_with_coeffs, gram_matrix_complex,
+    complex_lincomb) with only the shared library replaced by tests/cabi_emulator.py: marshalling + scratch decode + the
+    stacked [x; g] Gram pass + the padded coefficient matrix, against autograd of the reference's Gram-Schmidt."""
+    import cabi_emulator
+    from generative_audio_b200 import training
+    lib = cabi_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 5, 2, 6, 10, generator=g)
+    tgt = torch.randn(2, 5, 2, 6, 10, generator=g)
+    with torch.enable_grad():
+        a = x.clone().requires_grad_(True)
+        w = training.GramSchmidtFn.apply(a)
+        ((w - tgt) ** 2).sum().backward()
+        b = x.double().requires_grad_(True)
+        wr = _gs_ref(b.flatten(3)).view_as(b)
+        ((wr - tgt.double()) ** 2).sum().backward()
+    assert lib.calls == ["nppc_gram_schmidt_complex", "nppc_gram_schmidt_complex", "nppc_complex_lincomb"]
+    assert ((w.detach().double() - wr.detach()).abs().max() / wr.abs().max()).item() < 1e-5
+    assert torch.equal(w.detach()[:, 0], x[:, 0])
+    assert ((a.grad.double() - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-4
