@@ -210,7 +210,11 @@ class RestorationWrapper(nn.Module):
 
 
 def gram_schmidt_to_spec_mag(x: torch.Tensor) -> torch.Tensor:
-    """inpainting/nppc/pc_wrapper.py:43-59: real MGS over [B, n_dirs, F*T]; un-normalised directions are returned."""
+    """inpainting/nppc/pc_wrapper.py:43-59: real MGS over [B, n_dirs, F*T]; un-normalised directions are returned.
+    Differentiable like the reference's when x carries a graph (inpainting_training.GramSchmidtRealFn, n_dirs <= 6)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        from .inpainting_training import GramSchmidtRealFn
+        return GramSchmidtRealFn.apply(x)
     return ops.gram_schmidt_real(x)
 
 
@@ -229,7 +233,11 @@ class AudioInpaintingPCWrapper(nn.Module):
         self.net = UNet(self.config.model_configuration)
 
     def head(self, mag_spec: torch.Tensor, mask: torch.Tensor):
-        return ops.mask_blend(None, self.net(mag_spec), mask)
+        y = self.net(mag_spec)
+        if torch.is_grad_enabled() and y.requires_grad:      # keep the graph (train-mode head): masking kernel as an autograd Function
+            from .inpainting_training import MaskOutFn
+            return MaskOutFn.apply(y, mask)
+        return ops.mask_blend(None, y, mask)
 
     def forward(self, mag_spec: torch.Tensor, mask: torch.Tensor):
         return gram_schmidt_to_spec_mag(self.head(mag_spec, mask))
@@ -267,11 +275,20 @@ class NPPCModel(nn.Module):
         with torch.no_grad():
             return self.pretrained_restoration_model(masked_spec_mag_log, mask)
 
+    # Opt-in, as for the audio model: with `model.differentiable_forward = True` and grad mode on, forward() keeps the autograd
+    # graph through the PC head (UNet through torch autograd, masking and real Gram-Schmidt as autograd Functions over the
+    # kernels; n_dirs <= 6), so the reference trainer's own `w_mat = self.nppc_model(x, mask)`; loss; `.backward()`
+    # (nppc_trainer.py:347-373) works unchanged.  InpaintingNPPCStep.train_step is the faster way (fused Gram-Schmidt + loss).
+    differentiable_forward = False
+
     def forward(self, masked_spec_mag_norm: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         """masked_spec_mag_norm, mask [B,1,F,T] -> w_mat [B,n_dirs,F,T] (nppc_model.py:119-145)."""
         pred = self.get_pred_spec_mag_norm(masked_spec_mag_norm, mask)
+        x = torch.cat((masked_spec_mag_norm, pred), dim=1)
+        if self.differentiable_forward and torch.is_grad_enabled():
+            return self.pc_wrapper(x, mask)
         with torch.no_grad():
-            return self.pc_wrapper(torch.cat((masked_spec_mag_norm, pred), dim=1), mask)
+            return self.pc_wrapper(x, mask)
 
 
 def preprocess_data(clean_spec: torch.Tensor, masked_spec: torch.Tensor, mask: torch.Tensor):

@@ -17,7 +17,7 @@ What runs where:
 import torch
 
 from . import ops
-from .gs_backward import gs_coeffs_from_gram, gs_loss_grad_coeffs
+from .gs_backward import gs_coeffs_from_gram, gs_grad_coeffs, gs_loss_grad_coeffs
 
 
 class MaskOutFn(torch.autograd.Function):
@@ -56,6 +56,31 @@ class GsLossRealFn(torch.autograd.Function):
         A = gs_coeffs_from_gram(G, head.shape[1])        # fp64 replay from the fp64 Gram matrix (the scratch holds A in fp32 only)
         coef = gs_loss_grad_coeffs(G, A, lam, real=True) * g_obj.double()
         return ops.real_lincomb(head, gt, pred, coef), None, None, None
+
+
+class GramSchmidtRealFn(torch.autograd.Function):
+    """gram_schmidt_to_spec_mag (inpainting/nppc/pc_wrapper.py:43-59) with a backward for an ARBITRARY upstream gradient (a loss
+    written in torch by the caller, as the reference trainer does): x [B, n, F, T] -> w_mat, n <= 6.  Same construction as
+    training.GramSchmidtFn on real numbers: one Gram pass over the stacked (x; g), gs_grad_coeffs, one linear combination."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if x.shape[1] > 6:
+            raise NotImplementedError("differentiable Gram-Schmidt: n_dirs <= 6 (the backward stacks 2 n vectors; kernels take 12)")
+        ctx.save_for_backward(x)
+        return ops.gram_schmidt_real(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        B, n = x.shape[:2]
+        S = torch.cat([x, g.to(x.dtype)], dim=1).contiguous()
+        G2 = ops.gram_matrix_real(S)
+        coef = gs_grad_coeffs(G2, gs_coeffs_from_gram(G2, n))
+        full = torch.zeros(B, 2 * n, 2 * n + 1, dtype=coef.dtype, device=coef.device)
+        full[:, :n, :2 * n] = coef
+        zero = torch.zeros(B, *x.shape[2:], device=x.device, dtype=x.dtype)
+        return ops.real_lincomb(S, zero, zero, full)[:, :n].contiguous()
 
 
 def head_forward_train(pc_wrapper, mag_spec: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

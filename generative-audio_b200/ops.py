@@ -368,6 +368,21 @@ def _decode_gs_scratch_real(scr: torch.Tensor, B: int, n: int, nv: int):
     return G, A
 
 
+def gram_matrix_real(v: torch.Tensor):
+    """Symmetric Gram matrix G [B,m,m] float64 of m <= 12 real vectors v [B,m,...]: the fp64 Gram pass of the real Gram-Schmidt
+    kernel (one read of v), taken from the scratch of a nppc_gram_schmidt_real call whose output is discarded."""
+    v = _f32(v)
+    _chk(v)
+    B, m = v.shape[:2]
+    P = v[0, 0].numel()
+    out = torch.empty_like(v)
+    scr = _gs_scratch(B, m, v.device)
+    assert scr.numel() >= B * GS_SCRATCH_BYTES
+    _lib.check(_lib.load().nppc_gram_schmidt_real(v.data_ptr(), B, m, P, scr.data_ptr(), out.data_ptr(), _stream()),
+               "nppc_gram_schmidt_real")
+    return _decode_gs_scratch_real(scr, B, m, m)[0]
+
+
 def real_lincomb(x: torch.Tensor, gt: torch.Tensor, pred: torch.Tensor, coef: torch.Tensor):
     """out[b,i] = sum_k coef[b,i,k] x[b,k] + coef[b,i,n] (gt - pred)[b] for REAL vectors: x [B,n,...], gt / pred [B,...],
     coef [B,n,n+1] real — the streaming pass of the inpainting head's Gram-Schmidt + loss backward.  Runs on

@@ -9,13 +9,19 @@ from .networks import MultiDirectionFullSubNet_Plus
 
 
 def gram_schmidt_to_crm(x: torch.Tensor) -> torch.Tensor:
-    """x [B, n_dirs, 2, F, T] -> orthogonalised (un-normalised) directions, same shape."""
+    """x [B, n_dirs, 2, F, T] -> orthogonalised (un-normalised) directions, same shape.  Differentiable like the reference's
+    (pc_wrapper.py:8-44, normalisers detached at :37) when x carries a graph: the kernels then run under
+    training.GramSchmidtFn (n_dirs <= 6) instead of silently dropping the gradient."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        from .training import GramSchmidtFn
+        return GramSchmidtFn.apply(x)
     return ops.gram_schmidt_complex(x)
 
 
 def gram_schmidt_to_spec_mag(x: torch.Tensor) -> torch.Tensor:
-    """x [B, n_dirs, F, T] real -> same shape."""
-    return ops.gram_schmidt_real(x)
+    """x [B, n_dirs, F, T] real -> same shape (graph-preserving: see inpainting.gram_schmidt_to_spec_mag)."""
+    from .inpainting import gram_schmidt_to_spec_mag as impl
+    return impl(x)
 
 
 class AudioPCWrapper(nn.Module):

@@ -509,7 +509,7 @@ def inpaint_loss(w_mat, clean, pred, *, step: int, grace: float, lambda0: float)
     w_norms = w_norms / err_norm[:, None]
     err_proj = torch.einsum("bki,bi->bk", w_hat, err)
     reconst_err = 1 - err_proj.pow(2).sum(dim=1)
-    second_moment_mse = (w_norms.pow(2) - err_proj.pow(2)).pow(2)
+    second_moment_mse = (w_norms.pow(2) - err_proj.detach().pow(2)).pow(2)      # the reference's stop-gradient, nppc_trainer.py:371
     lam = second_moment_lambda(step, grace, lambda0)
     objective = reconst_err.mean() + lam * second_moment_mse.mean()
     return dict(err_norm=err_norm, err_proj=err_proj, w_norms=w_norms, reconst_err=reconst_err,

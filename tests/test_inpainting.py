@@ -520,3 +520,33 @@ def test_inpainting_train_step_through_the_real_ops_wrappers_on_an_emulated_cabi
     assert lib.calls == ["nppc_logmag_stats", "nppc_logmag_apply", "nppc_logmag_apply", "nppc_mask_blend",      # frozen half
                          "nppc_mask_blend", "nppc_gs_loss_fused_real",                                         # head forward
                          "nppc_complex_lincomb", "nppc_mask_blend"]                                            # backward
+
+
+def test_reference_inpainting_trainer_pattern_through_differentiable_forward(monkeypatch):
+    """`model.differentiable_forward = True`: the reference trainer's own base_step pattern — w_mat = model(x, mask), the loss in
+    torch (nppc_trainer.py:347-373, restated by the oracle), backward — through the product model on the emulated C ABI,
+    against the unmodified reference's gradients (same fixture as the fused training step)."""
+    import cabi_emulator
+    import generative_audio_b200 as g
+    lib = cabi_emulator.install(monkeypatch)
+    gd, gg = load_golden("inpaint_model_b2"), load_golden("inpaint_step_b2_grads")
+    m = _cpu_product_model()
+    m.pc_wrapper.train()
+    clean_n, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"], gd["masked_spec"], gd["mask"])
+    with torch.enable_grad():
+        assert not m(masked_n, m4).requires_grad                      # default: the inference path, even with grad mode on
+        m.differentiable_forward = True
+        lib.calls.clear()
+        w = m(masked_n, m4)
+        assert w.requires_grad
+        pred = m.get_pred_spec_mag_norm(masked_n, m4)
+        st = O.inpaint_loss(w, clean_n, pred, step=600, grace=500, lambda0=1.0)
+        st["objective"].backward()
+    assert lib.calls == ["nppc_mask_blend", "nppc_mask_blend", "nppc_gram_schmidt_real",                    # forward
+                         "nppc_mask_blend",                                                                  # get_pred (2nd restoration pass)
+                         "nppc_gram_schmidt_real", "nppc_complex_lincomb", "nppc_mask_blend"]                # backward
+    assert abs(st["objective"].item() - gg["s600_objective"].item()) < 2e-3 * abs(gg["s600_objective"].item())
+    params = dict(m.pc_wrapper.net.named_parameters())
+    for k, s in PICKS.items():
+        assert rel_err(params[k].grad.flatten()[::s], gg[f"s600_grad_{k}"]) < 5e-3, k
+    assert all(p.grad is None for p in m.pretrained_restoration_model.parameters())

@@ -319,3 +319,47 @@ def test_differentiable_gram_schmidt_through_the_real_ops_wrappers_on_an_emulate
     assert ((w.detach().double() - wr.detach()).abs().max() / wr.abs().max()).item() < 1e-5
     assert torch.equal(w.detach()[:, 0], x[:, 0])
     assert ((a.grad.double() - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-4
+
+
+def test_gram_schmidt_to_crm_keeps_the_graph_when_its_input_has_one(monkeypatch):
+    """The reference's gram_schmidt_to_crm is differentiable; the drop-in must not silently return a graph-less tensor for an
+    input that requires grad (emulated C ABI; plain kernel path when no graph is involved)."""
+    import cabi_emulator
+    import generative_audio_b200 as G
+    lib = cabi_emulator.install(monkeypatch)
+    x = torch.randn(1, 3, 2, 4, 5, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        w0 = G.gram_schmidt_to_crm(x)
+    assert not w0.requires_grad and lib.calls == ["nppc_gram_schmidt_complex"]
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_(True)
+        w = G.gram_schmidt_to_crm(xr)
+        assert w.requires_grad and torch.equal(w.detach(), w0)
+        w.square().sum().backward()
+        assert xr.grad is not None and xr.grad.abs().max() > 0
+        with pytest.raises(NotImplementedError):
+            G.gram_schmidt_to_crm(torch.zeros(1, 7, 2, 4, 5, requires_grad=True))
+
+
+def test_real_gram_schmidt_keeps_the_graph_and_matches_autograd(monkeypatch):
+    """gram_schmidt_to_spec_mag (inpainting): differentiable for an arbitrary torch loss through GramSchmidtRealFn — real wrappers
+    on the emulated C ABI (Gram pass over the stacked [x; g] via nppc_gram_schmidt_real, linear combination on the two planes of
+    nppc_complex_lincomb) against autograd of the reference's real Gram-Schmidt."""
+    import cabi_emulator
+    import generative_audio_b200 as G
+    lib = cabi_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 5, 6, 10, generator=g)
+    tgt = torch.randn(2, 5, 6, 10, generator=g)
+    with torch.enable_grad():
+        a = x.clone().requires_grad_(True)
+        w = G.gram_schmidt_to_spec_mag(a)
+        ((w - tgt) ** 2).sum().backward()
+        b = x.double().requires_grad_(True)
+        wr = _gs_real_ref(b)
+        ((wr - tgt.double()) ** 2).sum().backward()
+    assert lib.calls == ["nppc_gram_schmidt_real", "nppc_gram_schmidt_real", "nppc_complex_lincomb"]
+    assert ((w.detach().double() - wr.detach()).abs().max() / wr.abs().max()).item() < 1e-5
+    assert ((a.grad.double() - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-4
+    with torch.no_grad():
+        assert not G.inpainting.gram_schmidt_to_spec_mag(x).requires_grad

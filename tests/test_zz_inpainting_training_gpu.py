@@ -53,3 +53,28 @@ def test_inpainting_training_step_vs_reference_gradients(step):
     with torch.no_grad():
         _, obj3, _ = stepper.base_step(_batch(gd))
     assert abs(obj3.item() - objective.item()) < 1e-4 * abs(objective.item())
+
+
+def test_reference_trainer_pattern_through_differentiable_forward():
+    """`model.differentiable_forward = True`: w_mat = model(x, mask) keeps the graph (UNet autograd, MaskOutFn, GramSchmidtRealFn);
+    the reference trainer's loss written in torch (oracle restatement, on the device) and backward reproduce its gradients."""
+    import generative_audio_b200 as g
+    import nppc_oracle as O
+    from test_inpainting import PICKS
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gd, gg = load_golden("inpaint_model_b2"), load_golden("inpaint_step_b2_grads")
+    m = _product_model()
+    m.pc_wrapper.train()
+    clean_n, m4, masked_n = g.inpainting.preprocess_data(gd["clean_spec"].cuda(), gd["masked_spec"].cuda(), gd["mask"].cuda())
+    with torch.enable_grad():
+        assert not m(masked_n, m4).requires_grad
+        m.differentiable_forward = True
+        w = m(masked_n, m4)
+        assert w.requires_grad
+        st = O.inpaint_loss(w, clean_n, m.get_pred_spec_mag_norm(masked_n, m4), step=600, grace=500, lambda0=1.0)
+        st["objective"].backward()
+    assert abs(st["objective"].item() - gg["s600_objective"].item()) < 2e-3 * abs(gg["s600_objective"].item())
+    params = dict(m.pc_wrapper.net.named_parameters())
+    for k, s in PICKS.items():
+        assert rel_err(params[k].grad.flatten()[::s].cpu(), gg[f"s600_grad_{k}"]) < 2e-2, k
