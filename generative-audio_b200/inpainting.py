@@ -234,7 +234,8 @@ class AudioInpaintingPCWrapper(nn.Module):
 
     def head(self, mag_spec: torch.Tensor, mask: torch.Tensor):
         y = self.net(mag_spec)
-        if torch.is_grad_enabled() and y.requires_grad:      # keep the graph (train-mode head): masking kernel as an autograd Function
+        if self.training and torch.is_grad_enabled() and y.requires_grad:   # train-mode head: keep the graph (masking kernel as an
+            # autograd Function); an eval-mode head stays the graph-less inference path whatever the caller's grad mode is
             from .inpainting_training import MaskOutFn
             return MaskOutFn.apply(y, mask)
         return ops.mask_blend(None, y, mask)
