@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FAST = settings(max_examples=25, deadline=None)
+FAST = settings(max_examples=25, deadline=None, derandomize=True, database=None)   # same examples on every box
 
 
 def _randn(seed, *shape, dtype=torch.float64):
