@@ -4,8 +4,10 @@ CPU tensors' memory.  Purpose: run the product's REAL `ops.py` wrappers (pointer
 the autograd Functions above them without a GPU, so that code written while no GPU was available is exercised end to end
 against an independent restatement of what the kernels promise.  Never imported by the product; nothing here is timed.
 
-Emulated: nppc_mask_blend, nppc_logmag_stats / _apply, nppc_gram_schmidt_complex / _real, nppc_gs_loss_fused_real,
-nppc_complex_lincomb.  Host-only entry points (nppc_gs_scratch_bytes, nppc_last_error, ...) go to the real library."""
+EmulatedLib: nppc_mask_blend, nppc_logmag_stats / _apply, nppc_gram_schmidt_complex / _real, nppc_gs_loss_fused_real,
+nppc_complex_lincomb (numpy restatements incl. the scratch bytes).  EmulatedLibFull adds the STFT / iSTFT / cRM / cIRM / norm /
+unfold / drop_band / complex loss entry points, each delegating to the oracle function the header cites.  Host-only entry points
+(nppc_gs_scratch_bytes, ...) go to the real library."""
 import ctypes
 
 import numpy as np
@@ -29,7 +31,7 @@ def f64(ptr, count):
     return _arr(ptr, count, ctypes.c_double, np.float64)
 
 
-def _solve(G, n, nv, has_err, cplx, eps_add):
+def _solve(G, n, nv, has_err, cplx, eps_add, do_gs=True):
     """The coefficient-space MGS of gs_solve (reference recurrences incl. the conjugated coefficient) -> A [n,n], stats."""
     A = np.zeros((n, n), dtype=np.complex128)
     ahat, v = [], []
@@ -39,7 +41,7 @@ def _solve(G, n, nv, has_err, cplx, eps_add):
     for i in range(n):
         a = np.zeros(n, np.complex128)
         a[i] = 1.0
-        for j in range(i):
+        for j in range(i if do_gs else 0):
             c = np.sum(np.conj(a) * v[j])          # sum_p conj(w[p]) what_j[p] = sum_k conj(a[k]) (G ahat_j)[k]
             a = a - ahat[j] * c
         nrm = np.sqrt(max((np.conj(a) @ (G[:n, :n] @ a)).real, 0.0))
@@ -58,7 +60,7 @@ def _solve(G, n, nv, has_err, cplx, eps_add):
     return A, stats
 
 
-def _run_gs(x_ptr, gt_ptr, pred_ptr, B, n, P, scr_ptr, out_ptr, cplx, outs=None):
+def _run_gs(x_ptr, gt_ptr, pred_ptr, B, n, P, scr_ptr, out_ptr, cplx, outs=None, do_gs=True):
     comp = 2 if cplx else 1
     x = f32(x_ptr, B * n * comp * P).reshape(B, n, comp, P).astype(np.float64)
     has_err = bool(gt_ptr)
@@ -77,7 +79,7 @@ def _run_gs(x_ptr, gt_ptr, pred_ptr, B, n, P, scr_ptr, out_ptr, cplx, outs=None)
         for j in range(nv):
             for k in range(j, nv):                                             # the kernels fill the UPPER triangle only
                 Gs[j, k] = (G[j, k].real, G[j, k].imag)
-        A, st = _solve(G, n, nv, has_err, cplx, 1e-8 if cplx else 1e-6)
+        A, st = _solve(G, n, nv, has_err, cplx, 1e-8 if cplx else 1e-6, do_gs)
         As = np.zeros((NA, NA, 2), dtype=np.float32)
         As[:n, :n, 0], As[:n, :n, 1] = A.real, A.imag
         scr[b, :G_BYTES] = np.frombuffer(Gs.tobytes(), dtype=np.uint8)
@@ -179,3 +181,110 @@ def install(monkeypatch):
     monkeypatch.setattr(g.inpainting.UNet, "forward", g.inpainting.UNet._forward)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     return lib
+
+
+# ---- front / back end entry points, computed by the oracle (oracle/nppc_oracle.py) on views of the caller's memory -------------
+def _t(ptr, shape):
+    import torch
+    n = int(np.prod(shape))
+    return torch.from_numpy(f32(ptr, n).reshape(shape))
+
+
+class EmulatedLibFull(EmulatedLib):
+    """EmulatedLib + the elementwise / index / transform entry points of the hot path, each delegating to the oracle function
+    that the header names as its reference (`include/nppc_b200.h`).  Used by tests/test_ops_contract_cpu.py."""
+
+    def nppc_stft_mri(self, wave, B, L, n_fft, hop, mag, real, imag, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_stft_mri")
+        F, T = n_fft // 2 + 1, 1 + L // hop
+        m, r, i = O.stft_mri(_t(wave, (B, L)), n_fft, hop, n_fft)
+        _t(mag, (B, F, T))[:], _t(real, (B, F, T))[:], _t(imag, (B, F, T))[:] = m[:, 0], r[:, 0], i[:, 0]
+        return 0
+
+    def nppc_istft(self, real, imag, B, T, n_fft, hop, length, wave, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_istft")
+        F = n_fft // 2 + 1
+        _t(wave, (B, length))[:] = O.istft(_t(real, (B, F, T)), _t(imag, (B, F, T)), length, n_fft, hop)
+        return 0
+
+    def nppc_crm_decompress_apply(self, crm, real, imag, B, FT, conj, out_mag, out_real, out_imag, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_crm_decompress_apply")
+        m = O.decompress_cirm(_t(crm, (B, 2, FT)))
+        mag, er, ei = O.crm_apply(m[:, 0], m[:, 1], _t(real, (B, FT)), _t(imag, (B, FT)), bool(conj))
+        if out_mag:
+            _t(out_mag, (B, FT))[:] = mag
+        _t(out_real, (B, FT))[:], _t(out_imag, (B, FT))[:] = er, ei
+        return 0
+
+    def nppc_decompress_cirm(self, m, n, out, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_decompress_cirm")
+        _t(out, (n,))[:] = O.decompress_cirm(_t(m, (n,)))
+        return 0
+
+    def nppc_build_cirm(self, nr, ni, cr, ci, B, FT, gt, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_build_cirm")
+        g = O.build_cirm(*(_t(p, (B, FT)) for p in (nr, ni, cr, ci)))             # [B, FT, 2]
+        _t(gt, (B, 2, FT))[:] = g.permute(0, 2, 1)
+        return 0
+
+    def nppc_offline_laplace_norm(self, x, B, n, sums, y, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_offline_laplace_norm")
+        _t(y, (B, n))[:] = O.offline_laplace_norm(_t(x, (B, 1, 1, n)).clone())[:, 0, 0]
+        return 0
+
+    def nppc_pad_offline_laplace_norm(self, x, B, F, T, look_ahead, sums, y, stream):
+        import torch
+
+        import nppc_oracle as O
+        self.calls.append("nppc_pad_offline_laplace_norm")
+        xp = torch.nn.functional.pad(_t(x, (B, 1, F, T)), [0, look_ahead])
+        _t(y, (B, F, T + look_ahead))[:] = O.offline_laplace_norm(xp)[:, 0]
+        return 0
+
+    def nppc_cumulative_laplace_norm(self, x, BC, F, T, y, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_cumulative_laplace_norm")
+        _t(y, (BC, F, T))[:] = O.cumulative_laplace_norm(_t(x, (BC, 1, F, T)).clone())[:, 0]
+        return 0
+
+    def nppc_unfold(self, x, B, C, F, T, num_neighbor, out, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_unfold")
+        _t(out, (B, F, C, 2 * num_neighbor + 1, T))[:] = O.unfold(_t(x, (B, C, F, T)), num_neighbor)
+        return 0
+
+    def nppc_drop_band(self, x, B, C, F, T, groups, out, stream):
+        import nppc_oracle as O
+        self.calls.append("nppc_drop_band")
+        if not B > groups:                      # the library reports the reference's assertion (feature.py:263) as rc = -1
+            self._msg = f"Batch size = {B}, num_groups = {groups}. The batch size should larger than the num_groups."
+            return -1
+        G = max(groups, 1)
+        _t(out, (B, C, F // G, T))[:] = O.drop_band(_t(x, (B, C, F, T)), groups)
+        return 0
+
+    def nppc_last_error(self):
+        return getattr(self, "_msg", "").encode()
+
+    def nppc_gs_loss_fused(self, x, gt, pred, B, n, P, scratch, w_mat, err_norm, err_proj, w_norms, reconst, second, stream):
+        self.calls.append("nppc_gs_loss_fused")
+        return _run_gs(x, gt, pred, B, n, P, scratch, w_mat, True, (err_norm, err_proj, w_norms, reconst, second))
+
+    def nppc_projection_loss(self, x, gt, pred, B, n, P, scratch, err_norm, err_proj, w_norms, reconst, second, stream):
+        self.calls.append("nppc_projection_loss")
+        # an explicit w_mat: no orthogonalisation (A = identity); statistics only
+        return _run_gs(x, gt, pred, B, n, P, scratch, 0, True, (err_norm, err_proj, w_norms, reconst, second), do_gs=False)
+
+
+def install_full(monkeypatch):
+    lib = install(monkeypatch)
+    full = EmulatedLibFull(lib._real)
+    import generative_audio_b200 as g
+    monkeypatch.setattr(g._lib, "load", lambda: full)
+    return full
