@@ -160,3 +160,43 @@ def test_round_robin_shards_partition_the_job(n, world):
     sizes = [len(s) for s in shards]
     assert max(sizes) - min(sizes) <= 1
     assert all(i % world == r for r, s in enumerate(shards) for i in s)
+
+
+@settings(max_examples=15, deadline=None, derandomize=True, database=None)
+@given(B=st.integers(1, 3), n=st.integers(1, 6), P=st.integers(10, 40), lam=st.floats(1e-6, 1.0), real=st.booleans(),
+       seed=st.integers(0, 10**6))
+def test_coefficient_space_backward_matches_autograd_on_random_shapes(B, n, P, lam, real, seed):
+    """gs_backward: Gram-Schmidt (+ objective) backward from Gram matrices alone, complex and real, any (B, n, P, lambda):
+    (1) the fused objective's gradient, (2) the gradient for an arbitrary upstream, (3) the coefficient replay from G."""
+    from generative_audio_b200.gs_backward import gs_coeffs_from_gram, gs_grad_coeffs, gs_loss_grad_coeffs
+    from test_training_math_cpu import _gs_real_ref, _gs_ref, _loss_real_ref, _loss_ref
+    P = max(P, 2 * n + 3)
+    comp = 1 if real else 2
+    x = _randn(seed, B, n, comp, P)
+    gt, pred, up = _randn(seed + 1, B, comp, P), _randn(seed + 2, B, comp, P), _randn(seed + 3, B, n, comp, P)
+
+    def cvec(t, dim):                                        # (re, im) planes -> complex (or the single real plane)
+        return t.select(dim, 0) if real else torch.complex(t.select(dim, 0), t.select(dim, 1))
+
+    with torch.enable_grad():
+        a = x.clone().requires_grad_(True)
+        if real:
+            _loss_real_ref(_gs_real_ref(a), gt[:, None], pred[:, None], lam).backward()
+        else:
+            _loss_ref(_gs_ref(a), gt, pred, lam).backward()
+        b = x.clone().requires_grad_(True)
+        ((_gs_real_ref(b) if real else _gs_ref(b)) * up).sum().backward()
+    xv, e, gv = cvec(x, 2), cvec(gt - pred, 1), cvec(up, 2)
+    V = torch.cat([xv, e[:, None]], 1)
+    G = torch.einsum("bjp,bkp->bjk", V.conj(), V)
+    A = gs_coeffs_from_gram(G, n)
+    d1 = torch.einsum("bik,bkp->bip", gs_loss_grad_coeffs(G, A, lam, real=real), V)
+    V2 = torch.cat([xv, gv], 1)
+    G2 = torch.einsum("bjp,bkp->bjk", V2.conj(), V2)
+    d2 = torch.einsum("bik,bkp->bip", gs_grad_coeffs(G2, gs_coeffs_from_gram(G2, n)), V2)
+
+    def planes(d):
+        return d[:, :, None] if real else torch.stack([d.real, d.imag], 2)
+
+    assert ((planes(d1) - a.grad).abs().max() / a.grad.abs().max()).item() < 1e-7
+    assert ((planes(d2) - b.grad).abs().max() / b.grad.abs().max()).item() < 1e-7
