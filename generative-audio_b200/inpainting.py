@@ -367,6 +367,28 @@ class InpaintingNPPCStep(CheckpointMixin):
         self.step += 1
         return objective.detach(), log
 
+    @torch.no_grad()
+    def validate(self, batches):
+        """NPPCAudioInpaintingTrainer.validate (nppc_trainer.py:689-706): the whole model in eval mode, mean objective and mean
+        reconstruction error over an iterable of batches -> (avg_val_loss, avg_val_reconst_err) as device scalars (one host
+        read at the end instead of two per batch); the PC head goes back to train mode afterwards.
+        Deviation, on purpose: the reference ends with `self.nppc_model.train()`, which also flips the FROZEN restoration UNet
+        into train mode (dropout active, BatchNorm batch statistics) for every later training step; here it stays in eval."""
+        model = self.nppc_model
+        was_training = model.pc_wrapper.training
+        model.eval()
+        try:
+            losses, errs = [], []
+            for batch in batches:
+                reconst_err, objective, _ = self._base_step_kernels(batch)
+                losses.append(objective)
+                errs.append(reconst_err.mean())
+            if not losses:
+                raise ValueError("validate: no batches")
+            return torch.stack(losses).mean(), torch.stack(errs).mean()
+        finally:
+            model.pc_wrapper.train(was_training)
+
     def _base_step_kernels(self, batch):
         masked_spec, mask, clean_spec = batch
         clean, m, masked = preprocess_data(clean_spec.cuda(), masked_spec.cuda(), mask.cuda())

@@ -550,3 +550,25 @@ def test_reference_inpainting_trainer_pattern_through_differentiable_forward(mon
     for k, s in PICKS.items():
         assert rel_err(params[k].grad.flatten()[::s], gg[f"s600_grad_{k}"]) < 5e-3, k
     assert all(p.grad is None for p in m.pretrained_restoration_model.parameters())
+
+
+def test_inpainting_validate_matches_the_reference_statistics_and_restores_modes(monkeypatch):
+    """InpaintingNPPCStep.validate (nppc_trainer.py:689-706) on the emulated C ABI: eval-mode statistics equal the reference's
+    base_step fixture; the head returns to train mode, the frozen restoration UNet never leaves eval (the reference's
+    `self.nppc_model.train()` would flip it — deliberately not reproduced)."""
+    import cabi_emulator
+    import generative_audio_b200 as g
+    cabi_emulator.install(monkeypatch)
+    gd = load_golden("inpaint_model_b2")
+    batch = (gd["masked_spec"], gd["mask"], gd["clean_spec"])
+    m = _cpu_product_model()
+    m.pc_wrapper.train()
+    st = g.inpainting.InpaintingNPPCStep(m, 1.0, 500)
+    st.step = 300
+    loss, err = st.validate([batch, batch])
+    assert abs(loss.item() - gd["s300_objective"].item()) < 2e-3 * abs(gd["s300_objective"].item())
+    assert abs(err.item() - gd["s300_reconst_err"].mean().item()) < 2e-3
+    assert m.pc_wrapper.training and not m.pretrained_restoration_model.training and not any(
+        mod.training for mod in m.pretrained_restoration_model.modules())
+    with pytest.raises(ValueError):
+        st.validate([])
